@@ -1,0 +1,698 @@
+// C ABI of goldpolish_b200 (see include/goldpolish_b200.h for the reference mapping).
+// Host-side plumbing only: device buffers, staging copies, wave scheduling, kernel launches.
+#include "gp_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t need)
+  {
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = need + need / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, need); want = need; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template<typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+} // namespace
+
+struct gp_ctx {
+  gp_config cfg;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // pack, build, polish (start, stop)
+  std::string err;
+  gp_stats stats;
+  bool build_timed = false, polish_timed = false, pack_timed = false;
+
+  // read store
+  uint64_t n_reads = 0;
+  std::vector<uint32_t> h_read_len;
+  DevBuf d_ascii, d_ascii_off, d_pk, d_nm, d_read_boff, d_read_len;
+
+  // build
+  uint32_t n_batches = 0;      // batches of the current filter set
+  bool filters_ready = false;
+  bool build_staged = false;
+  uint32_t wave_batches = 0;
+  std::vector<uint32_t> wave_first, wave_count, wave_order_off;
+  DevBuf d_batch_entry_off, d_entries, d_bf_pool, d_cbf_pool, d_stream_order, d_next, d_counters;
+
+  // polish
+  uint32_t n_contigs = 0;
+  bool polish_staged = false, polish_done = false;
+  uint32_t grow = 0; // overflow retries enlarge the buffers
+  std::vector<uint64_t> h_in_off, h_cap_off, h_node_off;
+  std::vector<uint32_t> h_len, h_order, h_batch;
+  DevBuf d_input, d_in_off, d_buf0, d_buf1, d_cap_off, d_cur_len, d_which, d_dropped, d_nodes, d_node_off,
+    d_contig_batch, d_order, d_pnext, d_pcounters, d_error, d_out, d_out_off;
+};
+
+#define GP_FAIL(ctx, code, msg)                                                                              \
+  do {                                                                                                       \
+    (ctx)->err = (msg);                                                                                      \
+    return (code);                                                                                           \
+  } while (0)
+
+#define GP_CUDA(ctx, call)                                                                                   \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess) {                                                                                 \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                       \
+      cudaGetLastError();                                                                                    \
+      return e_ == cudaErrorMemoryAllocation ? GP_ERR_OOM : GP_ERR_CUDA;                                     \
+    }                                                                                                        \
+  } while (0)
+
+namespace {
+
+// small device helpers that do not belong to a hot kernel -------------------------------
+__global__ void scatter_contigs_kernel(const char* __restrict__ in, const uint64_t* __restrict__ in_off,
+                                       char* __restrict__ buf0, const uint64_t* __restrict__ cap_off,
+                                       uint32_t* __restrict__ cur_len, uint32_t n)
+{
+  for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+    const uint64_t a = in_off[c];
+    const uint32_t len = uint32_t(in_off[c + 1] - a);
+    char* dst = buf0 + cap_off[c];
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = in[a + i];
+    if (threadIdx.x == 0) cur_len[c] = len;
+  }
+}
+
+__global__ void gather_contigs_kernel(const char* __restrict__ buf0, const char* __restrict__ buf1,
+                                      const uint64_t* __restrict__ cap_off, const uint8_t* __restrict__ which,
+                                      const uint64_t* __restrict__ out_off, char* __restrict__ out, uint32_t n)
+{
+  for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+    const uint64_t o = out_off[c];
+    const uint32_t len = uint32_t(out_off[c + 1] - o);
+    const char* src = (which[c] ? buf1 : buf0) + cap_off[c];
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) out[o + i] = src[i];
+  }
+}
+
+int validate_config(const gp_config& c, std::string& why)
+{
+  if (c.nk == 0 || c.nk > GP_MAX_K_VALUES) { why = "nk must be 1..8"; return GP_ERR_ARG; }
+  for (uint32_t i = 0; i < c.nk; i++)
+    if (c.k[i] < 4 || c.k[i] > 32) { why = "k must be within 4..32"; return GP_ERR_ARG; }
+  if (c.max_insertions > 5) { why = "max_insertions must be <= 5"; return GP_ERR_ARG; }
+  if (c.max_deletions > 10) { why = "max_deletions must be <= 10"; return GP_ERR_ARG; }
+  if (c.mode < 0 || c.mode > 2) { why = "mode must be 0..2"; return GP_ERR_ARG; }
+  if (c.jump == 0) { why = "jump must be >= 1"; return GP_ERR_ARG; }
+  return GP_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void gp_default_config(gp_config* cfg)
+{
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = sizeof(gp_config);
+  cfg->device = 0;
+  cfg->nk = 4;
+  cfg->k[0] = 32; cfg->k[1] = 28; cfg->k[2] = 24; cfg->k[3] = 20; // scripts/goldpolish:189-190
+  cfg->max_insertions = 5; cfg->max_deletions = 5; cfg->mode = 1; cfg->mask = 1; // scripts/goldpolish-ntedit:27
+  cfg->missing_ratio = 0.5f; cfg->edit_ratio = 0.5f;
+  cfg->jump = 3; cfg->min_contig_len = 100; // ntedit.cpp:94,85
+  cfg->max_resident_batches = 0;
+}
+
+const char* gp_last_error(const gp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gp_ctx_create(const gp_config* cfg, gp_ctx** out)
+{
+  if (!cfg || !out) { g_create_error = "null argument"; return GP_ERR_ARG; }
+  *out = nullptr;
+  gp_config c;
+  gp_default_config(&c);
+  std::memcpy(&c, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(gp_config), sizeof(gp_config)));
+  c.struct_size = sizeof(gp_config);
+  std::string why;
+  if (int rc = validate_config(c, why)) { g_create_error = why; return rc; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                     "); goldpolish_b200 has no CPU path";
+    return GP_ERR_NO_DEVICE;
+  }
+  if (c.device < 0 || c.device >= ndev) { g_create_error = "device ordinal out of range"; return GP_ERR_ARG; }
+  if ((e = cudaSetDevice(c.device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return GP_ERR_CUDA; }
+  gp_ctx* ctx = new gp_ctx();
+  ctx->cfg = c;
+  std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, c.device);
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete ctx;
+    return GP_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  *out = ctx;
+  return GP_OK;
+}
+
+void gp_ctx_destroy(gp_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = { &ctx->d_ascii, &ctx->d_ascii_off, &ctx->d_pk, &ctx->d_nm, &ctx->d_read_boff, &ctx->d_read_len,
+                     &ctx->d_batch_entry_off, &ctx->d_entries, &ctx->d_bf_pool, &ctx->d_cbf_pool, &ctx->d_stream_order,
+                     &ctx->d_next, &ctx->d_counters, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
+                     &ctx->d_cap_off, &ctx->d_cur_len, &ctx->d_which, &ctx->d_dropped, &ctx->d_nodes, &ctx->d_node_off,
+                     &ctx->d_contig_batch, &ctx->d_order, &ctx->d_pnext, &ctx->d_pcounters, &ctx->d_error, &ctx->d_out,
+                     &ctx->d_out_off };
+  for (auto* b : bufs) b->release();
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int gp_ctx_set_stream(gp_ctx* ctx, void* cuda_stream)
+{
+  if (!ctx) return GP_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return GP_OK;
+}
+
+int gp_ctx_synchronize(gp_ctx* ctx)
+{
+  if (!ctx) return GP_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GP_OK;
+}
+
+int gp_get_stats(const gp_ctx* cctx, gp_stats* out)
+{
+  if (!cctx || !out) return GP_ERR_ARG;
+  gp_ctx* ctx = const_cast<gp_ctx*>(cctx);
+  cudaSetDevice(ctx->cfg.device);
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->pack_timed) cudaEventElapsedTime(&ctx->stats.pack_ms, ctx->ev[0], ctx->ev[1]);
+  if (ctx->build_timed) {
+    cudaEventElapsedTime(&ctx->stats.build_ms, ctx->ev[2], ctx->ev[3]);
+    unsigned long long c[2] = { 0, 0 };
+    GP_CUDA(ctx, cudaMemcpy(c, ctx->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
+    ctx->stats.kmer_ops = c[0];
+    ctx->stats.serial_kmers = c[1];
+  }
+  if (ctx->polish_timed) {
+    cudaEventElapsedTime(&ctx->stats.polish_ms, ctx->ev[4], ctx->ev[5]);
+    unsigned long long c[4] = { 0, 0, 0, 0 };
+    GP_CUDA(ctx, cudaMemcpy(c, ctx->d_pcounters.p, sizeof c, cudaMemcpyDeviceToHost));
+    ctx->stats.triggers = c[0]; ctx->stats.edits = c[1]; ctx->stats.masked = c[2]; ctx->stats.rollbacks = c[3];
+  }
+  *out = ctx->stats;
+  return GP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// read store
+// ------------------------------------------------------------------------------------
+int gp_reads_upload(gp_ctx* ctx, const char* seqs, const uint64_t* offsets, uint64_t n_reads)
+{
+  if (!ctx || (!seqs && n_reads) || !offsets) return GP_ERR_ARG;
+  if (n_reads > 0xFFFFFFF0ull) GP_FAIL(ctx, GP_ERR_ARG, "too many reads");
+  cudaSetDevice(ctx->cfg.device);
+  const uint64_t n_ascii = offsets[n_reads];
+  std::vector<uint64_t> boff(n_reads + 1);
+  ctx->h_read_len.resize(n_reads);
+  uint64_t b = 0;
+  for (uint64_t r = 0; r < n_reads; r++) {
+    const uint64_t len = offsets[r + 1] - offsets[r];
+    if (len >= (1ull << 31)) GP_FAIL(ctx, GP_ERR_ARG, "read longer than 2^31 bases");
+    boff[r] = b;
+    ctx->h_read_len[r] = uint32_t(len);
+    b += (len + 31) & ~31ull;
+  }
+  boff[n_reads] = b;
+  const uint64_t words = b / 32 + 2; // one spare word past the last read for the window loads
+  GP_CUDA(ctx, ctx->d_ascii.ensure(n_ascii + 16));
+  GP_CUDA(ctx, ctx->d_ascii_off.ensure((n_reads + 1) * 8));
+  GP_CUDA(ctx, ctx->d_read_boff.ensure((n_reads + 1) * 8));
+  GP_CUDA(ctx, ctx->d_read_len.ensure((n_reads + 1) * 4));
+  GP_CUDA(ctx, ctx->d_pk.ensure(words * 8));
+  GP_CUDA(ctx, ctx->d_nm.ensure(words * 4));
+  cudaStream_t s = ctx->stream;
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_ascii.p, seqs, n_ascii, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_ascii_off.p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_read_boff.p, boff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_read_len.p, ctx->h_read_len.data(), n_reads * 4, cudaMemcpyHostToDevice, s));
+  // the two spare words must read as "no seed"
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_nm.as<uint32_t>() + (words - 2), 0xFF, 8, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pk.as<uint64_t>() + (words - 2), 0, 16, s));
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+  gp::launch_pack_reads(ctx->d_ascii.as<char>(), ctx->d_ascii_off.as<uint64_t>(), ctx->d_read_boff.as<uint64_t>(),
+                        ctx->d_pk.as<uint64_t>(), ctx->d_nm.as<uint32_t>(), uint32_t(n_reads), s);
+  GP_CUDA(ctx, cudaGetLastError());
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+  ctx->pack_timed = true;
+  ctx->stats.pack_launches = n_reads ? 1 : 0;
+  GP_CUDA(ctx, cudaStreamSynchronize(s)); // boff (host vector) must outlive the copy
+  ctx->n_reads = n_reads;
+  return GP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// filter build
+// ------------------------------------------------------------------------------------
+int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_off, const gp_read_entry* entries)
+{
+  if (!ctx || !batch_entry_off || (!entries && n_batches && batch_entry_off[n_batches])) return GP_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  const gp_config& c = ctx->cfg;
+  for (uint32_t i = 0; i < c.nk; i++)
+    if (c.k[i] % 4 != 0) GP_FAIL(ctx, GP_ERR_ARG, "building filters needs k values that are multiples of 4");
+  const uint64_t n_entries = batch_entry_off[n_batches];
+  std::vector<uint64_t> work(n_batches, 0);
+  for (uint32_t b = 0; b < n_batches; b++) {
+    for (uint64_t e = batch_entry_off[b]; e < batch_entry_off[b + 1]; e++) {
+      if (entries[e].read_id >= ctx->n_reads) GP_FAIL(ctx, GP_ERR_ARG, "read_id out of range (upload reads first)");
+      if (entries[e].kmer_threshold < 4) // fill_bfs, src/utils.cpp:105-107
+        GP_FAIL(ctx, GP_ERR_ARG, "kmer_threshold must be greater than or equal to 4");
+      work[b] += ctx->h_read_len[entries[e].read_id];
+    }
+  }
+  // how many batches can hold their counting filters at once
+  const uint64_t per_batch = uint64_t(c.nk) * gp::kCbfCounters;
+  const uint64_t bf_bytes = uint64_t(n_batches) * c.nk * gp::kBfBytes;
+  GP_CUDA(ctx, ctx->d_bf_pool.ensure(std::max<uint64_t>(bf_bytes, 4)));
+  uint32_t wave = n_batches;
+  if (c.max_resident_batches) wave = std::min(wave, c.max_resident_batches);
+  {
+    size_t free_b = 0, total_b = 0;
+    GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t usable = uint64_t(free_b) + ctx->d_cbf_pool.cap;
+    const uint64_t headroom = 2ull << 30;
+    const uint64_t fit = usable > headroom ? (usable - headroom) / per_batch : 0;
+    if (fit == 0 && n_batches) GP_FAIL(ctx, GP_ERR_OOM, "not enough device memory for one batch of counting filters");
+    wave = uint32_t(std::min<uint64_t>(wave, fit));
+  }
+  if (n_batches) {
+    cudaError_t e = ctx->d_cbf_pool.ensure(uint64_t(wave) * per_batch);
+    while (e != cudaSuccess && wave > 1) { cudaGetLastError(); wave = (wave + 1) / 2; e = ctx->d_cbf_pool.ensure(uint64_t(wave) * per_batch); }
+    GP_CUDA(ctx, e);
+  }
+  ctx->wave_batches = wave;
+  ctx->wave_first.clear(); ctx->wave_count.clear(); ctx->wave_order_off.clear();
+  std::vector<uint32_t> order_all;
+  order_all.reserve(size_t(n_batches) * c.nk);
+  for (uint32_t first = 0; first < n_batches; first += wave) {
+    const uint32_t cnt = std::min(wave, n_batches - first);
+    ctx->wave_first.push_back(first);
+    ctx->wave_count.push_back(cnt);
+    ctx->wave_order_off.push_back(uint32_t(order_all.size()));
+    // longest stream first (the tail of the launch is one warp finishing one stream)
+    std::vector<uint32_t> idx(size_t(cnt) * c.nk);
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b2) {
+      return work[first + a / c.nk] > work[first + b2 / c.nk];
+    });
+    order_all.insert(order_all.end(), idx.begin(), idx.end());
+  }
+  const size_t n_waves = ctx->wave_first.size();
+  GP_CUDA(ctx, ctx->d_batch_entry_off.ensure((size_t(n_batches) + 1) * 8));
+  GP_CUDA(ctx, ctx->d_entries.ensure(std::max<size_t>(n_entries, 1) * sizeof(gp_read_entry)));
+  GP_CUDA(ctx, ctx->d_stream_order.ensure(std::max<size_t>(order_all.size(), 1) * 4));
+  GP_CUDA(ctx, ctx->d_next.ensure(std::max<size_t>(n_waves, 1) * 4));
+  GP_CUDA(ctx, ctx->d_counters.ensure(16));
+  cudaStream_t s = ctx->stream;
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_entry_off.p, batch_entry_off, (size_t(n_batches) + 1) * 8, cudaMemcpyHostToDevice, s));
+  if (n_entries)
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_entries.p, entries, n_entries * sizeof(gp_read_entry), cudaMemcpyHostToDevice, s));
+  if (!order_all.empty())
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_stream_order.p, order_all.data(), order_all.size() * 4, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaStreamSynchronize(s)); // order_all is a local
+  ctx->n_batches = n_batches;
+  ctx->build_staged = true;
+  ctx->filters_ready = false;
+  return GP_OK;
+}
+
+int gp_build_run(gp_ctx* ctx)
+{
+  if (!ctx) return GP_ERR_ARG;
+  if (!ctx->build_staged) GP_FAIL(ctx, GP_ERR_STATE, "gp_build_run before gp_build_stage");
+  cudaSetDevice(ctx->cfg.device);
+  const gp_config& c = ctx->cfg;
+  cudaStream_t s = ctx->stream;
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+  uint32_t launches = 0;
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16, s));
+  if (ctx->n_batches) {
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_next.p, 0, ctx->wave_first.size() * 4, s));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->n_batches) * c.nk * gp::kBfBytes, s));
+    launches += 3;
+  }
+  for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
+    gp::BuildParams p;
+    p.pk = ctx->d_pk.as<uint64_t>();
+    p.nm = ctx->d_nm.as<uint32_t>();
+    p.read_boff = ctx->d_read_boff.as<uint64_t>();
+    p.read_len = ctx->d_read_len.as<uint32_t>();
+    p.batch_entry_off = ctx->d_batch_entry_off.as<uint64_t>();
+    p.entries = ctx->d_entries.as<gp_read_entry>();
+    p.cbf_pool = ctx->d_cbf_pool.as<uint8_t>();
+    p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
+    p.stream_order = ctx->d_stream_order.as<uint32_t>() + ctx->wave_order_off[wv];
+    p.next_stream = ctx->d_next.as<uint32_t>() + wv;
+    p.counters = ctx->d_counters.as<unsigned long long>();
+    p.n_streams = ctx->wave_count[wv] * c.nk;
+    p.first_batch = ctx->wave_first[wv];
+    p.nk = c.nk;
+    for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
+    gp::launch_build_filters(p, ctx->sm_count, s);
+    GP_CUDA(ctx, cudaGetLastError());
+    launches += 2;
+  }
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+  ctx->build_timed = true;
+  ctx->stats.build_launches = launches;
+  ctx->filters_ready = true;
+  return GP_OK;
+}
+
+int gp_build_fetch(gp_ctx* ctx, uint8_t* bf_out)
+{
+  if (!ctx) return GP_ERR_ARG;
+  if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
+  cudaSetDevice(ctx->cfg.device);
+  if (bf_out && ctx->n_batches)
+    GP_CUDA(ctx, cudaMemcpyAsync(bf_out, ctx->d_bf_pool.p, uint64_t(ctx->n_batches) * ctx->cfg.nk * gp::kBfBytes,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GP_OK;
+}
+
+int gp_build_fetch_cbf(gp_ctx* ctx, uint32_t batch, uint32_t k_index, uint8_t* cbf_out)
+{
+  if (!ctx || !cbf_out) return GP_ERR_ARG;
+  if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
+  if (batch >= ctx->n_batches || k_index >= ctx->cfg.nk) GP_FAIL(ctx, GP_ERR_ARG, "batch / k index out of range");
+  // counting filters of a wave are overwritten by the next wave: only the last wave is still resident
+  const size_t last = ctx->wave_first.size() - 1;
+  if (batch < ctx->wave_first[last]) GP_FAIL(ctx, GP_ERR_STATE, "counting filter of an earlier wave is no longer resident");
+  cudaSetDevice(ctx->cfg.device);
+  const uint64_t sid = uint64_t(batch - ctx->wave_first[last]) * ctx->cfg.nk + k_index;
+  GP_CUDA(ctx, cudaMemcpyAsync(cbf_out, ctx->d_cbf_pool.as<uint8_t>() + sid * gp::kCbfCounters, gp::kCbfCounters,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GP_OK;
+}
+
+int gp_build_filters(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_off, const gp_read_entry* entries,
+                     uint8_t* bf_out)
+{
+  int rc = gp_build_stage(ctx, n_batches, batch_entry_off, entries);
+  if (rc) return rc;
+  if ((rc = gp_build_run(ctx))) return rc;
+  return gp_build_fetch(ctx, bf_out);
+}
+
+int gp_filters_load(gp_ctx* ctx, uint32_t n_batches, const uint8_t* bf_payloads)
+{
+  if (!ctx || (!bf_payloads && n_batches)) return GP_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  const uint64_t bytes = uint64_t(n_batches) * ctx->cfg.nk * gp::kBfBytes;
+  GP_CUDA(ctx, ctx->d_bf_pool.ensure(std::max<uint64_t>(bytes, 4)));
+  if (bytes) GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_bf_pool.p, bf_payloads, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->n_batches = n_batches;
+  ctx->filters_ready = true;
+  ctx->build_staged = false;
+  return GP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// polish
+// ------------------------------------------------------------------------------------
+static int polish_layout(gp_ctx* ctx)
+{
+  const uint32_t n = ctx->n_contigs;
+  const uint32_t g = ctx->grow;
+  ctx->h_cap_off.assign(n + 1, 0);
+  ctx->h_node_off.assign(n + 1, 0);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t len = ctx->h_len[i];
+    uint64_t cap = len + (len >> 1) + 4096;
+    uint64_t nodes = (len >> 2) + 2048;
+    cap <<= g; nodes <<= g;
+    cap = (cap + 15) & ~15ull;
+    if (cap >= (1ull << 32)) { ctx->err = "contig too long for 32-bit positions"; return GP_ERR_ARG; }
+    ctx->h_cap_off[i + 1] = ctx->h_cap_off[i] + cap;
+    ctx->h_node_off[i + 1] = ctx->h_node_off[i] + nodes;
+  }
+  GP_CUDA(ctx, ctx->d_buf0.ensure(std::max<uint64_t>(ctx->h_cap_off[n], 16)));
+  GP_CUDA(ctx, ctx->d_buf1.ensure(std::max<uint64_t>(ctx->h_cap_off[n], 16)));
+  GP_CUDA(ctx, ctx->d_nodes.ensure(std::max<uint64_t>(ctx->h_node_off[n], 1) * sizeof(gp::EdNode)));
+  GP_CUDA(ctx, ctx->d_cap_off.ensure((size_t(n) + 1) * 8));
+  GP_CUDA(ctx, ctx->d_node_off.ensure((size_t(n) + 1) * 8));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_cap_off.p, ctx->h_cap_off.data(), (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_node_off.p, ctx->h_node_off.data(), (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GP_OK;
+}
+
+int gp_polish_stage(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uint64_t* offsets, const uint32_t* contig_batch)
+{
+  if (!ctx || !offsets || (!seqs && n_contigs && offsets[n_contigs]) || (!contig_batch && n_contigs)) return GP_ERR_ARG;
+  if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "gp_polish needs filters (gp_build_filters or gp_filters_load)");
+  cudaSetDevice(ctx->cfg.device);
+  const uint32_t n = n_contigs;
+  ctx->n_contigs = n;
+  ctx->h_len.resize(n);
+  ctx->h_in_off.assign(offsets, offsets + n + 1);
+  ctx->h_batch.assign(contig_batch, contig_batch + n);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t len = offsets[i + 1] - offsets[i];
+    if (len >= (1ull << 31)) GP_FAIL(ctx, GP_ERR_ARG, "contig longer than 2^31 bases");
+    if (contig_batch[i] >= ctx->n_batches) GP_FAIL(ctx, GP_ERR_ARG, "contig_batch out of range of the current filter set");
+    ctx->h_len[i] = uint32_t(len);
+  }
+  ctx->h_order.resize(n);
+  std::iota(ctx->h_order.begin(), ctx->h_order.end(), 0u);
+  std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](uint32_t a, uint32_t b) { return ctx->h_len[a] > ctx->h_len[b]; });
+  const uint64_t total = offsets[n];
+  GP_CUDA(ctx, ctx->d_input.ensure(std::max<uint64_t>(total, 16)));
+  GP_CUDA(ctx, ctx->d_in_off.ensure((size_t(n) + 1) * 8));
+  GP_CUDA(ctx, ctx->d_cur_len.ensure(std::max<size_t>(n, 1) * 4));
+  GP_CUDA(ctx, ctx->d_which.ensure(std::max<size_t>(n, 1)));
+  GP_CUDA(ctx, ctx->d_dropped.ensure(std::max<size_t>(n, 1)));
+  GP_CUDA(ctx, ctx->d_contig_batch.ensure(std::max<size_t>(n, 1) * 4));
+  GP_CUDA(ctx, ctx->d_order.ensure(std::max<size_t>(n, 1) * 4));
+  GP_CUDA(ctx, ctx->d_pnext.ensure(4));
+  GP_CUDA(ctx, ctx->d_pcounters.ensure(32));
+  GP_CUDA(ctx, ctx->d_error.ensure(4));
+  cudaStream_t s = ctx->stream;
+  if (total) GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_input.p, seqs, total, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, offsets, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, s));
+  if (n) {
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_contig_batch.p, contig_batch, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), size_t(n) * 4, cudaMemcpyHostToDevice, s));
+  }
+  ctx->grow = 0;
+  if (int rc = polish_layout(ctx)) return rc;
+  ctx->polish_staged = true;
+  ctx->polish_done = false;
+  return GP_OK;
+}
+
+static int polish_launch(gp_ctx* ctx)
+{
+  const gp_config& c = ctx->cfg;
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = ctx->n_contigs;
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pnext.p, 0, 4, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pcounters.p, 0, 32, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_error.p, 0, 4, s));
+  if (n == 0) return GP_OK;
+  const uint32_t grid = std::min<uint32_t>(n, uint32_t(ctx->sm_count) * 8u);
+  scatter_contigs_kernel<<<grid, 256, 0, s>>>(ctx->d_input.as<char>(), ctx->d_in_off.as<uint64_t>(), ctx->d_buf0.as<char>(),
+                                              ctx->d_cap_off.as<uint64_t>(), ctx->d_cur_len.as<uint32_t>(), n);
+  GP_CUDA(ctx, cudaGetLastError());
+  gp::EditParams p;
+  std::memset(&p, 0, sizeof p);
+  p.n_contigs = n;
+  p.buf[0] = ctx->d_buf0.as<char>();
+  p.buf[1] = ctx->d_buf1.as<char>();
+  p.cap_off = ctx->d_cap_off.as<uint64_t>();
+  p.cur_len = ctx->d_cur_len.as<uint32_t>();
+  p.which = ctx->d_which.as<uint8_t>();
+  p.dropped = ctx->d_dropped.as<uint8_t>();
+  p.nodes = ctx->d_nodes.as<gp::EdNode>();
+  p.node_off = ctx->d_node_off.as<uint64_t>();
+  p.contig_batch = ctx->d_contig_batch.as<uint32_t>();
+  p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
+  p.order = ctx->d_order.as<uint32_t>();
+  p.next_contig = ctx->d_pnext.as<uint32_t>();
+  p.counters = ctx->d_pcounters.as<unsigned long long>();
+  p.error = ctx->d_error.as<int>();
+  p.nk = c.nk;
+  for (uint32_t i = 0; i < c.nk; i++) {
+    p.k[i] = c.k[i];
+    // the reference's float expressions, evaluated once on the host
+    // (ntedit.cpp:1521-1523, 1624-1626 / 1335-1337, 1228-1230, 2024-2025)
+    const float kf = static_cast<float>(c.k[i]);
+    const float jf = static_cast<float>(c.jump);
+    p.thr_missing[i] = (kf / jf) * c.missing_ratio;
+    p.thr_edit[i] = (kf / jf) * c.edit_ratio;
+    p.thr_del[i] = (1 + (kf / jf)) * c.edit_ratio;
+    p.insertion_cap[i] = static_cast<unsigned>(kf * 1.5f);
+  }
+  p.max_insertions = c.max_insertions; p.max_deletions = c.max_deletions; p.jump = c.jump;
+  p.min_contig_len = c.min_contig_len; p.mode = c.mode; p.mask = c.mask;
+  gp::launch_edit(p, ctx->sm_count, s);
+  GP_CUDA(ctx, cudaGetLastError());
+  return GP_OK;
+}
+
+int gp_polish_run(gp_ctx* ctx)
+{
+  if (!ctx) return GP_ERR_ARG;
+  if (!ctx->polish_staged) GP_FAIL(ctx, GP_ERR_STATE, "gp_polish_run before gp_polish_stage");
+  cudaSetDevice(ctx->cfg.device);
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+  if (int rc = polish_launch(ctx)) return rc;
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->polish_timed = true;
+  ctx->stats.polish_launches = ctx->n_contigs ? 5 : 3;
+  ctx->polish_done = true;
+  return GP_OK;
+}
+
+int gp_polish_fetch(gp_ctx* ctx, char* out_seqs, uint64_t out_cap, uint64_t* out_offsets, uint8_t* out_dropped)
+{
+  if (!ctx || !out_offsets) return GP_ERR_ARG;
+  if (!ctx->polish_done) GP_FAIL(ctx, GP_ERR_STATE, "gp_polish_fetch before gp_polish_run");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = ctx->n_contigs;
+  std::vector<uint32_t> len(n);
+  std::vector<uint8_t> dropped(n);
+  for (;;) {
+    int err = 0;
+    GP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->d_error.p, 4, cudaMemcpyDeviceToHost, s));
+    if (n) {
+      GP_CUDA(ctx, cudaMemcpyAsync(len.data(), ctx->d_cur_len.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+      GP_CUDA(ctx, cudaMemcpyAsync(dropped.data(), ctx->d_dropped.p, n, cudaMemcpyDeviceToHost, s));
+    }
+    GP_CUDA(ctx, cudaStreamSynchronize(s));
+    if (!err) break;
+    // an edited contig outgrew its buffers: enlarge them and run the polish again on the device
+    if (ctx->grow >= 4) GP_FAIL(ctx, GP_ERR_OVERFLOW, "edited contig outgrew its device buffers");
+    ctx->grow++;
+    if (int rc = polish_layout(ctx)) return rc;
+    if (int rc = polish_launch(ctx)) return rc;
+  }
+  uint64_t o = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    out_offsets[i] = o;
+    if (!dropped[i]) o += len[i];
+    if (out_dropped) out_dropped[i] = dropped[i];
+  }
+  out_offsets[n] = o;
+  if (o > out_cap || (o && !out_seqs)) GP_FAIL(ctx, GP_ERR_ARG, "output buffer too small (needed size is in out_offsets[n])");
+  if (o) {
+    GP_CUDA(ctx, ctx->d_out.ensure(o));
+    GP_CUDA(ctx, ctx->d_out_off.ensure((size_t(n) + 1) * 8));
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, out_offsets, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, s));
+    const uint32_t grid = std::min<uint32_t>(n, uint32_t(ctx->sm_count) * 8u);
+    gather_contigs_kernel<<<grid, 256, 0, s>>>(ctx->d_buf0.as<char>(), ctx->d_buf1.as<char>(), ctx->d_cap_off.as<uint64_t>(),
+                                               ctx->d_which.as<uint8_t>(), ctx->d_out_off.as<uint64_t>(), ctx->d_out.as<char>(), n);
+    GP_CUDA(ctx, cudaGetLastError());
+    GP_CUDA(ctx, cudaMemcpyAsync(out_seqs, ctx->d_out.p, o, cudaMemcpyDeviceToHost, s));
+    GP_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  return GP_OK;
+}
+
+int gp_polish(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uint64_t* offsets, const uint32_t* contig_batch,
+              char* out_seqs, uint64_t out_cap, uint64_t* out_offsets, uint8_t* out_dropped)
+{
+  int rc = gp_polish_stage(ctx, n_contigs, seqs, offsets, contig_batch);
+  if (rc) return rc;
+  if ((rc = gp_polish_run(ctx))) return rc;
+  return gp_polish_fetch(ctx, out_seqs, out_cap, out_offsets, out_dropped);
+}
+
+// ------------------------------------------------------------------------------------
+// host-side rules
+// ------------------------------------------------------------------------------------
+int gp_kmer_threshold(uint64_t mappings_bases)
+{ // src/goldpolish_targeted_bfs.cpp:45-53
+  const double a = 4.66943, b = 2.11391e-07;
+  const int t = int(std::round(a + double(mappings_bases) * b));
+  return std::min(t, 13);
+}
+
+uint64_t gp_mappings_cap(uint64_t target_len, double subsample_max_per_10kbp)
+{ // src/goldpolish_targeted_bfs.cpp:96-99
+  return uint64_t(double(target_len) * subsample_max_per_10kbp / 10000.0);
+}
+
+int gp_guard_rejects(uint64_t input_bytes, uint64_t output_bytes)
+{ // scripts/goldpolish-ntedit:31-34: bc scale=4 truncates the quotient, then "< 0.75"
+  if (input_bytes == 0) return 0;
+  return (output_bytes * 10000ull) / input_bytes < 7500ull ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------
+// roof microbenchmark
+// ------------------------------------------------------------------------------------
+int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t region_bytes, double* sectors_per_s, float* ms)
+{
+  if (!ctx || !sectors_per_s || warps == 0 || iters == 0 || region_bytes < 4096) return GP_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  DevBuf cbf, bf;
+  GP_CUDA(ctx, cbf.ensure(uint64_t(warps) * region_bytes));
+  cudaError_t e = bf.ensure(uint64_t(warps) * gp::kBfBytes);
+  if (e != cudaSuccess) { cbf.release(); GP_CUDA(ctx, e); }
+  cudaStream_t s = ctx->stream;
+  cudaMemsetAsync(cbf.p, 0, uint64_t(warps) * region_bytes, s);
+  cudaMemsetAsync(bf.p, 0, uint64_t(warps) * gp::kBfBytes, s);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  gp::launch_roof(cbf.as<uint8_t>(), bf.as<uint32_t>(), region_bytes, std::min(iters, 64u), warps, s); // warm-up
+  cudaEventRecord(a, s);
+  gp::launch_roof(cbf.as<uint8_t>(), bf.as<uint32_t>(), region_bytes, iters, warps, s);
+  cudaEventRecord(b, s);
+  e = cudaStreamSynchronize(s);
+  float t = 0;
+  cudaEventElapsedTime(&t, a, b);
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cbf.release(); bf.release();
+  GP_CUDA(ctx, e);
+  if (ms) *ms = t;
+  *sectors_per_s = double(warps) * iters * 32.0 * 8.0 / (double(t) * 1e-3);
+  return GP_OK;
+}
+
+} // extern "C"

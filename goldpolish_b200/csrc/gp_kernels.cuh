@@ -1,0 +1,61 @@
+// Kernel parameter blocks and launchers shared between the .cu files and the C ABI.
+#pragma once
+
+#include "../../include/goldpolish_b200.h"
+#include "gp_common.cuh"
+
+namespace gp {
+
+struct BuildParams {
+  const uint64_t* pk;               // packed reads, 32 bases per word
+  const uint32_t* nm;               // "no seed" mask, 32 bases per word
+  const uint64_t* read_boff;        // per read: first base index (multiple of 32)
+  const uint32_t* read_len;
+  const uint64_t* batch_entry_off;  // global batch index -> entries
+  const gp_read_entry* entries;
+  uint8_t* cbf_pool;                // wave-local: stream s at s * kCbfCounters
+  uint32_t* bf_pool;                // global: (batch * nk + ki) * kBfWords
+  const uint32_t* stream_order;     // wave-local stream ids, longest first
+  uint32_t* next_stream;            // work counter (zeroed before launch)
+  unsigned long long* counters;     // [0] k-mer ops, [1] serially resolved k-mers
+  uint32_t n_streams;
+  uint32_t first_batch;
+  uint32_t nk;
+  uint32_t k[kMaxK];
+};
+
+struct EdNode {      // seqNode of ntedit.cpp:468-475 (num_support is never observable)
+  int32_t type;      // -1 unset, 0 draft range [s, e], 1 inserted character c
+  uint32_t s, e, c;
+};
+
+struct EditParams {
+  uint32_t n_contigs;
+  char* buf[2];                 // ping-pong sequence storage, contig i at cap_off[i]
+  const uint64_t* cap_off;      // n_contigs + 1
+  uint32_t* cur_len;            // in: draft length, out: polished length
+  uint8_t* which;               // out: buffer index holding the result
+  uint8_t* dropped;             // out: 1 if the record is not emitted
+  EdNode* nodes;                // contig i at node_off[i]
+  const uint64_t* node_off;     // n_contigs + 1
+  const uint32_t* contig_batch;
+  const uint32_t* bf_pool;      // (batch * nk + ki) * kBfWords
+  const uint32_t* order;        // contig ids, longest first
+  uint32_t* next_contig;
+  unsigned long long* counters; // [0] triggers [1] edits [2] masked [3] rollbacks
+  int* error;                   // set to 1 on buffer overflow
+  uint32_t nk;
+  uint32_t k[kMaxK];
+  float thr_missing[kMaxK], thr_edit[kMaxK], thr_del[kMaxK];
+  uint32_t insertion_cap[kMaxK];
+  uint32_t max_insertions, max_deletions, jump, min_contig_len;
+  int32_t mode, mask;
+};
+
+void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint64_t* base_off, uint64_t* pk,
+                       uint32_t* nm, uint32_t n_reads, cudaStream_t s);
+void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
+void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t iters, uint32_t warps, cudaStream_t s);
+void launch_edit(const EditParams& p, int sm_count, cudaStream_t s);
+
+} // namespace gp

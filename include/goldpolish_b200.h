@@ -1,0 +1,158 @@
+/* goldpolish_b200 -- C ABI of the B200-native GoldPolish hot path.
+ *
+ * Plain C, pointers and sizes only; no C++ or torch types cross this boundary.  One context
+ * per GPU; calls on a context are serialised by the caller.  Every function returns 0 on
+ * success or a negative gp_status; gp_last_error() gives the message.  There is no CPU
+ * fallback: without a usable CUDA device gp_ctx_create fails.
+ *
+ * What each entry point replaces in the reference (paths relative to bcgsc/goldpolish):
+ *
+ *   gp_reads_upload      SeqIndex::get_seq<1> feeding fill_bfs, src/seqindex.hpp:59-102 and
+ *                        src/goldpolish_targeted_bfs.cpp:130-133 (whole reads, uploaded once,
+ *                        2-bit packed + validity mask on the device)
+ *   gp_build_filters     serve_batch's filter loop, src/goldpolish_targeted_bfs.cpp:70-77,
+ *                        124-140, i.e. fill_bfs, src/utils.cpp:96-123 (btllib::NtHash roll,
+ *                        KmerCountingBloomFilter8::insert_thresh_contains, KmerBloomFilter::
+ *                        insert) for every (batch, k); bf_out payloads are what
+ *                        KmerBloomFilter::save writes after its text header (:138-140)
+ *   gp_filters_load      btllib::KmerBloomFilter(path) payload, subprojects/ntedit/
+ *                        ntedit.cpp:2012-2022 (lets ntedit-gr run on filters built elsewhere)
+ *   gp_polish            readAndCorrect + kmerizeAndCorrect + writeEditsToFile for every
+ *                        contig, subprojects/ntedit/ntedit.cpp:1414-1867, chained over the
+ *                        context's k list as scripts/goldpolish-ntedit:20-29 chains processes
+ *   gp_guard_rejects     the 0.75 size guard, scripts/goldpolish-ntedit:31-40
+ *   gp_kmer_threshold    mappings_bases_to_kmer_threshold, src/goldpolish_targeted_bfs.cpp:45-53
+ *   gp_mappings_cap      mappings_num_max, src/goldpolish_targeted_bfs.cpp:96-99
+ */
+#ifndef GOLDPOLISH_B200_H
+#define GOLDPOLISH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_MAX_K_VALUES 8
+#define GP_CBF_BYTES 10485760ULL /* src/goldpolish_targeted_bfs.cpp:270 */
+#define GP_BF_BYTES 524288ULL    /* src/goldpolish_targeted_bfs.cpp:271 */
+#define GP_HASH_NUM 4u           /* src/goldpolish_targeted_bfs.cpp:272 */
+
+typedef enum {
+  GP_OK = 0,
+  GP_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+  GP_ERR_CUDA = -2,     /* CUDA runtime error (message holds cudaGetErrorString) */
+  GP_ERR_NO_DEVICE = -3,/* no CUDA device: this library has no CPU path */
+  GP_ERR_OOM = -4,      /* device or host allocation failed */
+  GP_ERR_STATE = -5,    /* call order (e.g. polish before filters exist) */
+  GP_ERR_OVERFLOW = -6  /* an edited contig outgrew its device buffers */
+} gp_status;
+
+typedef struct gp_ctx gp_ctx;
+
+typedef struct {
+  uint32_t struct_size;            /* sizeof(gp_config), for ABI growth */
+  int32_t device;                  /* CUDA device ordinal */
+  uint32_t nk;                     /* number of k values (<= GP_MAX_K_VALUES) */
+  uint32_t k[GP_MAX_K_VALUES];     /* descending, e.g. 32 28 24 20; each 4..32, multiple of 4 for building */
+  /* ntEdit options, defaults = scripts/goldpolish-ntedit:27 (-d5 -i5 -m1 -X0.5 -Y0.5 -a1) */
+  uint32_t max_insertions;         /* -i, 0..5 */
+  uint32_t max_deletions;          /* -d, 0..10 */
+  int32_t mode;                    /* -m, 0..2 */
+  int32_t mask;                    /* -a */
+  float missing_ratio;             /* -X */
+  float edit_ratio;                /* -Y */
+  uint32_t jump;                   /* -j */
+  uint32_t min_contig_len;         /* -z */
+  uint32_t max_resident_batches;   /* cap on batches whose counting filters live at once; 0 = fit to free memory */
+} gp_config;
+
+/* one read handed to fill_bfs: index into the uploaded read store + the target's kmer_threshold */
+typedef struct {
+  uint32_t read_id;
+  uint32_t kmer_threshold; /* T of goldpolish_targeted_bfs.cpp:124-125; fill_bfs uses T-2+idx(k) */
+} gp_read_entry;
+
+typedef struct {
+  uint64_t kmer_ops;        /* valid (read k-mer, k) pairs processed by the last build */
+  uint64_t serial_kmers;    /* of those, resolved on the in-order (colliding) path */
+  uint64_t triggers;        /* ntEdit: absent k-mers that started an edit attempt (last polish) */
+  uint64_t edits;           /* substitutions + insertions + deletions applied */
+  uint64_t masked;          /* soft-masked positions */
+  uint64_t rollbacks;       /* low-complexity insertion rollbacks */
+  float build_ms;           /* device time of the last build (CUDA events on the ctx stream) */
+  float polish_ms;          /* device time of the last polish */
+  float pack_ms;            /* device time of the last read packing */
+  uint32_t build_launches;  /* kernels launched by the last build */
+  uint32_t polish_launches; /* kernels launched by the last polish */
+  uint32_t pack_launches;
+} gp_stats;
+
+void gp_default_config(gp_config* cfg);
+int gp_ctx_create(const gp_config* cfg, gp_ctx** out);
+void gp_ctx_destroy(gp_ctx* ctx);
+const char* gp_last_error(const gp_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as void*),
+ * e.g. so that a caller's CUDA events bracket it.  NULL restores the context's own stream. */
+int gp_ctx_set_stream(gp_ctx* ctx, void* cuda_stream);
+int gp_ctx_synchronize(gp_ctx* ctx);
+int gp_get_stats(const gp_ctx* ctx, gp_stats* out);
+
+/* ---- read store ------------------------------------------------------------------- */
+/* seqs: ASCII bases of all reads back to back; read i = seqs[offsets[i] .. offsets[i+1]).
+ * Host buffers; copied to the device and packed there.  Replaces any previous store. */
+int gp_reads_upload(gp_ctx* ctx, const char* seqs, const uint64_t* offsets, uint64_t n_reads);
+
+/* ---- filter build ----------------------------------------------------------------- */
+/* Batch b hashes entries[batch_entry_off[b] .. batch_entry_off[b+1]) in that order, every read
+ * with every k of the context, into its own nk (counting filter, filter) pairs.
+ * bf_out (host, may be NULL): n_batches * nk * GP_BF_BYTES payload bytes, batch-major then k.
+ * The filters stay resident as the context's current filter set for gp_polish. */
+int gp_build_filters(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_off,
+                     const gp_read_entry* entries, uint8_t* bf_out);
+
+/* split form of the same call (stage = host->device copies, run = kernels only,
+ * fetch = device->host copy); gp_build_filters == stage + run + fetch */
+int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_off, const gp_read_entry* entries);
+int gp_build_run(gp_ctx* ctx);
+int gp_build_fetch(gp_ctx* ctx, uint8_t* bf_out);
+/* debug / parity: counting-filter bytes of (batch, k index) after the last build */
+int gp_build_fetch_cbf(gp_ctx* ctx, uint32_t batch, uint32_t k_index, uint8_t* cbf_out);
+
+/* Make externally built payloads (n_batches * nk * GP_BF_BYTES) the current filter set. */
+int gp_filters_load(gp_ctx* ctx, uint32_t n_batches, const uint8_t* bf_payloads);
+
+/* ---- polish ----------------------------------------------------------------------- */
+/* Contig i = seqs[offsets[i] .. offsets[i+1]) uses the filters of batch contig_batch[i] and is
+ * run through every k of the context in order.  Outputs (host): out_seqs/out_offsets in CSR
+ * form (a dropped contig has an empty range), out_dropped[i] = 1 when the reference would not
+ * emit the record (shorter than min_contig_len at any round, ntedit.cpp:1850).
+ * Returns GP_ERR_ARG if out_cap is too small (needed size in out_offsets[n_contigs]). */
+int gp_polish(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uint64_t* offsets,
+              const uint32_t* contig_batch, char* out_seqs, uint64_t out_cap, uint64_t* out_offsets,
+              uint8_t* out_dropped);
+
+int gp_polish_stage(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uint64_t* offsets,
+                    const uint32_t* contig_batch);
+int gp_polish_run(gp_ctx* ctx);
+int gp_polish_fetch(gp_ctx* ctx, char* out_seqs, uint64_t out_cap, uint64_t* out_offsets, uint8_t* out_dropped);
+
+/* ---- host-side rules shared with the reference ------------------------------------ */
+int gp_kmer_threshold(uint64_t mappings_bases);
+uint64_t gp_mappings_cap(uint64_t target_len, double subsample_max_per_10kbp);
+int gp_guard_rejects(uint64_t input_bytes, uint64_t output_bytes);
+
+/* ---- measurement support ---------------------------------------------------------- */
+/* Random-access roof microbenchmark with the build kernel's access shape: `warps` warps, each
+ * doing `iters` rounds of 32x4 dependent byte loads + conditional byte stores into a private
+ * region of region_bytes, plus 32x4 atomicOr into a private 512 KiB region.  Returns sector
+ * touches per second (8 per k-mer op) in *sectors_per_s. */
+int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t region_bytes, double* sectors_per_s,
+                       float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

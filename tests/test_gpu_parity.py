@@ -1,0 +1,97 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from util import KS, dataset, oracle_build, oracle_polish_contig, plan
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gp():
+    import goldpolish_b200
+    return goldpolish_b200
+
+
+@pytest.fixture(scope="module")
+def small(gp):
+    d = dataset(genome_len=60000)
+    ctx = gp.Context()
+    ctx.upload_reads(d.read_seq, d.read_off)
+    yield d, ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("bsize", [1, 3])
+def test_filters_match_oracle(gp, small, bsize):
+    d, ctx = small
+    pl = plan(d, bsize=bsize)
+    bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    st = ctx.stats()
+    ref = oracle_build(d, pl)
+    n_batches = len(pl.batch_entry_off) - 1
+    assert bfs.shape == (n_batches, 4, gp.BF_BYTES)
+    ops = 0
+    for b in range(n_batches):
+        ops += ref[b].ops
+        for ki in range(4):
+            assert np.array_equal(bfs[b, ki], ref[b].bfs[ki]), f"BF payload differs: batch {b} k={KS[ki]}"
+            assert np.array_equal(ctx.fetch_cbf(b, ki), ref[b].cbfs[ki]), f"CBF differs: batch {b} k={KS[ki]}"
+    assert st["kmer_ops"] == ops
+    assert st["build_launches"] > 0
+
+
+def test_filters_wave_invariance(gp, small):
+    """Splitting the batches into waves (limited counting-filter residency) changes nothing."""
+    d, ctx = small
+    pl = plan(d, bsize=2)
+    a = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    ctx2 = gp.Context(max_resident_batches=2)
+    ctx2.upload_reads(d.read_seq, d.read_off)
+    b = ctx2.build_filters(pl.batch_entry_off, pl.entries)
+    ctx2.close()
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("bsize", [1, 4])
+def test_polish_matches_oracle(gp, small, bsize):
+    d, ctx = small
+    pl = plan(d, bsize=bsize)
+    bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    out, off, dropped = ctx.polish(d.contig_seq, d.contig_off, pl.contig_batch)
+    st = ctx.stats()
+    assert st["polish_launches"] > 0
+    for c in range(d.n_contigs):
+        want = oracle_polish_contig(d.contig(c), [bfs[pl.contig_batch[c], ki] for ki in range(4)])
+        got = out[int(off[c]):int(off[c + 1])].tobytes()
+        if want is None:
+            assert dropped[c] == 1 and got == b""
+        else:
+            assert dropped[c] == 0
+            assert got == want, f"contig {c} (len {len(d.contig(c))}) differs from the oracle"
+    assert st["edits"] > 0 and st["masked"] > 0
+
+
+def test_polish_identity_filters(gp, small):
+    """All-ones filter: every k-mer present, nothing is edited.  All-zero filter: every position that
+    passes the look-ahead is soft-masked and nothing else changes (size-independent properties)."""
+    d, ctx = small
+    nb = 1
+    ones = np.full((nb, 4, gp.BF_BYTES), 0xFF, dtype=np.uint8)
+    ctx.load_filters(ones)
+    cb = np.zeros(d.n_contigs, dtype=np.uint32)
+    out, off, dropped = ctx.polish(d.contig_seq, d.contig_off, cb)
+    for c in range(d.n_contigs):
+        got = out[int(off[c]):int(off[c + 1])].tobytes()
+        if len(d.contig(c)) < 100:
+            assert dropped[c]
+        else:
+            assert got == d.contig(c)
+    ctx.load_filters(np.zeros_like(ones))
+    out, off, dropped = ctx.polish(d.contig_seq, d.contig_off, cb)
+    for c in range(d.n_contigs):
+        got = out[int(off[c]):int(off[c + 1])].tobytes()
+        if len(d.contig(c)) >= 100:
+            assert got.upper() == d.contig(c).upper() and len(got) == len(d.contig(c))
+            want = oracle_polish_contig(d.contig(c), [np.zeros(gp.BF_BYTES, np.uint8)] * 4)
+            assert got == want
