@@ -36,6 +36,7 @@ class _Stats(C.Structure):
     _fields_ = [("kmer_ops", C.c_uint64), ("serial_kmers", C.c_uint64), ("triggers", C.c_uint64),
                 ("edits", C.c_uint64), ("masked", C.c_uint64), ("rollbacks", C.c_uint64),
                 ("build_ms", C.c_float), ("polish_ms", C.c_float), ("pack_ms", C.c_float),
+                ("build_kernel_ms", C.c_float), ("edit_kernel_ms", C.c_float),
                 ("build_launches", C.c_uint32), ("polish_launches", C.c_uint32), ("pack_launches", C.c_uint32)]
 
 

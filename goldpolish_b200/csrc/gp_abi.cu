@@ -38,6 +38,8 @@ struct gp_ctx {
   int sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // pack, build, polish (start, stop)
+  std::vector<cudaEvent_t> wave_ev;  // build kernel only: (start, stop) per wave
+  cudaEvent_t edit_ev[2] = { nullptr, nullptr }; // edit kernel only
   std::string err;
   gp_stats stats;
   bool build_timed = false, polish_timed = false, pack_timed = false;
@@ -171,6 +173,7 @@ int gp_ctx_create(const gp_config* cfg, gp_ctx** out)
   }
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  for (auto& ev : ctx->edit_ev) cudaEventCreate(&ev);
   *out = ctx;
   return GP_OK;
 }
@@ -188,6 +191,8 @@ void gp_ctx_destroy(gp_ctx* ctx)
                      &ctx->d_out_off };
   for (auto* b : bufs) b->release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->edit_ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->wave_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -218,6 +223,11 @@ int gp_get_stats(const gp_ctx* cctx, gp_stats* out)
   if (ctx->pack_timed) cudaEventElapsedTime(&ctx->stats.pack_ms, ctx->ev[0], ctx->ev[1]);
   if (ctx->build_timed) {
     cudaEventElapsedTime(&ctx->stats.build_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->stats.build_kernel_ms = 0;
+    for (size_t wv = 0; wv < ctx->wave_first.size() && 2 * wv + 1 < ctx->wave_ev.size(); wv++) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, ctx->wave_ev[2 * wv], ctx->wave_ev[2 * wv + 1]) == cudaSuccess) ctx->stats.build_kernel_ms += t;
+    }
     unsigned long long c[2] = { 0, 0 };
     GP_CUDA(ctx, cudaMemcpy(c, ctx->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.kmer_ops = c[0];
@@ -225,6 +235,8 @@ int gp_get_stats(const gp_ctx* cctx, gp_stats* out)
   }
   if (ctx->polish_timed) {
     cudaEventElapsedTime(&ctx->stats.polish_ms, ctx->ev[4], ctx->ev[5]);
+    ctx->stats.edit_kernel_ms = 0;
+    if (ctx->n_contigs) cudaEventElapsedTime(&ctx->stats.edit_kernel_ms, ctx->edit_ev[0], ctx->edit_ev[1]);
     unsigned long long c[4] = { 0, 0, 0, 0 };
     GP_CUDA(ctx, cudaMemcpy(c, ctx->d_pcounters.p, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.triggers = c[0]; ctx->stats.edits = c[1]; ctx->stats.masked = c[2]; ctx->stats.rollbacks = c[3];
@@ -369,7 +381,6 @@ int gp_build_run(gp_ctx* ctx)
   if (ctx->n_batches) {
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_next.p, 0, ctx->wave_first.size() * 4, s));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->n_batches) * c.nk * gp::kBfBytes, s));
-    launches += 3;
   }
   for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
     gp::BuildParams p;
@@ -389,9 +400,12 @@ int gp_build_run(gp_ctx* ctx)
     p.nk = c.nk;
     for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
+    while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
+    GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
     gp::launch_build_filters(p, ctx->sm_count, s);
     GP_CUDA(ctx, cudaGetLastError());
-    launches += 2;
+    GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
+    launches += 1;
   }
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
   ctx->build_timed = true;
@@ -569,8 +583,10 @@ static int polish_launch(gp_ctx* ctx)
   }
   p.max_insertions = c.max_insertions; p.max_deletions = c.max_deletions; p.jump = c.jump;
   p.min_contig_len = c.min_contig_len; p.mode = c.mode; p.mask = c.mask;
+  GP_CUDA(ctx, cudaEventRecord(ctx->edit_ev[0], s));
   gp::launch_edit(p, ctx->sm_count, s);
   GP_CUDA(ctx, cudaGetLastError());
+  GP_CUDA(ctx, cudaEventRecord(ctx->edit_ev[1], s));
   return GP_OK;
 }
 
@@ -583,7 +599,7 @@ int gp_polish_run(gp_ctx* ctx)
   if (int rc = polish_launch(ctx)) return rc;
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   ctx->polish_timed = true;
-  ctx->stats.polish_launches = ctx->n_contigs ? 5 : 3;
+  ctx->stats.polish_launches = ctx->n_contigs ? 2 : 0; // scatter + edit kernels
   ctx->polish_done = true;
   return GP_OK;
 }

@@ -84,7 +84,9 @@ typedef struct {
   float build_ms;           /* device time of the last build (CUDA events on the ctx stream) */
   float polish_ms;          /* device time of the last polish */
   float pack_ms;            /* device time of the last read packing */
-  uint32_t build_launches;  /* kernels launched by the last build */
+  float build_kernel_ms;    /* of build_ms, the filter-build kernel alone (memsets excluded) */
+  float edit_kernel_ms;     /* of polish_ms, the edit kernel alone */
+  uint32_t build_launches;  /* kernels (not memsets) launched by the last build */
   uint32_t polish_launches; /* kernels launched by the last polish */
   uint32_t pack_launches;
 } gp_stats;
