@@ -62,8 +62,8 @@ void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint6
 // build
 // ------------------------------------------------------------------------------------
 constexpr int kBuildWarps = 8;
-constexpr int kTabSlots = 256;
-constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr int kTabBits = 9;
+constexpr int kTabSlots = 1 << kTabBits;
 
 // byte tables for hashing 4 packed bases at a time; k-independent because groups are counted
 // from the k-mer end for the forward strand and from its start for the reverse strand.
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
   __shared__ uint64_t tr[8 * 256];
   __shared__ uint32_t tabs[kBuildWarps][kTabSlots];
   fill_hash_tables(tf, tr);
+  for (uint32_t i = threadIdx.x; i < kBuildWarps * kTabSlots; i += blockDim.x) (&tabs[0][0])[i] = 0u;
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31u;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
         const uint64_t w0 = __ldg(p.pk + wi), w1 = __ldg(p.pk + wi + 1);
         const uint64_t w = sh ? ((w0 >> (2 * sh)) | (w1 << (64 - 2 * sh))) : w0;
 
-        uint32_t ci[4], bi[4], c[4];
+        uint32_t ci[4] = { 0xFFFFFFF0u, 0xFFFFFFF1u, 0xFFFFFFF2u, 0xFFFFFFF3u }, bi[4], c[4];
         if (valid) {
           uint64_t fh = 0, rh = 0;
           for (uint32_t m = 0; m < kq; m++) {
@@ -171,34 +172,43 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
           for (int j = 0; j < 4; j++) c[j] = __ldcg(cbf + ci[j]);
         }
 
-        // who touches each counter first in this step?  open-addressed table keyed by counter
-        // index, value = lowest lane seen
-        for (uint32_t i = lane; i < kTabSlots; i += 32) tab[i] = kEmpty;
-        __syncwarp();
-        uint32_t hs[4];
+        // Which lanes share a counter with a LOWER lane of this step?  Lanes publish themselves
+        // in a small direct-mapped table of lane masks (slot = hash of the counter index);
+        // slot sharing only nominates candidates, the counter indices themselves are then
+        // compared through shuffles, so the answer is exact whatever the table size.
+        uint32_t sl[4];
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const uint32_t val = (ci[j] << 5) | lane;
-            uint32_t s = (ci[j] * 2654435761u) >> 24;
-            hs[j] = s;
-            for (;;) {
-              const uint32_t old = atomicCAS(&tab[s], kEmpty, val);
-              if (old == kEmpty) break;
-              if ((old >> 5) == ci[j]) { atomicMin(&tab[s], val); break; }
-              s = (s + 1) & (kTabSlots - 1);
-            }
+            sl[j] = (ci[j] * 2654435761u) >> (32 - kTabBits);
+            atomicOr(&tab[sl[j]], 1u << lane);
           }
         }
         __syncwarp();
-        bool indep = true;
+        uint32_t lower = 0;
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            uint32_t s = hs[j], v;
-            while (((v = tab[s]) >> 5) != ci[j]) s = (s + 1) & (kTabSlots - 1);
-            indep &= (v & 31u) == lane;
+          for (int j = 0; j < 4; j++) lower |= tab[sl[j]];
+          lower &= (1u << lane) - 1u;
+        }
+        __syncwarp();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) tab[sl[j]] = 0u; // leave the table clean for the next step
+        }
+        bool indep = true;
+        const uint32_t rounds = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(lower));
+        for (uint32_t it = 0; it < rounds; it++) {
+          const uint32_t l = lower ? (uint32_t)__ffs(lower) - 1u : lane;
+          lower &= lower - 1u;
+          const uint32_t o0 = __shfl_sync(0xffffffffu, ci[0], l), o1 = __shfl_sync(0xffffffffu, ci[1], l);
+          const uint32_t o2 = __shfl_sync(0xffffffffu, ci[2], l), o3 = __shfl_sync(0xffffffffu, ci[3], l);
+          if (l != lane) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) indep &= (ci[j] != o0) & (ci[j] != o1) & (ci[j] != o2) & (ci[j] != o3);
           }
+        }
+        if (valid) {
           if (indep) cbf_bf_apply(cbf, bf, ci, bi, c, thr);
           ops++;
         }

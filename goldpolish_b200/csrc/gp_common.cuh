@@ -106,8 +106,10 @@ __host__ __device__ __forceinline__ uint64_t extra_hash(uint64_t base, uint32_t 
 // h mod 10485760 (= 5 * 2^21): low 21 bits unchanged, (h >> 21) mod 5 above them
 __host__ __device__ __forceinline__ uint32_t cbf_index(uint64_t h)
 {
+  // (h >> 21) mod 5 with 32-bit arithmetic: 2^32 == 1 (mod 5)
   const uint64_t hi = h >> 21;
-  return uint32_t(h & 0x1FFFFFu) | (uint32_t(hi % 5u) << 21);
+  const uint32_t m = (uint32_t(hi) % 5u + uint32_t(hi >> 32) % 5u) % 5u;
+  return uint32_t(h & 0x1FFFFFu) | (m << 21);
 }
 __host__ __device__ __forceinline__ uint32_t bf_index(uint64_t h) { return uint32_t(h) & uint32_t(kBfBits - 1); }
 

@@ -16,22 +16,24 @@
 // The reference's rope (vector<seqNode>) is kept literally in global memory and mutated by
 // lane 0 with the reference's own slot arithmetic, because its low-complexity rollback
 // (:1038-1100) leaves holes whose position decides what the writer emits.  Hashing never walks
-// the rope: the k window characters live in a shared-memory ring and the characters ahead of
-// the tail cursor in a shared-memory look-ahead buffer refilled from the rope.
+// the rope: the window and the characters ahead of the tail cursor live in a shared-memory
+// stream ring refilled from the rope, window hashes come 32 at a time from XOR scans, and the
+// presence bits of the next 64 windows are cached so that a run of soft-masked positions costs
+// one filter lookup phase per position.
 #include "gp_common.cuh"
 #include "gp_kernels.cuh"
 
 namespace gp {
 
 constexpr int kEditWarps = 4;
-constexpr uint32_t kABuf = 128; // look-ahead ring (power of two)
-constexpr uint32_t kRing = 64;  // window ring (power of two, >= 32)
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct Cur {
   uint32_t pos, idx; // (seq_i, node_index) of the reference
   EdNode n;          // cached nodes[idx]; type -2 when idx is past the vector
 };
+
+constexpr uint32_t kVBuf = 256; // stream ring (power of two)
 
 struct WS {
   char* seq;
@@ -45,12 +47,20 @@ struct WS {
   uint32_t max_ins, max_del;
   int mode, mask;
   Cur h, t, m;
-  HashState hs;
-  uint32_t rh;     // ring head
-  uint32_t a0, an; // look-ahead window [a0, a0+an)
-  bool exhausted;  // refilling hit the end of the stream
-  unsigned char* ring;
-  unsigned char* abuf;
+  HashState hs;      // hash of the current window (valid inside the trigger handler)
+  // the stream around the window: vb[i & 255] = character with absolute stream index i;
+  // [hp, hp+k) is the window, [hp+k, ve) the characters ahead of the tail cursor
+  unsigned char* vb;
+  uint32_t hp, ve;
+  bool exhausted;    // refilling hit the end of the stream
+  // two blocks of 32 windows starting at absolute index B (lane j: windows B+j and B+32+j)
+  bool blk_valid;
+  uint32_t B;
+  uint64_t f0, r0, f1, r1;
+  uint64_t pres;     // bit i: window B+i is in the filter
+  uint64_t acc;      // bit i: character B+k+i exists and is an accepted base
+  uint64_t exist;    // bit i: character B+k+i exists
+  uint64_t samp;     // bit kk: kk % jump == 0 && kk < k
   int err;
   uint32_t lane;
   uint32_t n_trig, n_edit, n_mask, n_roll;
@@ -87,9 +97,19 @@ __device__ __forceinline__ void st_node(EdNode* p, const EdNode& n)
   *reinterpret_cast<int4*>(p) = make_int4(n.type, int(n.s), int(n.e), int(n.c));
 }
 
-__device__ __forceinline__ bool bf_contains(const WS& w, const HashState& h)
+// rotate both halves right by s (inverse of srol)
+__device__ __forceinline__ uint64_t sror(uint64_t v, uint32_t s)
+{
+  const uint32_t a = s % 31u, b = s % 33u;
+  uint64_t hi = v >> 33, lo = v & 0x1FFFFFFFFULL;
+  hi = ((hi >> a) | (hi << (31u - a))) & 0x7FFFFFFFULL;
+  lo = ((lo >> b) | (lo << (33u - b))) & 0x1FFFFFFFFULL;
+  return (hi << 33) | lo;
+}
+
+__device__ __forceinline__ bool bf_contains(const WS& w, uint64_t fh, uint64_t rh)
 { // btllib KmerBloomFilter::contains with the four ntHash values (ntedit.cpp:1470)
-  const uint64_t b = h.fh + h.rh;
+  const uint64_t b = fh + rh;
   uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
   h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
   const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
@@ -97,6 +117,7 @@ __device__ __forceinline__ bool bf_contains(const WS& w, const HashState& h)
   const uint32_t w2 = __ldg(w.bf + (n2 >> 5)), w3 = __ldg(w.bf + (n3 >> 5));
   return ((w0 >> (n0 & 31u)) & (w1 >> (n1 & 31u)) & (w2 >> (n2 & 31u)) & (w3 >> (n3 & 31u)) & 1u) != 0u;
 }
+__device__ __forceinline__ bool bf_contains(const WS& w, const HashState& h) { return bf_contains(w, h.fh, h.rh); }
 
 // ---- rope cursors (getCharacter :667-678, increment :681-699) -------------------------
 __device__ __forceinline__ void cur_load(const WS& w, Cur& c)
@@ -125,57 +146,95 @@ __device__ __forceinline__ void cur_increment(const WS& w, Cur& c)
     if (c.n.type == 0) c.pos = c.n.s;
   }
 }
+// `steps` increments; inside a draft range they collapse to one addition
+__device__ __forceinline__ void cur_advance(const WS& w, Cur& c, uint32_t steps)
+{
+  while (steps) {
+    if (c.n.type == 0 && c.pos < c.n.e) {
+      const uint32_t d = min(steps, c.n.e - c.pos);
+      c.pos += d;
+      steps -= d;
+    } else {
+      cur_increment(w, c);
+      steps--;
+    }
+  }
+}
 __device__ __forceinline__ bool cur_dead(const WS& w, const Cur& c) { return c.pos >= w.len || c.idx >= w.nn; }
 
-__device__ __forceinline__ uint32_t ring_at(const WS& w, uint32_t j) { return w.ring[(w.rh + j) & (kRing - 1)]; }
-__device__ __forceinline__ uint32_t ahead_at(const WS& w, uint32_t j) { return w.abuf[(w.a0 + j) & (kABuf - 1)]; }
+__device__ __forceinline__ uint32_t v_at(const WS& w, uint32_t abs_i) { return w.vb[abs_i & (kVBuf - 1)]; }
+__device__ __forceinline__ uint32_t ring_at(const WS& w, uint32_t j) { return v_at(w, w.hp + j); }
+__device__ __forceinline__ uint32_t ahead_at(const WS& w, uint32_t j) { return v_at(w, w.hp + w.k + j); }
+__device__ __forceinline__ uint32_t ahead_count(const WS& w) { return w.ve - (w.hp + w.k); }
 
-// Refill the look-ahead buffer by walking the rope from the materialisation cursor exactly as
-// successive roll() calls would move the tail cursor (:958-966).
-__device__ void ahead_fill(WS& w, uint32_t want)
+// Extend the stream buffer to absolute index `upto` by walking the rope from the
+// materialisation cursor exactly as successive roll() calls would move the tail cursor (:958-966).
+__device__ void stream_fill(WS& w, uint32_t upto)
 {
-  while (w.an < want && !w.exhausted) {
+  if (w.ve >= upto || w.exhausted) return;
+  while (w.ve < upto && !w.exhausted) {
     if (cur_dead(w, w.m)) { w.exhausted = true; break; }
     if (w.m.n.type == 0 && w.m.pos < w.m.n.e && w.m.pos + 1 < w.len) {
-      uint32_t run = min(min(w.m.n.e, w.len - 1) - w.m.pos, min(want - w.an, 32u));
-      if (w.lane < run) w.abuf[(w.a0 + w.an + w.lane) & (kABuf - 1)] = (unsigned char)w.seq[w.m.pos + 1 + w.lane];
+      const uint32_t run = min(min(w.m.n.e, w.len - 1) - w.m.pos, min(upto - w.ve, 32u));
+      if (w.lane < run) w.vb[(w.ve + w.lane) & (kVBuf - 1)] = (unsigned char)w.seq[w.m.pos + 1 + w.lane];
       w.m.pos += run;
-      w.an += run;
+      w.ve += run;
       continue;
     }
     cur_increment(w, w.m);
     if (cur_dead(w, w.m)) { w.exhausted = true; break; }
-    if (w.lane == 0) w.abuf[(w.a0 + w.an) & (kABuf - 1)] = (unsigned char)cur_char(w, w.m);
-    w.an++;
+    if (w.lane == 0) w.vb[w.ve & (kVBuf - 1)] = (unsigned char)cur_char(w, w.m);
+    w.ve++;
   }
   __syncwarp();
 }
-__device__ __forceinline__ void ahead_reset(WS& w)
+
+__device__ __forceinline__ uint64_t xor_scan_incl(uint64_t v, uint32_t lane)
 {
-  w.a0 = 0; w.an = 0; w.exhausted = false;
-  w.m = w.t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t u = __shfl_up_sync(kFull, v, o);
+    if (lane >= (uint32_t)o) v ^= u;
+  }
+  return v;
 }
 
-// One main-loop roll (:939-969 + NTMC64 :304-314).  Returns false when the reference's roll()
-// would; on success `in` is the incoming character.
-__device__ bool roll_main(WS& w, uint32_t& in)
+// Hash and look up the 32 windows that start at absolute indices Bp .. Bp+31 (lane j: window
+// Bp+j).  ntHash is XOR-linear in the per-base seeds: with U_i = srol^(62-i)(seed(c_i)) and
+// W_i = srol^i(cseed(c_i)) over the 63 characters c_i = stream[Bp+i], a window's forward hash
+// is sror^(63-j-k) of the XOR of U over its k characters and its reverse hash sror^j of the
+// XOR of W, so two 64-element XOR scans give all 32 windows (nthash.hpp:100-119 restated).
+__device__ void compute_block(const WS& w, uint32_t Bp, uint64_t& fh, uint64_t& rh, uint32_t& pres, uint32_t& acc,
+                              uint32_t& exist)
 {
-  if (cur_dead(w, w.h)) return false;
-  if (w.an == 0) ahead_fill(w, 64);
-  const uint32_t out = ring_at(w, 0);
-  cur_increment(w, w.h);
-  if (cur_dead(w, w.t)) return false;
-  if (w.an == 0) return false; // tail cursor cannot advance
-  in = ahead_at(w, 0);
-  cur_increment(w, w.t);
-  hs_roll(w.hs, w.k, out, in);
-  __syncwarp();
-  if (w.lane == 0) w.ring[(w.rh + w.k) & (kRing - 1)] = (unsigned char)in;
-  w.rh = (w.rh + 1) & (kRing - 1);
-  w.a0 = (w.a0 + 1) & (kABuf - 1);
-  w.an--;
-  __syncwarp();
-  return true;
+  const uint32_t lane = w.lane, k = w.k;
+  const uint32_t a0 = Bp + lane, a1 = Bp + lane + 32;
+  const uint32_t c0 = a0 < w.ve ? v_at(w, a0) : 0u;
+  const uint32_t c1 = (a1 < w.ve && lane < 31) ? v_at(w, a1) : 0u;
+  uint64_t u0 = srol(seed_of_char(c0), 62 - lane), u1 = lane < 31 ? srol(seed_of_char(c1), 30 - lane) : 0ull;
+  uint64_t x0 = srol(cseed_of_char(c0), lane), x1 = srol(cseed_of_char(c1), lane + 32);
+  u0 = xor_scan_incl(u0, lane); u1 = xor_scan_incl(u1, lane);
+  x0 = xor_scan_incl(x0, lane); x1 = xor_scan_incl(x1, lane);
+  u1 ^= __shfl_sync(kFull, u0, 31);
+  x1 ^= __shfl_sync(kFull, x0, 31);
+  // exclusive prefix at j (= inclusive at j-1) and inclusive prefix at j+k-1
+  uint64_t pu = __shfl_up_sync(kFull, u0, 1), px = __shfl_up_sync(kFull, x0, 1);
+  if (lane == 0) { pu = 0; px = 0; }
+  const uint32_t e = lane + k - 1; // 0..62
+  const uint64_t eu_lo = __shfl_sync(kFull, u0, e & 31u), eu_hi = __shfl_sync(kFull, u1, e & 31u);
+  const uint64_t ex_lo = __shfl_sync(kFull, x0, e & 31u), ex_hi = __shfl_sync(kFull, x1, e & 31u);
+  const uint64_t su = (e < 32 ? eu_lo : eu_hi) ^ pu;
+  const uint64_t sx = (e < 32 ? ex_lo : ex_hi) ^ px;
+  fh = sror(su, 63 - lane - k);
+  rh = sror(sx, lane);
+  const bool wexists = Bp + lane + k <= w.ve;
+  const bool present = wexists && bf_contains(w, fh, rh);
+  const uint32_t ca = Bp + k + lane;
+  const bool cex = ca < w.ve;
+  const bool cacc = cex && is_accepted(v_at(w, ca));
+  pres = __ballot_sync(kFull, present);
+  acc = __ballot_sync(kFull, cacc);
+  exist = __ballot_sync(kFull, cex);
 }
 
 // ---- lane-0 rope surgery ---------------------------------------------------------------
@@ -450,6 +509,7 @@ __device__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint
 {
   const uint32_t ntry = num_tries(w.max_ins);
   const uint32_t k = w.k;
+  const uint32_t an = ahead_count(w);
   uint32_t best_key = 0; // (support << 12) | order+1 for modes 1/2; mode 0 keeps the smallest order
   uint32_t first_key = 0xffffffffu;
   for (uint32_t i = w.lane; i < ntry; i += 32) {
@@ -483,12 +543,12 @@ __device__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint
     const uint32_t nd = num_deletions + w.lane;
     HashState t = w.hs;
     uint32_t present = 0;
-    if (nd - 1 < w.an) { // the character that follows the deleted run must exist
+    if (nd - 1 < an) { // the character that follows the deleted run must exist
       hs_changelast(t, k, draft_char, ahead_at(w, nd - 1)); // :1190-1197
       if (bf_contains(w, t)) present++;                     // :1201-1203
       for (uint32_t kk = 1; kk + 2 <= k; kk++) {            // :1204-1220
         const uint32_t ai = nd - 1 + kk;
-        if (ai >= w.an) break; // roll() fails: end of contig
+        if (ai >= an) break; // roll() fails: end of contig
         hs_roll(t, k, ring_at(w, kk - 1), ahead_at(w, ai));
         if (kk % w.jump == 0 && bf_contains(w, t)) present++;
       }
@@ -508,10 +568,8 @@ __device__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint
   }
   if (best_key == 0 && first_key == 0xffffffffu) return false;
   uint32_t order, support;
-  if (w.mode == 0) { // first good indel wins (:1338-1344, :1377-1382)
+  if (w.mode == 0) { // first good indel wins (:1338-1344, :1377-1382); its support is only recorded
     order = first_key;
-    // its support: recompute from the lane that owns it is unnecessary -- support is only
-    // recorded, never compared again in mode 0
     support = 1;
   } else {
     order = (best_key & 0xfffu) - 1;
@@ -524,7 +582,7 @@ __device__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint
   return true;
 }
 
-// makeEdit, :972-1154.  Returns false when the contig cannot continue (buffer overflow).
+// makeEdit, :972-1154
 __device__ void make_edit(WS& w, uint32_t draft_char, const Best& best)
 {
   const uint32_t k = w.k;
@@ -592,6 +650,16 @@ __device__ void make_edit(WS& w, uint32_t draft_char, const Best& best)
     w.t.idx = t_idx; w.t.pos = t_seq; w.h.idx = h_idx; w.h.pos = h_seq;
   }
   __syncwarp();
+  if (best.type == 0) {
+    // soft-mask (or nothing): the rope shape, the cursors and every window hash are unchanged
+    if (w.mask) {
+      if (w.lane == 0) w.vb[(w.hp + k - 1) & (kVBuf - 1)] = (unsigned char)to_lower(draft_char);
+      w.n_mask++;
+      cur_load(w, w.t);
+      __syncwarp();
+    }
+    return;
+  }
   w.nn = __shfl_sync(kFull, w.nn, 0);
   w.err = __shfl_sync(kFull, w.err, 0);
   w.t.idx = __shfl_sync(kFull, w.t.idx, 0);
@@ -604,31 +672,25 @@ __device__ void make_edit(WS& w, uint32_t draft_char, const Best& best)
   found = __shfl_sync(kFull, int(found), 0) != 0;
   cur_load(w, w.t);
   cur_load(w, w.h);
+  w.blk_valid = false; // the window's last character changed: every cached hash is stale
   if (reseeded) {
     w.n_roll++;
-    if (found) { // re-seed window, hash and look-ahead from the k-mer the reference found
-      w.hs.fh = 0; w.hs.rh = 0;
-      for (uint32_t i = 0; i < k; i++) w.hs.fh = srol1(w.hs.fh) ^ seed_of_char(kmer[i]);
-      for (uint32_t i = 0; i < k; i++) w.hs.rh = srol1(w.hs.rh) ^ cseed_of_char(kmer[k - 1 - i]);
-      if (w.lane < k) w.ring[(w.rh + w.lane) & (kRing - 1)] = kmer[w.lane];
-      __syncwarp();
-    }
-    ahead_reset(w);
+    if (found && w.lane < k) w.vb[(w.hp + w.lane) & (kVBuf - 1)] = kmer[w.lane]; // window the reference re-seeded from
+    w.ve = w.hp + k; w.exhausted = false; w.m = w.t;
+    __syncwarp();
     return;
   }
-  if (best.type != 0 || w.mask) {
-    hs_changelast(w.hs, k, draft_char, new_last); // :1028, :1106, :1122-1129, :1145
-    if (w.lane == 0) w.ring[(w.rh + k - 1) & (kRing - 1)] = (unsigned char)new_last;
-    __syncwarp();
-  }
-  if (best.type == 0) w.n_mask += w.mask ? 1u : 0u; else w.n_edit++;
-  if (stream_changed) ahead_reset(w);
+  if (w.lane == 0) w.vb[(w.hp + k - 1) & (kVBuf - 1)] = (unsigned char)new_last;
+  w.n_edit++;
+  if (stream_changed) { w.ve = w.hp + k; w.exhausted = false; w.m = w.t; }
+  __syncwarp();
 }
 
 // One contig through one k: kmerizeAndCorrect, :1414-1771.  Result is left in the rope.
 __device__ void edit_round(WS& w)
 {
   const uint32_t k = w.k, lane = w.lane, len = w.len;
+  if (len == 0) { w.nn = 0; return; }
   // findFirstAcceptedKmer(0), :392-413: smallest i with [i, i+k) accepted and i + k < len
   uint32_t h0 = len - 1;
   {
@@ -636,91 +698,82 @@ __device__ void edit_round(WS& w)
     bool found = false;
     for (uint32_t base = 0; base + 1 < len && !found; base += 32) {
       const uint32_t e = base + lane;
-      const bool acc = (e + 1 < len) && is_accepted((unsigned char)w.seq[e]);
-      const uint32_t bits = __ballot_sync(kFull, acc);
+      const bool a = (e + 1 < len) && is_accepted((unsigned char)w.seq[e]);
+      const uint32_t bits = __ballot_sync(kFull, a);
+      if (bits == 0xffffffffu && run + 32 < k) { run += 32; continue; }
       for (uint32_t i = 0; i < 32; i++) {
         if ((bits >> i) & 1u) { run++; if (run >= k) { h0 = base + i + 1 - k; found = true; break; } }
         else run = 0;
       }
     }
   }
-  if (len == 0) { w.nn = 0; return; }
   // root node (:1451-1456)
   if (lane == 0) { EdNode root = { 0, 0, len - 1, 0 }; st_node(w.nd, root); }
   w.nn = 1;
   __syncwarp();
   if (uint64_t(h0) + k - 1 >= len) return; // no seed: the do-loop breaks at once (:1463)
-  // seed k-mer (:1441-1444)
-  w.hs.fh = 0; w.hs.rh = 0;
-  for (uint32_t i = 0; i < k; i++) w.hs.fh = srol1(w.hs.fh) ^ seed_of_char((unsigned char)w.seq[h0 + i]);
-  for (uint32_t i = 0; i < k; i++) w.hs.rh = srol1(w.hs.rh) ^ cseed_of_char((unsigned char)w.seq[h0 + k - 1 - i]);
-  w.rh = 0;
-  if (lane < k) w.ring[lane] = (unsigned char)w.seq[h0 + lane];
+  // seed window (:1441-1444); absolute stream indices start at the draft position
+  w.hp = h0;
+  if (lane < k) w.vb[(h0 + lane) & (kVBuf - 1)] = (unsigned char)w.seq[h0 + lane];
+  w.ve = h0 + k;
+  w.exhausted = false;
   w.h.pos = h0; w.h.idx = 0; cur_load(w, w.h);
   w.t.pos = h0 + k - 1; w.t.idx = 0; cur_load(w, w.t);
-  ahead_reset(w);
+  w.m = w.t;
+  w.blk_valid = false;
+  w.samp = 0;
+  for (uint32_t kk = 0; kk < k; kk += w.jump) w.samp |= 1ull << kk;
+  const uint64_t kbits = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
   __syncwarp();
 
   for (;;) {
     if (w.err) return;
     if (uint64_t(w.h.pos) + k - 1 >= len) break; // :1463
-    ahead_fill(w, 32 + k + 12);
-    // ---- scan: windows 0..31 from the current state ----
-    // stage the next 32 incoming characters behind the window so that ring_at(j) is the
-    // outgoing character of roll j even when j >= k (k < 32)
-    if (lane < w.an) w.ring[(w.rh + k + lane) & (kRing - 1)] = (unsigned char)ahead_at(w, lane);
-    __syncwarp();
-    HashState mine = w.hs, run = w.hs;
-    for (uint32_t j = 0; j < 32; j++) {
-      if (j < w.an) hs_roll(run, k, ring_at(w, j), ahead_at(w, j));
-      if (lane == j + 1) mine = run;
+    if (!w.blk_valid) {
+      w.B = w.hp;
+      stream_fill(w, w.B + 106);
+      uint32_t p0, a0, e0, p1, a1, e1;
+      compute_block(w, w.B, w.f0, w.r0, p0, a0, e0);
+      compute_block(w, w.B + 32, w.f1, w.r1, p1, a1, e1);
+      w.pres = uint64_t(p0) | (uint64_t(p1) << 32);
+      w.acc = uint64_t(a0) | (uint64_t(a1) << 32);
+      w.exist = uint64_t(e0) | (uint64_t(e1) << 32);
+      w.blk_valid = true;
     }
-    // lane j: window j exists when j rolls were possible
-    const bool exists = lane <= w.an;
-    const bool absent = exists && !bf_contains(w, mine);
-    const bool bad = (lane < w.an) && !is_accepted(ahead_at(w, lane));
-    const bool endw = w.exhausted && lane == w.an; // window checked, then roll() fails
-    const uint32_t ev = __ballot_sync(kFull, absent | bad | endw);
-    uint32_t adv;
-    HashState at;
-    if (ev == 0) {
-      adv = 32;
-      at = run; // state after 32 rolls
-    } else {
-      adv = __ffs(ev) - 1;
-      at.fh = __shfl_sync(kFull, mine.fh, adv);
-      at.rh = __shfl_sync(kFull, mine.rh, adv);
+    uint32_t j = w.hp - w.B;
+    if (j >= 32) {
+      if (j >= 64) { w.blk_valid = false; continue; }
+      w.f0 = w.f1; w.r0 = w.r1;
+      w.pres >>= 32; w.acc >>= 32; w.exist >>= 32;
+      w.B += 32; j -= 32;
+      stream_fill(w, w.B + 106);
+      uint32_t p1, a1, e1;
+      compute_block(w, w.B + 32, w.f1, w.r1, p1, a1, e1);
+      w.pres |= uint64_t(p1) << 32; w.acc |= uint64_t(a1) << 32; w.exist |= uint64_t(e1) << 32;
     }
-    const bool trig = __shfl_sync(kFull, int(absent), adv & 31u) != 0 && ev != 0;
-    // advance the real state by `adv` rolls
-    if (adv > 0) {
-      for (uint32_t i = 0; i < adv; i++) { cur_increment(w, w.h); cur_increment(w, w.t); }
-      w.rh = (w.rh + adv) & (kRing - 1);
-      w.a0 = (w.a0 + adv) & (kABuf - 1);
-      w.an -= adv;
-      w.hs = at;
-      __syncwarp();
+    // ---- scan the rest of block 0: first absent window, non-accepted incoming base or end ----
+    const uint32_t span = 32 - j;
+    const uint64_t evbits = ((~w.pres | ~w.acc) >> j) & (span >= 64 ? ~0ull : ((1ull << span) - 1ull));
+    const uint32_t adv = evbits ? uint32_t(__ffsll((long long)evbits) - 1) : span;
+    if (adv) {
+      cur_advance(w, w.h, adv);
+      cur_advance(w, w.t, adv);
+      w.hp += adv;
+      j += adv;
     }
-    if (ev == 0) continue;
+    if (!evbits) continue;
     if (uint64_t(w.h.pos) + k - 1 >= len) break; // loop-top check of the iteration we landed on
 
-    if (trig) {
+    if (!((w.pres >> j) & 1ull)) {
       // ---- the window is absent: look-ahead confirmation (:1470-1523) ----
       w.n_trig++;
-      ahead_fill(w, k + 12);
       const uint32_t draft_char = to_upper(ring_at(w, k - 1)); // :1480
-      const bool have_k = w.an >= k;
-      const bool lane_ok = lane >= k || (lane < w.an && is_accepted(ahead_at(w, lane)));
-      const bool all_ok = __all_sync(kFull, lane_ok) && have_k;
+      const bool all_ok = ((w.acc >> j) & kbits) == kbits;      // k more accepted bases exist
       if (all_ok) {
-        HashState mine2 = w.hs, r2 = w.hs;
-        for (uint32_t kk = 0; kk < k; kk++) {
-          hs_roll(r2, k, ring_at(w, kk), ahead_at(w, kk));
-          if (lane == kk) mine2 = r2;
-        }
-        const bool miss = lane < k && (lane % w.jump == 0) && !bf_contains(w, mine2);
-        const uint32_t check_missing = __popc(__ballot_sync(kFull, miss));
+        const uint32_t check_missing = (uint32_t)__popcll((~w.pres >> (j + 1)) & w.samp);
         if (float(check_missing) >= w.thrM) { // :1517-1523
+          w.hs.fh = __shfl_sync(kFull, w.f0, j);
+          w.hs.rh = __shfl_sync(kFull, w.r0, j);
           uint32_t num_deletions = 1;       // :1526
           Best best = { 0, 0, 0, 0, 0, 0 };
           uint32_t packed;
@@ -729,37 +782,43 @@ __device__ void edit_round(WS& w)
           HashState g = w.hs;
           const uint32_t my_base = (packed >> (8 * (lane & 3u))) & 255u;
           hs_changelast(g, k, draft_char, my_base);
-          const bool gate = lane < nb && (bf_contains(w, g) || w.mode == 2);
+          const bool gate = lane < nb && (w.mode == 2 || bf_contains(w, g));
           const uint32_t gates = __ballot_sync(kFull, gate);
-          for (uint32_t b = 0; b < nb; b++) {
-            if (!((gates >> b) & 1u)) continue;
-            const uint32_t sub_base = (packed >> (8 * b)) & 255u;
-            HashState m3 = w.hs, r3 = w.hs;
-            hs_changelast(r3, k, draft_char, sub_base);
-            for (uint32_t kk = 0; kk < k; kk++) { // :1585-1606
-              const uint32_t out = kk + 1 < k ? ring_at(w, kk) : sub_base;
-              hs_roll(r3, k, out, ahead_at(w, kk));
-              if (lane == kk) m3 = r3;
-            }
-            const bool hit = lane < k && (lane % w.jump == 0) && bf_contains(w, m3);
-            const uint32_t present = __popc(__ballot_sync(kFull, hit));
-            if (float(present) >= w.thrE) { // :1621-1626
-              if (present >= best.support) { best.type = 1; best.sub_base = sub_base; best.support = present; }
-              if (w.mode == 0 || w.mode == 1) continue; // :1680-1682
-            }
-            if (w.mode == 2 || best.type != 1) { // :1686
-              if (try_indels(w, draft_char, sub_base, num_deletions, best)) {
-                if (w.mode == 0 || w.mode == 1) break; // :1707-1709
+          if (gates) {
+            // windows j+1 .. j+k of the unedited stream, lane i <- window j+1+i
+            const uint32_t wi = j + 1 + lane; // <= 63 for lane < k
+            const uint64_t bf_lo = __shfl_sync(kFull, w.f0, wi & 31u), bf_hi = __shfl_sync(kFull, w.f1, wi & 31u);
+            const uint64_t br_lo = __shfl_sync(kFull, w.r0, wi & 31u), br_hi = __shfl_sync(kFull, w.r1, wi & 31u);
+            const uint64_t base_f = wi < 32 ? bf_lo : bf_hi, base_r = wi < 32 ? br_lo : br_hi;
+            for (uint32_t b = 0; b < nb; b++) {
+              if (!((gates >> b) & 1u)) continue;
+              const uint32_t sub_base = (packed >> (8 * b)) & 255u;
+              // replacing the tail base changes window j+1+i by one rotated seed difference per
+              // strand (:1585-1606); window j+k no longer contains the base
+              uint64_t cf = base_f, cr = base_r;
+              if (lane + 1 < k) {
+                cf ^= srol(seed_of_char(draft_char) ^ seed_of_char(sub_base), 1 + lane);
+                cr ^= srol(cseed_of_char(draft_char) ^ cseed_of_char(sub_base), k - 2 - lane);
+              }
+              const bool hit = lane < k && (lane % w.jump == 0) && bf_contains(w, cf, cr);
+              const uint32_t present = __popc(__ballot_sync(kFull, hit));
+              if (float(present) >= w.thrE) { // :1621-1626
+                if (present >= best.support) { best.type = 1; best.sub_base = sub_base; best.support = present; }
+                if (w.mode == 0 || w.mode == 1) continue; // :1680-1682
+              }
+              if (w.mode == 2 || best.type != 1) { // :1686
+                if (try_indels(w, draft_char, sub_base, num_deletions, best)) {
+                  if (w.mode == 0 || w.mode == 1) break; // :1707-1709
+                }
               }
             }
+            if (lane == 0) {
+              // a substitution trial was made and reverted with the UPPER-cased base (:1609-1615)
+              if (w.t.n.type == 0) w.seq[w.t.pos] = (char)draft_char;
+              else if (w.t.n.type == 1) { EdNode x = w.t.n; x.c = draft_char; st_node(w.nd + w.t.idx, x); }
+            }
+            __syncwarp();
           }
-          if (gates != 0u && lane == 0) {
-            // a substitution trial was made and reverted with the UPPER-cased base (:1609-1615)
-            if (w.t.n.type == 0) w.seq[w.t.pos] = (char)draft_char;
-            else if (w.t.n.type == 1) { EdNode x = w.t.n; x.c = draft_char; st_node(w.nd + w.t.idx, x); }
-          }
-          __syncwarp();
-          cur_load(w, w.t);
           make_edit(w, draft_char, best); // :1715-1736
           if (w.err) return;
         }
@@ -769,10 +828,14 @@ __device__ void edit_round(WS& w)
     long long target = -1;
     bool alive = true;
     do {
-      uint32_t in;
-      if (roll_main(w, in)) {
-        if (!is_accepted(in)) target = (long long)w.t.pos + (long long)k;
-      } else { alive = false; break; }
+      if (cur_dead(w, w.h)) { alive = false; break; }      // roll(), :952
+      stream_fill(w, w.hp + k + 1);
+      cur_increment(w, w.h);
+      if (cur_dead(w, w.t) || w.ve <= w.hp + k) { alive = false; break; } // :958-965
+      const uint32_t in = v_at(w, w.hp + k);
+      cur_increment(w, w.t);
+      w.hp++;
+      if (!is_accepted(in)) target = (long long)w.t.pos + (long long)k;
     } while (target >= 0 && (long long)w.t.pos != target);
     if (!alive) break;
   }
@@ -804,8 +867,7 @@ __device__ uint32_t emit_rope(const WS& w, char* dst, uint32_t cap, int& err)
 
 __global__ void __launch_bounds__(kEditWarps * 32) edit_kernel(EditParams p)
 {
-  __shared__ unsigned char ring_sh[kEditWarps][kRing];
-  __shared__ unsigned char ahead_sh[kEditWarps][kABuf];
+  __shared__ unsigned char vb_sh[kEditWarps][kVBuf];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   unsigned long long n_trig = 0, n_edit = 0, n_mask = 0, n_roll = 0;
   for (;;) {
@@ -821,8 +883,7 @@ __global__ void __launch_bounds__(kEditWarps * 32) edit_kernel(EditParams p)
     bool dropped = false;
     WS w;
     w.lane = lane;
-    w.ring = ring_sh[warp];
-    w.abuf = ahead_sh[warp];
+    w.vb = vb_sh[warp];
     w.nd = p.nodes + p.node_off[ci];
     w.ncap = uint32_t(p.node_off[ci + 1] - p.node_off[ci]);
     w.max_ins = p.max_insertions; w.max_del = p.max_deletions; w.jump = p.jump;
