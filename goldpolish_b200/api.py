@@ -29,7 +29,8 @@ class _Config(C.Structure):
                 ("k", C.c_uint32 * GP_MAX_K), ("max_insertions", C.c_uint32), ("max_deletions", C.c_uint32),
                 ("mode", C.c_int32), ("mask", C.c_int32), ("missing_ratio", C.c_float),
                 ("edit_ratio", C.c_float), ("jump", C.c_uint32), ("min_contig_len", C.c_uint32),
-                ("max_resident_batches", C.c_uint32)]
+                ("max_resident_batches", C.c_uint32), ("use_ratio", C.c_int32),
+                ("missing_threshold", C.c_float), ("edit_threshold", C.c_float)]
 
 
 class _Stats(C.Structure):

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -120,6 +121,7 @@ int validate_config(const gp_config& c, std::string& why)
   if (c.max_deletions > 10) { why = "max_deletions must be <= 10"; return GP_ERR_ARG; }
   if (c.mode < 0 || c.mode > 2) { why = "mode must be 0..2"; return GP_ERR_ARG; }
   if (c.jump == 0) { why = "jump must be >= 1"; return GP_ERR_ARG; }
+  if (!c.use_ratio && (!(c.missing_threshold > 0) || !(c.edit_threshold > 0))) { why = "x / y thresholds must be > 0"; return GP_ERR_ARG; }
   return GP_OK;
 }
 
@@ -136,6 +138,8 @@ void gp_default_config(gp_config* cfg)
   cfg->k[0] = 32; cfg->k[1] = 28; cfg->k[2] = 24; cfg->k[3] = 20; // scripts/goldpolish:189-190
   cfg->max_insertions = 5; cfg->max_deletions = 5; cfg->mode = 1; cfg->mask = 1; // scripts/goldpolish-ntedit:27
   cfg->missing_ratio = 0.5f; cfg->edit_ratio = 0.5f;
+  cfg->use_ratio = 1;                                        // GoldPolish always passes -X/-Y
+  cfg->missing_threshold = 5.0f; cfg->edit_threshold = 9.0f; // ntedit.cpp:88-89
   cfg->jump = 3; cfg->min_contig_len = 100; // ntedit.cpp:94,85
   cfg->max_resident_batches = 0;
 }
@@ -576,9 +580,15 @@ static int polish_launch(gp_ctx* ctx)
     // (ntedit.cpp:1521-1523, 1624-1626 / 1335-1337, 1228-1230, 2024-2025)
     const float kf = static_cast<float>(c.k[i]);
     const float jf = static_cast<float>(c.jump);
-    p.thr_missing[i] = (kf / jf) * c.missing_ratio;
-    p.thr_edit[i] = (kf / jf) * c.edit_ratio;
-    p.thr_del[i] = (1 + (kf / jf)) * c.edit_ratio;
+    if (c.use_ratio) {
+      p.thr_missing[i] = (kf / jf) * c.missing_ratio;
+      p.thr_edit[i] = (kf / jf) * c.edit_ratio;
+      p.thr_del[i] = (1 + (kf / jf)) * c.edit_ratio;
+    } else { // -x / -y form (ntedit.cpp:1519-1520, 1622-1623, 1333-1334, 1226-1227)
+      p.thr_missing[i] = kf / c.missing_threshold;
+      p.thr_edit[i] = kf / c.edit_threshold;
+      p.thr_del[i] = kf / c.edit_threshold;
+    }
     p.insertion_cap[i] = static_cast<unsigned>(kf * 1.5f);
   }
   p.max_insertions = c.max_insertions; p.max_deletions = c.max_deletions; p.jump = c.jump;

@@ -1,0 +1,465 @@
+// Host side of the GoldPolish drop-ins: everything that decides WHICH bytes reach the GPU.
+//
+// New C++ written against the behaviour of bcgsc/goldpolish (cited per function):
+//   SeqIndex      src/seqindex.cpp:12-142, src/seqindex.hpp:59-102
+//   Mappings      src/mappings.cpp:15-330
+//   selection     src/goldpolish_targeted_bfs.cpp:86-133
+//   .bf container btllib::KmerBloomFilter::save / load (btllib is not in the reference tree:
+//                 layout UNPINNED, kept in bf_format below and nowhere else)
+//   FASTA reader  kseq.h semantics as used by subprojects/ntedit/ntedit.cpp:1829-1842
+#pragma once
+
+#include "../../include/goldpolish_b200.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include <fcntl.h>
+#include <unistd.h>
+
+namespace gph {
+
+[[noreturn]] inline void die(const std::string& msg)
+{
+  std::cerr << "[goldpolish_b200] [ERROR] " << msg << std::endl;
+  std::exit(EXIT_FAILURE);
+}
+inline void info(const std::string& msg)
+{
+  if (!std::getenv("GP_QUIET")) std::cerr << "[goldpolish_b200] [INFO] " << msg << std::endl;
+}
+inline void check_gp(gp_ctx* ctx, int rc, const char* what)
+{
+  if (rc != GP_OK) die(std::string(what) + ": " + gp_last_error(ctx));
+}
+inline bool endswith(const std::string& s, const std::string& suf)
+{
+  return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// SeqIndex: id -> (byte offset of the sequence line, length, average phred)
+// ---------------------------------------------------------------------------------------
+struct SeqRecord {
+  uint64_t start = 0, len = 0;
+  double phred = 0.0;
+};
+
+class SeqIndex {
+public:
+  // Build from a FASTA with exactly 2 lines per record or a FASTQ with exactly 4
+  // (src/seqindex.cpp:12-66).  The first duplicate id wins (unordered_map::emplace).
+  static SeqIndex build(const std::string& seqs_path)
+  {
+    SeqIndex ix;
+    ix.seqs_path = seqs_path;
+    std::ifstream f(seqs_path);
+    if (!f.good()) die("cannot open " + seqs_path);
+    const bool fastq = f.peek() == '@';
+    std::string line, id;
+    long i = 0, byte = 0, id_end = 0, seq_start = 0, seq_len = 0;
+    while (bool(std::getline(f, line))) {
+      const long endbyte = byte + long(line.size());
+      const long phase = fastq ? i % 4 : i % 2;
+      if (phase == 0) {
+        id_end = endbyte;
+        const std::string first = line.substr(0, line.find(' ')); // split(line, " ")[0]
+        id = first.empty() ? std::string() : first.substr(1);
+        if (fastq) id = id.substr(0, id.find('\t')); // :33
+      } else if (phase == 1) {
+        seq_start = id_end + 1;
+        seq_len = endbyte - id_end - 1;
+        if (!fastq) ix.add(id, uint64_t(seq_start), uint64_t(seq_len), 0.0);
+      } else if (fastq && phase == 3) {
+        // calc_phred_avg(line, 0, line.size() - 1): the last quality character is left out (:45)
+        double ph = 0.0;
+        const size_t n = line.size() > 0 ? line.size() - 1 : 0;
+        if (n > 0) {
+          size_t sum = 0;
+          for (size_t q = 0; q < n; q++) sum += size_t((unsigned char)line[q]);
+          ph = double(sum) / double(n) - 33.0;
+        }
+        ix.add(id, uint64_t(seq_start), uint64_t(seq_len), ph);
+      }
+      byte = endbyte + 1;
+      i++;
+    }
+    return ix;
+  }
+
+  // id \t start \t len \t phred, default ostream formatting (src/seqindex.cpp:68-84)
+  void save(const std::string& path) const
+  {
+    std::ofstream o(path);
+    for (const auto& id : order) {
+      const auto& r = recs.at(id);
+      o << id << '\t' << r.start << '\t' << r.len << '\t' << r.phred << '\n';
+    }
+  }
+
+  // whitespace separated tokens, four per record (src/seqindex.cpp:86-125)
+  static SeqIndex load(const std::string& index_path, const std::string& seqs_path)
+  {
+    SeqIndex ix;
+    ix.seqs_path = seqs_path;
+    std::ifstream f(index_path);
+    if (!f.good()) die("cannot open " + index_path);
+    std::string tok, id;
+    uint64_t start = 0, len = 0;
+    unsigned long i = 0;
+    while (bool(f >> tok)) {
+      switch (i % 4) {
+      case 0: id = tok; break;
+      case 1: start = std::stoull(tok); break;
+      case 2: len = std::stoull(tok); break;
+      default: ix.add(id, start, len, std::stod(tok)); break;
+      }
+      i++;
+    }
+    return ix;
+  }
+
+  bool exists(const std::string& id) const { return recs.find(id) != recs.end(); }
+  const SeqRecord& at(const std::string& id) const
+  {
+    const auto it = recs.find(id);
+    if (it == recs.end()) die("sequence id not in index: " + id); // unordered_map::at would throw
+    return it->second;
+  }
+  size_t size() const { return recs.size(); }
+
+  // whole sequence line, as SeqIndex::get_seq<1> returns it (src/seqindex.hpp:59-102)
+  void read_seq(const std::string& id, std::string& out) const
+  {
+    const SeqRecord& r = at(id);
+    if (r.len >= 20ull * 1024ull * 1024ull) die("Seq size over buffer size."); // :88-90
+    if (fd < 0) {
+      fd = open(seqs_path.c_str(), O_RDONLY);
+      if (fd < 0) die("cannot open " + seqs_path);
+    }
+    out.resize(r.len);
+    size_t got = 0;
+    while (got < r.len) {
+      const ssize_t n = pread(fd, &out[got], r.len - got, off_t(r.start + got));
+      if (n <= 0) die("read did not read all bytes.");
+      got += size_t(n);
+    }
+  }
+
+  std::string seqs_path;
+  std::vector<std::string> order; // insertion order (save() of the reference iterates a hash map)
+
+private:
+  void add(const std::string& id, uint64_t start, uint64_t len, double phred)
+  {
+    if (recs.find(id) != recs.end()) return;
+    SeqRecord r;
+    r.start = start; r.len = len; r.phred = phred;
+    recs.emplace(id, r);
+    order.push_back(id);
+  }
+  std::unordered_map<std::string, SeqRecord> recs;
+  mutable int fd = -1;
+};
+
+// ---------------------------------------------------------------------------------------
+// Mappings: target id -> mapped read ids, first-seen order, de-duplicated
+// ---------------------------------------------------------------------------------------
+class Mappings {
+public:
+  // src/mappings.cpp:15-35: type by file suffix; the minimizer filter only for ntLink triples
+  Mappings(const std::string& path, const SeqIndex& targets, unsigned mx_min, unsigned mx_max, double mx_max_per_10kbp)
+  {
+    if (endswith(path, ".sam") || endswith(path, ".bam")) load_lines(path, targets, 3);
+    else if (endswith(path, ".paf")) load_lines(path, targets, 6);
+    else {
+      load_ntlink(path, targets, mx_min);
+      filter(mx_max_per_10kbp, mx_min, mx_max, targets);
+    }
+    seen.clear();
+    mx.clear();
+  }
+
+  const std::vector<std::string>& get(const std::string& target) const
+  {
+    static const std::vector<std::string> empty;
+    const auto it = maps.find(target);
+    return it == maps.end() ? empty : it->second;
+  }
+  const std::unordered_map<std::string, std::vector<std::string>>& all() const { return maps; }
+
+private:
+  void add(const std::string& read, const std::string& target, const SeqIndex& targets, unsigned m)
+  { // load_mapping, src/mappings.cpp:37-72
+    if (!targets.exists(target)) return;
+    auto& s = seen[target];
+    if (s.find(read) != s.end()) return;
+    s.insert(read);
+    maps[target].push_back(read);
+    mx[target].push_back(m);
+  }
+
+  void load_ntlink(const std::string& path, const SeqIndex& targets, unsigned mx_min)
+  { // :74-110
+    std::ifstream f(path);
+    if (!f.good()) die("cannot open " + path);
+    std::string tok, read, target;
+    unsigned long i = 0;
+    while (bool(f >> tok)) {
+      switch (i % 3) {
+      case 0: read = tok; break;
+      case 1: target = tok; break;
+      default: {
+        const unsigned long m = std::stoul(tok);
+        if (m >= mx_min) add(read, target, targets, unsigned(m));
+      }
+      }
+      i++;
+    }
+  }
+
+  // SAM (target column 3) / PAF (target column 6): query column 1; '@' lines skipped; a short
+  // line keeps the ids of the previous one, as the reference's loop does (:112-215)
+  void load_lines(const std::string& path, const SeqIndex& targets, int target_col)
+  {
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) die("cannot open " + path);
+    char* line = nullptr;
+    size_t n = 0;
+    std::string tok, read, target;
+    while (getline(&line, &n, f) > 0) {
+      if (line[0] == '@') continue;
+      std::stringstream ss(line);
+      int col = 1;
+      while (bool(ss >> tok)) {
+        if (col == 1) read = tok;
+        else if (col == target_col) target = tok;
+        col++;
+      }
+      add(read, target, targets, 0);
+    }
+    std::free(line);
+    std::fclose(f);
+  }
+
+  static unsigned count_ge(const std::vector<unsigned>& v, unsigned thr)
+  {
+    unsigned c = 0;
+    for (const auto x : v) c += x >= thr ? 1u : 0u;
+    return c;
+  }
+
+  void filter(double max_per_10kbp, unsigned mx_min, unsigned mx_max, const SeqIndex& targets)
+  { // :230-320
+    if (max_per_10kbp <= 0) die("max_mapped_seqs_per_target_10kbp is not positive.");
+    if (mx_min >= mx_max) die("mx_threshold_min is not smaller than mx_threshold_max.");
+    for (auto& kv : maps) {
+      auto& reads = kv.second;
+      if (reads.empty()) continue;
+      const auto& m = mx.at(kv.first);
+      if (!targets.exists(kv.first)) continue;
+      const int max_reads = int(std::ceil(double(targets.at(kv.first).len) * max_per_10kbp / 10000.0));
+      if (max_reads <= 0) die("max_mapped_seqs <= 0.");
+      int lo = int(mx_min), hi = int(mx_max), thr;
+      if (int(reads.size()) <= max_reads) thr = lo;
+      else if (int(count_ge(m, unsigned(hi))) > max_reads) thr = hi;
+      else {
+        while (hi - lo > 1) {
+          const int mid = (hi + lo) / 2;
+          if (int(count_ge(m, unsigned(mid))) > max_reads) lo = mid; else hi = mid;
+        }
+        thr = hi;
+      }
+      std::vector<std::string> kept;
+      for (size_t i = 0; i < reads.size(); i++)
+        if (int(m[i]) >= thr) kept.push_back(reads[i]);
+      reads.swap(kept);
+    }
+  }
+
+  std::unordered_map<std::string, std::vector<std::string>> maps;
+  std::unordered_map<std::string, std::unordered_set<std::string>> seen;
+  std::unordered_map<std::string, std::vector<unsigned>> mx;
+};
+
+// ---------------------------------------------------------------------------------------
+// read selection for one target (src/goldpolish_targeted_bfs.cpp:95-125)
+// ---------------------------------------------------------------------------------------
+struct Selection {
+  std::vector<std::string> reads; // in fill order
+  int kmer_threshold = 0;
+};
+
+inline Selection select_reads(const std::vector<std::string>& mapped, const SeqIndex& reads_index, uint64_t target_len,
+                              double subsample_max_per_10kbp)
+{
+  Selection sel;
+  const size_t n_adj = std::min<size_t>(mapped.size(), size_t(gp_mappings_cap(target_len, subsample_max_per_10kbp)));
+  std::vector<std::pair<std::string, size_t>> v;
+  v.reserve(mapped.size());
+  for (const auto& id : mapped) v.emplace_back(id, size_t(reads_index.at(id).phred)); // tuple<SeqId, size_t>
+  std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) {
+    return (a.second > b.second) || (a.second == b.second && a.first < b.first);
+  });
+  uint64_t bases = 0;
+  for (size_t i = 0; i < n_adj; i++) bases += reads_index.at(v[i].first).len;
+  sel.kmer_threshold = gp_kmer_threshold(bases);
+  if (sel.kmer_threshold <= 0) die("k-mer threshold must be >0.");
+  for (size_t i = 0; i < n_adj; i++) sel.reads.push_back(v[i].first);
+  return sel;
+}
+
+// ---------------------------------------------------------------------------------------
+// .bf container (btllib KmerBloomFilter).  UNPINNED: see file header.
+// ---------------------------------------------------------------------------------------
+namespace bf_format {
+
+inline const char* signature()
+{
+  const char* s = std::getenv("GP_BF_SIGNATURE");
+  return s ? s : "[BTLKmerBloomFilter_v6]";
+}
+inline const char* hash_fn()
+{
+  const char* s = std::getenv("GP_BF_HASH_FN");
+  return s ? s : "ntHash_v2";
+}
+constexpr unsigned kPlaceholderNewlines = 50;
+
+inline void save(const std::string& path, const uint8_t* payload, size_t bytes, unsigned hash_num, unsigned k)
+{
+  std::ofstream o(path, std::ios::out | std::ios::binary);
+  if (!o.good()) die("cannot write " + path);
+  o << signature() << '\n'
+    << "bytes = " << bytes << '\n'
+    << "hash_fn = \"" << hash_fn() << "\"\n"
+    << "hash_num = " << hash_num << '\n'
+    << "k = " << k << '\n'
+    << "[HeaderEnd]\n";
+  for (unsigned i = 0; i < kPlaceholderNewlines; i++) {
+    if (i == 1) o << "  <binary data>";
+    o << '\n';
+  }
+  o.write(reinterpret_cast<const char*>(payload), std::streamsize(bytes));
+}
+
+struct Header {
+  size_t bytes = 0;
+  unsigned hash_num = 0, k = 0;
+};
+
+// Reads any "[BTLKmerBloomFilter_v*]" header; the payload is the LAST `bytes` bytes of the file,
+// which is robust to the number of placeholder lines a given btllib version writes.
+inline Header load(const std::string& path, std::vector<uint8_t>& payload)
+{
+  std::ifstream f(path, std::ios::in | std::ios::binary);
+  if (!f.good()) die("cannot open " + path);
+  Header h;
+  std::string line;
+  bool sig = false, end = false;
+  while (bool(std::getline(f, line))) {
+    if (line == "[HeaderEnd]") { end = true; break; }
+    if (!sig) {
+      if (line.rfind("[BTLKmerBloomFilter_v", 0) != 0) die("Bloom filter file supplied (-r) is incorrect: " + path);
+      sig = true;
+      continue;
+    }
+    const auto eq = line.find('=');
+    if (eq == std::string::npos) continue;
+    auto trim = [](std::string s) {
+      const auto b = s.find_first_not_of(" \t\"");
+      const auto e = s.find_last_not_of(" \t\"\r");
+      return b == std::string::npos ? std::string() : s.substr(b, e - b + 1);
+    };
+    const auto key = trim(line.substr(0, eq)), val = trim(line.substr(eq + 1));
+    if (key == "bytes") h.bytes = std::stoull(val);
+    else if (key == "hash_num") h.hash_num = unsigned(std::stoul(val));
+    else if (key == "k") h.k = unsigned(std::stoul(val));
+  }
+  if (!end || h.bytes == 0) die("Bloom filter file supplied (-r) is incorrect: " + path);
+  f.seekg(0, std::ios::end);
+  const auto size = size_t(f.tellg());
+  if (size < h.bytes) die("truncated Bloom filter payload: " + path);
+  payload.resize(h.bytes);
+  f.seekg(std::streamoff(size - h.bytes), std::ios::beg);
+  f.read(reinterpret_cast<char*>(payload.data()), std::streamsize(h.bytes));
+  return h;
+}
+
+} // namespace bf_format
+
+// ---------------------------------------------------------------------------------------
+// FASTA/FASTQ reader with kseq semantics: gz or plain, multi-line sequences, name = text up
+// to the first whitespace, comment = rest of the header line
+// ---------------------------------------------------------------------------------------
+struct FastaRecord {
+  std::string name, comment, seq;
+};
+
+inline std::vector<FastaRecord> read_fasta(const std::string& path)
+{
+  gzFile f = gzopen(path.c_str(), "r");
+  if (!f) die("cannot open " + path);
+  std::string data;
+  char buf[1 << 16];
+  int n;
+  while ((n = gzread(f, buf, sizeof buf)) > 0) data.append(buf, size_t(n));
+  gzclose(f);
+  std::vector<FastaRecord> recs;
+  size_t i = 0;
+  const size_t N = data.size();
+  while (i < N) {
+    while (i < N && data[i] != '>' && data[i] != '@') i++; // kseq skips to the next header mark
+    if (i >= N) break;
+    const bool fq = data[i] == '@';
+    size_t e = data.find('\n', i);
+    if (e == std::string::npos) e = N;
+    std::string hdr = data.substr(i + 1, e - i - 1);
+    if (!hdr.empty() && hdr.back() == '\r') hdr.pop_back();
+    FastaRecord r;
+    const size_t sp = hdr.find_first_of(" \t");
+    r.name = hdr.substr(0, sp);
+    if (sp != std::string::npos) {
+      size_t c0 = sp + 1;
+      r.comment = hdr.substr(c0);
+    }
+    i = e + 1;
+    while (i < N && data[i] != '>' && data[i] != '+' && data[i] != '@') {
+      size_t le = data.find('\n', i);
+      if (le == std::string::npos) le = N;
+      for (size_t q = i; q < le; q++) {
+        const unsigned char c = (unsigned char)data[q];
+        if (c > 32) r.seq.push_back((char)c); // kseq keeps printable, non-space characters
+      }
+      i = le + 1;
+    }
+    if (fq && i < N && data[i] == '+') { // skip the quality block (same length as the sequence)
+      size_t le = data.find('\n', i);
+      i = le == std::string::npos ? N : le + 1;
+      size_t got = 0;
+      while (i < N && got < r.seq.size()) {
+        size_t le2 = data.find('\n', i);
+        if (le2 == std::string::npos) le2 = N;
+        got += le2 - i;
+        i = le2 + 1;
+      }
+    }
+    recs.push_back(std::move(r));
+  }
+  return recs;
+}
+
+} // namespace gph

@@ -66,6 +66,9 @@ typedef struct {
   uint32_t jump;                   /* -j */
   uint32_t min_contig_len;         /* -z */
   uint32_t max_resident_batches;   /* cap on batches whose counting filters live at once; 0 = fit to free memory */
+  int32_t use_ratio;               /* 1: thresholds from -X/-Y (default); 0: from -x/-y below */
+  float missing_threshold;         /* -x */
+  float edit_threshold;            /* -y */
 } gp_config;
 
 /* one read handed to fill_bfs: index into the uploaded read store + the target's kmer_threshold */

@@ -120,6 +120,25 @@ def main():
                     case["batches"][b]["server_bf_sha256"] = shas
                     assert shas == case["batches"][b]["bf_sha256"], "plan_batches disagrees with the reference server"
         filt["cases"].append(case)
+    # ntLink-style triples: the minimizer filter (mappings.cpp:230-320) with a tight cap, s = 100
+    kw = dict(genome_len=50000, seed=14)
+    d = sim.simulate(**kw)
+    nl = {"name": "ntlink_mx", "sim": kw, "bsize": 2, "mx_max": 12.0, "subsample_max": 100.0, "batches": []}
+    with tempfile.TemporaryDirectory(dir="/dev/shm") as w:
+        sim.simulate(write_dir=w, **kw)
+        reads = os.path.join(w, "reads.fq")
+        rd.run_index(os.path.join(w, "draft.fa"), os.path.join(w, "draft.fa.index"))
+        rd.run_index(reads, reads + ".index")
+        with rd.BfServer(os.path.join(w, "bfs"), os.path.join(w, "draft.fa"), os.path.join(w, "draft.fa.index"),
+                         os.path.join(w, "mappings.tsv"), reads, reads + ".index", mx_max=nl["mx_max"],
+                         subsample_max=nl["subsample_max"], threads=4) as srv:
+            for b in range((d.n_contigs + 1) // 2):
+                ids = [d.contig_name(c) for c in range(b * 2, min(b * 2 + 2, d.n_contigs))]
+                paths = srv.build(str(b), ids)
+                pays = [rd.parse_bf(paths[k])[1] for k in KS]
+                nl["batches"].append({"server_bf_sha256": [sha(x) for x in pays],
+                                      "bf_popcount": [int(np.unpackbits(np.frombuffer(x, np.uint8)).sum()) for x in pays]})
+    filt["ntlink"] = nl
     json.dump(filt, open(os.path.join(HERE, "filters.json"), "w"))
 
     # ---- (iii) ntEdit edge cases ----------------------------------------------------------

@@ -1,0 +1,134 @@
+"""The C++ drop-in tools (goldpolish_b200/host): index builder on CPU; FIFO server, ntedit-gr and
+goldpolish-ntedit on the GPU, all against golden vectors minted from the reference's binaries."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, KS, ROOT, ol, sha
+
+BIN = os.path.join(ROOT, "goldpolish_b200", "bin")
+ENV = dict(os.environ, GP_QUIET="1")
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def _tmp():
+    return tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+
+
+def test_index_tool_matches_reference_index():
+    import sim
+    g = _load("filters.json")
+    for case in g["cases"]:
+        with _tmp() as w:
+            d = sim.simulate(write_dir=w, **case["sim"])
+            reads = os.path.join(w, "reads.fq" if d.fastq else "reads.fa")
+            subprocess.check_call([os.path.join(BIN, "goldpolish-index"), reads, reads + ".idx"], env=ENV)
+            got = sha("".join(sorted(open(reads + ".idx").readlines())).encode())
+            assert got == case["reads_index_sha256"], case["name"]
+
+
+def _parse_bf(path):
+    data = open(path, "rb").read()
+    hdr_end = data.index(b"[HeaderEnd]\n")
+    fields = dict(ln.split(" = ") for ln in data[:hdr_end].decode().splitlines()[1:] if " = " in ln)
+    n = int(fields["bytes"])
+    return fields, data[len(data) - n:]
+
+
+@pytest.mark.gpu
+def test_fifo_server_matches_reference_server():
+    import sim
+    from oracle import ref_driver as rd
+    g = _load("filters.json")
+    jobs = [(c, "mappings.paf", 150.0, 40.0) for c in g["cases"][:2]] + [(g["ntlink"], "mappings.tsv", g["ntlink"]["mx_max"], g["ntlink"]["subsample_max"])]
+    for case, mapfile, mx_max, sub in jobs:
+        with _tmp() as w:
+            d = sim.simulate(write_dir=w, **case["sim"])
+            reads = os.path.join(w, "reads.fq" if d.fastq else "reads.fa")
+            for f in (os.path.join(w, "draft.fa"), reads):
+                subprocess.check_call([os.path.join(BIN, "goldpolish-index"), f, f + ".index"], env=ENV)
+            bs = case["bsize"]
+            with rd.BfServer(os.path.join(w, "bfs"), os.path.join(w, "draft.fa"), os.path.join(w, "draft.fa.index"),
+                             os.path.join(w, mapfile), reads, reads + ".index", mx_max=mx_max, subsample_max=sub,
+                             threads=2, binary=os.path.join(BIN, "goldpolish-targeted-bfs"), env=ENV) as srv:
+                for b, rec in enumerate(case["batches"]):
+                    ids = [d.contig_name(c) for c in range(b * bs, min((b + 1) * bs, d.n_contigs))]
+                    paths = srv.build(str(b), ids)
+                    got = []
+                    for k in KS:
+                        fields, pay = _parse_bf(paths[k])
+                        assert int(fields["k"]) == k and int(fields["hash_num"]) == 4 and int(fields["bytes"]) == 524288
+                        got.append(sha(pay))
+                    assert got == rec["server_bf_sha256"], (case["name"], b)
+                    # the per-batch pipes are gone, as after the reference's serve_batch (:144-145)
+                    assert not os.path.exists(os.path.join(w, "bfs", f"{b}-bfs_ready"))
+            assert not os.path.exists(os.path.join(w, "bfs", "batch_name_input"))
+
+
+def _truth_bf_files(w):
+    g = _load("ntedit_cases.json")
+    fs = ol.FilterSet(KS)
+    for _ in range(5):
+        fs.add_read(g["truth"].encode(), 4)
+    paths = []
+    for i, k in enumerate(KS):
+        p = os.path.join(w, f"k{k}.bf")
+        with open(p, "wb") as f:
+            f.write(f'[BTLKmerBloomFilter_v6]\nbytes = 524288\nhash_fn = "ntHash_v2"\nhash_num = 4\nk = {k}\n[HeaderEnd]\n'.encode())
+            f.write(b"\n  <binary data>\n" + b"\n" * 48)
+            f.write(fs.bfs[i].tobytes())
+        paths.append(p)
+    return g, fs, paths
+
+
+@pytest.mark.gpu
+def test_ntedit_gr_cli_matches_reference_binary():
+    cli = _load("ntedit_cli.json")
+    with _tmp() as w:
+        _, _, bfs = _truth_bf_files(w)
+        fa = os.path.join(w, "in.fa")
+        open(fa, "w").write(cli["input_fasta"])
+        subprocess.check_call([os.path.join(BIN, "ntedit-gr"), "-f", fa, "-r", bfs[0], "-d5", "-i5", "-m1", "-X0.5",
+                               "-Y0.5", "-b", os.path.join(w, "out"), "-t1", "-a1"], env=ENV)
+        assert open(os.path.join(w, "out_edited.fa")).read() == cli["edited_fasta"]
+        # error behaviour of ntedit.cpp:346-353,1944-1947: unreadable file / malformed option -> exit 1
+        assert subprocess.call([os.path.join(BIN, "ntedit-gr"), "-f", fa + ".missing", "-r", bfs[0]], env=ENV,
+                               stderr=subprocess.DEVNULL) == 1
+        assert subprocess.call([os.path.join(BIN, "ntedit-gr"), "-f", fa, "-r", bfs[0], "-d", "5x"], env=ENV,
+                               stderr=subprocess.DEVNULL) == 1
+
+
+@pytest.mark.gpu
+def test_goldpolish_ntedit_chain_and_guard():
+    with _tmp() as w:
+        g, fs, bfs = _truth_bf_files(w)
+        names = ["mixed_dense", "subs", "short_80bp", "lowercase"]
+        base = os.path.join(w, "batch")
+        with open(base + ".fa", "w") as f:
+            for n in names:
+                f.write(f">{n} some comment\n{g['cases'][n]['draft']}\n")
+        out = os.path.join(w, "batch.ntedited.fa")
+        subprocess.check_call([os.path.join(BIN, "goldpolish-ntedit"), base, " ".join(bfs), "32 28 24 20", "0.5", "0.5", "1", out],
+                              env=ENV, stdout=subprocess.DEVNULL)
+        want = "".join(f">{n} some comment\n{g['cases'][n]['chain']}\n" for n in names if g["cases"][n]["chain"] is not None)
+        assert os.path.islink(out)
+        assert os.path.basename(os.readlink(out)) == "batch.k32.X0.5.Y0.5_edited.k28.X0.5.Y0.5_edited.k24.X0.5.Y0.5_edited.k20.X0.5.Y0.5_edited.fa"
+        assert open(out).read() == want
+        # guard: a batch whose records are mostly dropped (< 100 bp) falls back to the original file
+        base2 = os.path.join(w, "tiny")
+        with open(base2 + ".fa", "w") as f:
+            for i in range(6):
+                f.write(f">t{i}\n{g['truth'][i * 90:i * 90 + 90]}\n")
+            f.write(f">keep\n{g['truth'][:150]}\n")
+        out2 = os.path.join(w, "tiny.ntedited.fa")
+        subprocess.check_call([os.path.join(BIN, "goldpolish-ntedit"), base2, " ".join(bfs), "32 28 24 20", "0.5", "0.5", "1", out2],
+                              env=ENV, stdout=subprocess.DEVNULL)
+        assert os.readlink(out2) == base2 + ".fa"
