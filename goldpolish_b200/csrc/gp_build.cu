@@ -142,7 +142,11 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
       if (len < k) continue;
       const uint64_t boff = p.read_boff[ent.read_id];
       const uint32_t npos = len - k + 1;
-      for (uint32_t p0 = 0; p0 < npos; p0 += 32) {
+      // One step = 32 consecutive positions.  Steps are software-pipelined: while step i waits
+      // for its counters, step i+1 is already hashed and its counter sectors are prefetched
+      // into L2, so that a lone stream (the tail of a launch) pays L2 latency per step instead
+      // of HBM latency.  Loads of step i+1 are only ISSUED after step i has stored.
+      auto prepare = [&](uint32_t p0, uint32_t (&ci)[4], uint32_t (&bi)[4]) -> bool {
         const uint32_t q = p0 + lane;
         const uint64_t g = boff + q;
         const uint64_t wi = g >> 5;
@@ -154,8 +158,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
         // 2 bit/base window
         const uint64_t w0 = __ldg(p.pk + wi), w1 = __ldg(p.pk + wi + 1);
         const uint64_t w = sh ? ((w0 >> (2 * sh)) | (w1 << (64 - 2 * sh))) : w0;
-
-        uint32_t ci[4] = { 0xFFFFFFF0u, 0xFFFFFFF1u, 0xFFFFFFF2u, 0xFFFFFFF3u }, bi[4], c[4];
+        ci[0] = 0xFFFFFFF0u; ci[1] = 0xFFFFFFF1u; ci[2] = 0xFFFFFFF2u; ci[3] = 0xFFFFFFF3u;
         if (valid) {
           uint64_t fh = 0, rh = 0;
           for (uint32_t m = 0; m < kq; m++) {
@@ -168,8 +171,23 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
           h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
           ci[0] = cbf_index(h0); ci[1] = cbf_index(h1); ci[2] = cbf_index(h2); ci[3] = cbf_index(h3);
           bi[0] = bf_index(h0); bi[1] = bf_index(h1); bi[2] = bf_index(h2); bi[3] = bf_index(h3);
+        }
+        return valid;
+      };
+      uint32_t ci[4], bi[4], c[4], nci[4], nbi[4];
+      bool valid = prepare(0, ci, bi), nvalid = false;
+      if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; j++) c[j] = __ldcg(cbf + ci[j]);
+        for (int j = 0; j < 4; j++) c[j] = __ldcg(cbf + ci[j]);
+      }
+      for (uint32_t p0 = 0; p0 < npos; p0 += 32) {
+        const bool has_next = p0 + 32 < npos;
+        if (has_next) {
+          nvalid = prepare(p0 + 32, nci, nbi);
+          if (nvalid) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(cbf + nci[j]));
+          }
         }
 
         // Which lanes share a counter with a LOWER lane of this step?  Lanes publish themselves
@@ -225,6 +243,15 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
           dep &= dep - 1;
         }
         __syncwarp(); // orders this step's counter stores before the next step's loads
+        if (has_next) {
+          valid = nvalid;
+#pragma unroll
+          for (int j = 0; j < 4; j++) { ci[j] = nci[j]; bi[j] = nbi[j]; }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) c[j] = __ldcg(cbf + ci[j]);
+          }
+        }
       }
     }
   }

@@ -51,6 +51,10 @@ struct WS {
   // the stream around the window: vb[i & 255] = character with absolute stream index i;
   // [hp, hp+k) is the window, [hp+k, ve) the characters ahead of the tail cursor
   unsigned char* vb;
+  // candidate-search tables (shared memory): per-round seed tables and per-call staging
+  const unsigned char* code; // byte -> 0 none, 1 A, 2 C, 3 G, 4 T (either case)
+  uint64_t* seedt;           // [0..4] F, [8..12] F rotated by k, [16..23] R (by c & 7), [24..31] R rotated by k
+  uint64_t* stage;           // [0..31] outF, [32..63] outR, [64..127] inF, [128..191] inRk
   uint32_t hp, ve;
   bool exhausted;    // refilling hit the end of the stream
   // two blocks of 32 windows starting at absolute index B (lane j: windows B+j and B+32+j)
@@ -512,28 +516,70 @@ __device__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint
   const uint32_t an = ahead_count(w);
   uint32_t best_key = 0; // (support << 12) | order+1 for modes 1/2; mode 0 keeps the smallest order
   uint32_t first_key = 0xffffffffu;
-  for (uint32_t i = w.lane; i < ntry; i += 32) {
-    unsigned char s[8];
-    const uint32_t L = insertion_string(index_char, i, s);
-    // the characters that follow the candidate's first base, then the draft base (:1279),
-    // packed so that indexing stays in registers
-    uint64_t tailp = 0;
-    for (uint32_t q = 1; q < L; q++) tailp |= uint64_t(s[q]) << (8 * (q - 1));
-    tailp |= uint64_t(draft_char) << (8 * (L - 1));
-    HashState t = w.hs;
-    hs_changelast(t, k, draft_char, index_char); // :1290
-    uint32_t present = 0;
-    for (uint32_t kk = 0; kk + 1 < k; kk++) { // :1294-1326
-      const uint32_t out = ring_at(w, kk);
-      const uint32_t in = kk < L ? uint32_t(tailp >> (8 * kk)) & 255u : ahead_at(w, kk - L);
-      hs_roll(t, k, out, in);
-      if (kk % w.jump == 0 && bf_contains(w, t)) present++;
+  // Stage what every candidate shares: the outgoing bases E[h..t-1] (their k-rotated forward
+  // seed and plain reverse seed) and the incoming bases ahead of t (plain forward, k-rotated
+  // reverse), so that one roll is four shared-memory loads and a handful of logic ops.
+  {
+    uint64_t* outF = w.stage, *outR = w.stage + 32, *inF = w.stage + 64, *inRk = w.stage + 128;
+    __syncwarp();
+    if (w.lane + 1 < k) {
+      const uint32_t c = ring_at(w, w.lane);
+      outF[w.lane] = w.seedt[8 + w.code[c]];
+      outR[w.lane] = w.seedt[16 + (c & 7u)];
     }
-    if (float(present) >= w.thrE && (w.mode == 0 || present > 0)) { // :1333-1337, :1400
-      const uint32_t order = 2 * i;
-      const uint32_t key = (present << 12) | (order + 1);
-      best_key = max(best_key, key);
-      first_key = min(first_key, order);
+    for (uint32_t q = w.lane; q < 64; q += 32) {
+      const uint32_t c = q < an ? ahead_at(w, q) : 0u;
+      inF[q] = w.seedt[w.code[c]];
+      inRk[q] = w.seedt[24 + (c & 7u)];
+    }
+    __syncwarp();
+    HashState base = w.hs;
+    hs_changelast(base, k, draft_char, index_char); // :1290
+    const uint64_t dF = w.seedt[w.code[draft_char]], dRk = w.seedt[24 + (draft_char & 7u)];
+    // a candidate can no longer qualify once it has missed more samples than the threshold allows
+    const uint32_t nsamp = (k - 2) / w.jump + 1;
+    const uint32_t need = w.thrE > 0.0f ? (uint32_t)ceilf(w.thrE) : 0u;
+    const uint32_t allowed = nsamp >= need ? nsamp - need : 0u;
+    for (uint32_t i = w.lane; i < ntry; i += 32) {
+      const uint32_t L = i < 1 ? 1 : i < 5 ? 2 : i < 21 ? 3 : i < 85 ? 4 : 5;
+      const uint32_t r = i - (L == 1 ? 0 : L == 2 ? 1 : L == 3 ? 5 : L == 4 ? 21 : 85); // base-4 digits of s[1..L-1]
+      HashState t = base;
+      uint32_t present = 0, misses = 0;
+      bool pend = false;
+      uint32_t pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pb0 = 0, pb1 = 0, pb2 = 0, pb3 = 0;
+      for (uint32_t kk = 0; kk + 1 < k; kk++) { // :1294-1326
+        uint64_t inf, inr;
+        if (kk < L) {
+          if (kk + 1 < L) { // next base of the insertion string
+            const uint32_t d = (r >> (2 * (L - 2 - kk))) & 3u;
+            inf = w.seedt[d + 1];
+            inr = w.seedt[24 + ((0x4731u >> (4 * d)) & 7u)];
+          } else { inf = dF; inr = dRk; } // then the draft base (:1279)
+        } else { inf = inF[kk - L]; inr = inRk[kk - L]; }
+        t.fh = srol1(t.fh) ^ inf ^ outF[kk];
+        t.rh = sror1(t.rh ^ inr ^ outR[kk]);
+        if (kk % w.jump == 0) {
+          if (pend) {
+            if (((pw0 >> pb0) & (pw1 >> pb1) & (pw2 >> pb2) & (pw3 >> pb3) & 1u) != 0u) present++; else misses++;
+            if (misses > allowed) { pend = false; break; }
+          }
+          const uint64_t b = t.fh + t.rh;
+          uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
+          h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
+          const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
+          pw0 = __ldg(w.bf + (n0 >> 5)); pw1 = __ldg(w.bf + (n1 >> 5));
+          pw2 = __ldg(w.bf + (n2 >> 5)); pw3 = __ldg(w.bf + (n3 >> 5));
+          pb0 = n0 & 31u; pb1 = n1 & 31u; pb2 = n2 & 31u; pb3 = n3 & 31u;
+          pend = true;
+        }
+      }
+      if (pend && (((pw0 >> pb0) & (pw1 >> pb1) & (pw2 >> pb2) & (pw3 >> pb3) & 1u) != 0u)) present++;
+      if (float(present) >= w.thrE && (w.mode == 0 || present > 0)) { // :1333-1337, :1400
+        const uint32_t order = 2 * i;
+        const uint32_t key = (present << 12) | (order + 1);
+        best_key = max(best_key, key);
+        first_key = min(first_key, order);
+      }
     }
   }
   // deletions num_deletions .. max_del, one per visited insertion index (:1359-1396)
@@ -586,6 +632,17 @@ __device__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint
 __device__ void make_edit(WS& w, uint32_t draft_char, const Best& best)
 {
   const uint32_t k = w.k;
+  if (best.type == 0) {
+    // no fix found (:1131-1146): soft-mask the base when -a1.  The rope shape, both cursors and
+    // every window hash are unchanged, so this touches nothing but the character itself.
+    if (w.mask) {
+      const uint32_t lc = to_lower(draft_char);
+      if (w.t.n.type == 0) { if (w.lane == 0) w.seq[w.t.pos] = (char)lc; }
+      else if (w.t.n.type == 1) { w.t.n.c = lc; if (w.lane == 0) st_node(w.nd + w.t.idx, w.t.n); }
+      w.n_mask++;
+    }
+    return;
+  }
   uint32_t new_last = 0;   // character now sitting at the tail of the window
   bool stream_changed = false, reseeded = false, found = false;
   __shared__ unsigned char kmer_sh[kEditWarps][32];
@@ -650,16 +707,6 @@ __device__ void make_edit(WS& w, uint32_t draft_char, const Best& best)
     w.t.idx = t_idx; w.t.pos = t_seq; w.h.idx = h_idx; w.h.pos = h_seq;
   }
   __syncwarp();
-  if (best.type == 0) {
-    // soft-mask (or nothing): the rope shape, the cursors and every window hash are unchanged
-    if (w.mask) {
-      if (w.lane == 0) w.vb[(w.hp + k - 1) & (kVBuf - 1)] = (unsigned char)to_lower(draft_char);
-      w.n_mask++;
-      cur_load(w, w.t);
-      __syncwarp();
-    }
-    return;
-  }
   w.nn = __shfl_sync(kFull, w.nn, 0);
   w.err = __shfl_sync(kFull, w.err, 0);
   w.t.idx = __shfl_sync(kFull, w.t.idx, 0);
@@ -721,6 +768,17 @@ __device__ void edit_round(WS& w)
   w.t.pos = h0 + k - 1; w.t.idx = 0; cur_load(w, w.t);
   w.m = w.t;
   w.blk_valid = false;
+  // seed tables for this k (nthash.hpp:21-63): plain and rotated by k, both strands
+  if (lane < 5) {
+    const uint64_t f = lane == 0 ? 0ull : seed_of_code(lane - 1);
+    w.seedt[lane] = f;
+    w.seedt[8 + lane] = srol(f, k);
+  }
+  if (lane >= 8 && lane < 16) {
+    const uint64_t r = cseed_of_char(lane - 8);
+    w.seedt[16 + lane - 8] = r;
+    w.seedt[24 + lane - 8] = srol(r, k);
+  }
   w.samp = 0;
   for (uint32_t kk = 0; kk < k; kk += w.jump) w.samp |= 1ull << kk;
   const uint64_t kbits = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
@@ -765,6 +823,52 @@ __device__ void edit_round(WS& w)
     if (uint64_t(w.h.pos) + k - 1 >= len) break; // loop-top check of the iteration we landed on
 
     if (!((w.pres >> j) & 1ull)) {
+      // ---- run of absent windows: speculate that the next positions end in "no fix" ----
+      // A soft-mask changes no hash, so for up to 10 consecutive positions the look-ahead
+      // counts come from the cached bits and all their candidate gates (:1565-1570) are
+      // looked up in ONE phase (lane = 3 * position + candidate).  Positions are then
+      // committed in order until one needs the full search, a skip, or the end of the block.
+      {
+        const uint32_t g = lane / 3u, bsel = lane - 3u * g, wj = j + g;
+        const bool in_range = lane < 30u && wj < 32u;
+        const uint32_t wjc = wj & 31u;
+        bool attempt_l = false;
+        if (in_range && !((w.pres >> wjc) & 1ull) && (((w.acc >> wjc) & kbits) == kbits))
+          attempt_l = float((uint32_t)__popcll((~w.pres >> (wjc + 1)) & w.samp)) >= w.thrM;
+        const uint32_t dch = to_upper(v_at(w, w.hp + g + k - 1));
+        uint32_t pk;
+        const uint32_t nbl = polish_bases(dch, pk);
+        HashState gh;
+        gh.fh = __shfl_sync(kFull, w.f0, wjc);
+        gh.rh = __shfl_sync(kFull, w.r0, wjc);
+        bool gate_l = false;
+        if (attempt_l && bsel < nbl) {
+          if (w.mode == 2) gate_l = true;
+          else { hs_changelast(gh, k, dch, (pk >> (8 * bsel)) & 255u); gate_l = bf_contains(w, gh); }
+        }
+        const uint32_t gate_bits = __ballot_sync(kFull, gate_l);
+        uint32_t done = 0;
+        for (uint32_t s = 0; s < 10; s++) {
+          const uint32_t wq = j + s;
+          if (wq >= 32 || !((w.acc >> wq) & 1ull)) break;       // skip / end: generic path
+          if (uint64_t(w.h.pos) + k - 1 >= len) break;            // :1463
+          if (!((w.pres >> wq) & 1ull)) {
+            const bool att = (((w.acc >> wq) & kbits) == kbits) &&
+                             float((uint32_t)__popcll((~w.pres >> (wq + 1)) & w.samp)) >= w.thrM;
+            if (att) {
+              if ((gate_bits >> (3 * s)) & 7u) break;             // a candidate is present: full search
+              Best none = { 0, 0, 0, 0, 0, 0 };
+              make_edit(w, to_upper(v_at(w, w.hp + k - 1)), none);
+            }
+            w.n_trig++;
+          }
+          cur_increment(w, w.h);
+          cur_increment(w, w.t);
+          w.hp++;
+          done++;
+        }
+        if (done) continue;
+      }
       // ---- the window is absent: look-ahead confirmation (:1470-1523) ----
       w.n_trig++;
       const uint32_t draft_char = to_upper(ring_at(w, k - 1)); // :1480
@@ -812,11 +916,9 @@ __device__ void edit_round(WS& w)
                 }
               }
             }
-            if (lane == 0) {
-              // a substitution trial was made and reverted with the UPPER-cased base (:1609-1615)
-              if (w.t.n.type == 0) w.seq[w.t.pos] = (char)draft_char;
-              else if (w.t.n.type == 1) { EdNode x = w.t.n; x.c = draft_char; st_node(w.nd + w.t.idx, x); }
-            }
+            // a substitution trial was made and reverted with the UPPER-cased base (:1609-1615)
+            if (w.t.n.type == 0) { if (lane == 0) w.seq[w.t.pos] = (char)draft_char; }
+            else if (w.t.n.type == 1) { w.t.n.c = draft_char; if (lane == 0) st_node(w.nd + w.t.idx, w.t.n); }
             __syncwarp();
           }
           make_edit(w, draft_char, best); // :1715-1736
@@ -868,6 +970,14 @@ __device__ uint32_t emit_rope(const WS& w, char* dst, uint32_t cap, int& err)
 __global__ void __launch_bounds__(kEditWarps * 32) edit_kernel(EditParams p)
 {
   __shared__ unsigned char vb_sh[kEditWarps][kVBuf];
+  __shared__ unsigned char code_sh[256];
+  __shared__ uint64_t seedt_sh[kEditWarps][32];
+  __shared__ uint64_t stage_sh[kEditWarps][192];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+    const uint32_t lc = i | 0x20u;
+    code_sh[i] = lc == 'a' ? 1 : lc == 'c' ? 2 : lc == 'g' ? 3 : lc == 't' ? 4 : 0;
+  }
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   unsigned long long n_trig = 0, n_edit = 0, n_mask = 0, n_roll = 0;
   for (;;) {
@@ -884,6 +994,9 @@ __global__ void __launch_bounds__(kEditWarps * 32) edit_kernel(EditParams p)
     WS w;
     w.lane = lane;
     w.vb = vb_sh[warp];
+    w.code = code_sh;
+    w.seedt = seedt_sh[warp];
+    w.stage = stage_sh[warp];
     w.nd = p.nodes + p.node_off[ci];
     w.ncap = uint32_t(p.node_off[ci + 1] - p.node_off[ci]);
     w.max_ins = p.max_insertions; w.max_del = p.max_deletions; w.jump = p.jump;
