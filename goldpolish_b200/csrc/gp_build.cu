@@ -12,6 +12,9 @@
 #include "gp_common.cuh"
 #include "gp_kernels.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace gp {
 
 // ------------------------------------------------------------------------------------
@@ -64,6 +67,7 @@ void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint6
 constexpr int kBuildWarps = 8;
 constexpr int kTabBits = 9;
 constexpr int kTabSlots = 1 << kTabBits;
+constexpr size_t kBuildSmem = 2 * 8 * 256 * sizeof(uint64_t) + size_t(kBuildWarps) * kTabSlots * sizeof(uint32_t);
 
 // byte tables for hashing 4 packed bases at a time; k-independent because groups are counted
 // from the k-mer end for the forward strand and from its start for the reverse strand.
@@ -103,34 +107,203 @@ __device__ __forceinline__ void cbf_bf_apply(uint8_t* __restrict__ cbf, uint32_t
   }
 }
 
+// ---- pieces shared by the two build kernels -------------------------------------------------
+
+// Per-lane registers that hold 32 consecutive packed / mask words of the current read (one word
+// per lane) and the 32 that follow.  Every read starts on a word boundary, so step s (32 k-mer
+// starts) needs words s and s+1 -- the same for all lanes: they are handed out by shuffle, and
+// the look-ahead registers are only touched on the last step of a chunk, 31 steps after their load.
+struct SeqRegs {
+  uint64_t pk_cur, pk_nxt;
+  uint32_t nm_cur, nm_nxt;
+};
+__device__ __forceinline__ void seq_load_chunk(const BuildParams& p, uint64_t wbase, uint32_t nwords, uint32_t chunk,
+                                               uint32_t lane, uint64_t& pkw, uint32_t& nmw)
+{
+  const uint32_t wq = chunk * 32u + lane;
+  const bool in = wq <= nwords; // one spare word is always allocated behind a read
+  pkw = in ? __ldg(p.pk + wbase + wq) : 0ull;
+  nmw = in ? __ldg(p.nm + wbase + wq) : 0xFFFFFFFFu;
+}
+
+struct StreamConsts {
+  uint32_t k, kq, kmask;
+  uint64_t mul1, mul2, mul3;
+};
+__device__ __forceinline__ StreamConsts stream_consts(uint32_t k)
+{
+  StreamConsts c;
+  c.k = k; c.kq = k >> 2;
+  c.kmask = k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
+  c.mul1 = 1ull ^ (uint64_t(k) * kMultiSeed);
+  c.mul2 = 2ull ^ (uint64_t(k) * kMultiSeed);
+  c.mul3 = 3ull ^ (uint64_t(k) * kMultiSeed);
+  return c;
+}
+
+template<int KQ>
+__device__ __forceinline__ void hash_bytes(const uint64_t* __restrict__ tf, const uint64_t* __restrict__ tr, uint64_t w,
+                                           uint64_t& fh, uint64_t& rh)
+{
+  uint64_t f[KQ], r[KQ];
+#pragma unroll
+  for (int m = 0; m < KQ; m++) {
+    const uint32_t b = uint32_t(w >> (8 * m)) & 255u;
+    f[m] = tf[((KQ - 1 - m) << 8) | b];
+    r[m] = tr[(m << 8) | b];
+  }
+  fh = 0; rh = 0;
+#pragma unroll
+  for (int m = 0; m < KQ; m++) { fh ^= f[m]; rh ^= r[m]; }
+}
+
+// Hash the k-mer that starts at position p0 + lane of the current read: validity from the mask
+// window, 4 bases per table lookup (all 16 lookups independent), the 3 derived hashes, then the
+// counter indices (mod 10485760) and filter bit indices (mod 2^22).
+__device__ __forceinline__ bool hash_step(const uint64_t* __restrict__ tf, const uint64_t* __restrict__ tr,
+                                          const SeqRegs& sr, uint32_t step, uint32_t p0, uint32_t npos, uint32_t lane,
+                                          const StreamConsts& sc, uint32_t (&ci)[4], uint32_t (&bi)[4])
+{
+  const uint32_t sidx = step & 31u;
+  const uint64_t w0 = __shfl_sync(0xffffffffu, sr.pk_cur, sidx);
+  const uint32_t m0 = __shfl_sync(0xffffffffu, sr.nm_cur, sidx);
+  uint64_t w1;
+  uint32_t m1;
+  if (sidx == 31u) { w1 = __shfl_sync(0xffffffffu, sr.pk_nxt, 0); m1 = __shfl_sync(0xffffffffu, sr.nm_nxt, 0); }
+  else { w1 = __shfl_sync(0xffffffffu, sr.pk_cur, sidx + 1); m1 = __shfl_sync(0xffffffffu, sr.nm_cur, sidx + 1); }
+  const uint32_t mw = __funnelshift_r(m0, m1, lane);
+  const bool valid = (p0 + lane < npos) && ((mw & sc.kmask) == 0u);
+  const uint64_t w = lane ? ((w0 >> (2 * lane)) | (w1 << (64 - 2 * lane))) : w0;
+  ci[0] = 0xFFFFFFF0u; ci[1] = 0xFFFFFFF1u; ci[2] = 0xFFFFFFF2u; ci[3] = 0xFFFFFFF3u;
+  bi[0] = bi[1] = bi[2] = bi[3] = 0u;
+  if (valid) {
+    uint64_t fh, rh;
+    switch (sc.kq) { // k is uniform per stream: pick the fully unrolled lookup (no per-byte branches)
+    case 8: hash_bytes<8>(tf, tr, w, fh, rh); break;
+    case 7: hash_bytes<7>(tf, tr, w, fh, rh); break;
+    case 6: hash_bytes<6>(tf, tr, w, fh, rh); break;
+    case 5: hash_bytes<5>(tf, tr, w, fh, rh); break;
+    case 4: hash_bytes<4>(tf, tr, w, fh, rh); break;
+    case 3: hash_bytes<3>(tf, tr, w, fh, rh); break;
+    case 2: hash_bytes<2>(tf, tr, w, fh, rh); break;
+    default: hash_bytes<1>(tf, tr, w, fh, rh); break;
+    }
+    const uint64_t h0 = fh + rh;
+    uint64_t h1 = h0 * sc.mul1, h2 = h0 * sc.mul2, h3 = h0 * sc.mul3;
+    h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
+    ci[0] = cbf_index(h0); ci[1] = cbf_index(h1); ci[2] = cbf_index(h2); ci[3] = cbf_index(h3);
+    bi[0] = bf_index(h0); bi[1] = bf_index(h1); bi[2] = bf_index(h2); bi[3] = bf_index(h3);
+  }
+  return valid;
+}
+
+// Commit one step in stream order.  `c` holds the counters loaded for the valid lanes.
+// Which lanes share a counter with a LOWER lane of this step?  Lanes publish themselves in a
+// small direct-mapped table of lane masks (slot = hash of the counter index); slot sharing only
+// nominates candidates, the counter indices themselves are then compared through shuffles, so
+// the answer is exact whatever the table size.  Independent lanes update in parallel, the rest
+// are replayed one at a time in lane order against the updated counters.
+__device__ __forceinline__ void commit_step(uint8_t* __restrict__ cbf, uint32_t* __restrict__ bf, uint32_t* tab,
+                                            uint32_t lane, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4],
+                                            uint32_t (&c)[4], uint32_t thr, unsigned long long& ops,
+                                            unsigned long long& serial)
+{
+  uint32_t sl[4];
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      sl[j] = (ci[j] * 2654435761u) >> (32 - kTabBits);
+      atomicOr(&tab[sl[j]], 1u << lane);
+    }
+  }
+  __syncwarp();
+  uint32_t lower = 0;
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) lower |= tab[sl[j]];
+    lower &= (1u << lane) - 1u;
+  }
+  __syncwarp();
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) tab[sl[j]] = 0u; // leave the table clean for the next step
+  }
+  bool indep = true;
+  const uint32_t rounds = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(lower));
+  for (uint32_t it = 0; it < rounds; it++) {
+    const uint32_t l = lower ? (uint32_t)__ffs(lower) - 1u : lane;
+    lower &= lower - 1u;
+    const uint32_t o0 = __shfl_sync(0xffffffffu, ci[0], l), o1 = __shfl_sync(0xffffffffu, ci[1], l);
+    const uint32_t o2 = __shfl_sync(0xffffffffu, ci[2], l), o3 = __shfl_sync(0xffffffffu, ci[3], l);
+    if (l != lane) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) indep &= (ci[j] != o0) & (ci[j] != o1) & (ci[j] != o2) & (ci[j] != o3);
+    }
+  }
+  if (valid) {
+    if (indep) cbf_bf_apply(cbf, bf, ci, bi, c, thr);
+    ops++;
+  }
+  uint32_t dep = __ballot_sync(0xffffffffu, valid && !indep);
+  while (dep) {
+    __syncwarp();
+    const uint32_t l = __ffs(dep) - 1;
+    if (lane == l) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) c[j] = __ldcg(cbf + ci[j]);
+      cbf_bf_apply(cbf, bf, ci, bi, c, thr);
+      serial++;
+    }
+    dep &= dep - 1;
+  }
+  __syncwarp(); // orders this step's counter stores before the next step's loads
+}
+
+__device__ __forceinline__ void flush_counters(const BuildParams& p, uint32_t lane, unsigned long long ops,
+                                               unsigned long long serial)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ops += __shfl_xor_sync(0xffffffffu, ops, o);
+    serial += __shfl_xor_sync(0xffffffffu, serial, o);
+  }
+  if (lane == 0) {
+    if (ops) atomicAdd(p.counters + 0, ops);
+    if (serial) atomicAdd(p.counters + 1, serial);
+  }
+}
+
+// ---- one warp per stream --------------------------------------------------------------------
+// Steps are software-pipelined: while step i waits for its counters, step i+1 is already hashed
+// and its counter sectors are prefetched into L2.  Loads of step i+1 are only ISSUED after step
+// i has stored.  Define GP_BUILD_TIMING to print the per-phase cycle budget of long streams.
 __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildParams p)
 {
-  __shared__ uint64_t tf[8 * 256];
-  __shared__ uint64_t tr[8 * 256];
-  __shared__ uint32_t tabs[kBuildWarps][kTabSlots];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* tf = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* tr = tf + 8 * 256;
+  uint32_t* tabs = reinterpret_cast<uint32_t*>(tr + 8 * 256);
   fill_hash_tables(tf, tr);
-  for (uint32_t i = threadIdx.x; i < kBuildWarps * kTabSlots; i += blockDim.x) (&tabs[0][0])[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < (blockDim.x >> 5) * kTabSlots; i += blockDim.x) tabs[i] = 0u;
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
-  uint32_t* tab = tabs[warp];
+  uint32_t* tab = tabs + warp * kTabSlots;
   unsigned long long ops = 0, serial = 0;
+#ifdef GP_BUILD_TIMING
+  long long tim[4] = { 0, 0, 0, 0 };
+#endif
 
   for (;;) {
     uint32_t slot = 0;
     if (lane == 0) slot = atomicAdd(p.next_stream, 1u);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot >= p.n_streams) break;
-    const uint32_t sid = p.stream_order[slot];     // local stream id within this wave
+    const uint32_t sid = p.stream_order[slot]; // local stream id within this wave
     const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk;
     const uint32_t batch = p.first_batch + lb;
-    const uint32_t k = p.k[ki];
-    const uint32_t kq = k >> 2; // bytes per k-mer
-    const uint32_t kmask = k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
-    const uint64_t mul1 = 1ull ^ (uint64_t(k) * kMultiSeed);
-    const uint64_t mul2 = 2ull ^ (uint64_t(k) * kMultiSeed);
-    const uint64_t mul3 = 3ull ^ (uint64_t(k) * kMultiSeed);
+    const StreamConsts sc = stream_consts(p.k[ki]);
     uint8_t* __restrict__ cbf = p.cbf_pool + uint64_t(sid) * kCbfCounters;
     uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
 
@@ -139,110 +312,43 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
       const gp_read_entry ent = p.entries[e];
       const uint32_t thr = ent.kmer_threshold - 2u + ki; // utils.cpp:108,121
       const uint32_t len = p.read_len[ent.read_id];
-      if (len < k) continue;
-      const uint64_t boff = p.read_boff[ent.read_id];
-      const uint32_t npos = len - k + 1;
-      // One step = 32 consecutive positions.  Steps are software-pipelined: while step i waits
-      // for its counters, step i+1 is already hashed and its counter sectors are prefetched
-      // into L2, so that a lone stream (the tail of a launch) pays L2 latency per step instead
-      // of HBM latency.  Loads of step i+1 are only ISSUED after step i has stored.
-      auto prepare = [&](uint32_t p0, uint32_t (&ci)[4], uint32_t (&bi)[4]) -> bool {
-        const uint32_t q = p0 + lane;
-        const uint64_t g = boff + q;
-        const uint64_t wi = g >> 5;
-        const uint32_t sh = uint32_t(g & 31u);
-        // 1 bit/base validity window
-        const uint32_t m0 = __ldg(p.nm + wi), m1 = __ldg(p.nm + wi + 1);
-        const uint32_t mw = __funnelshift_r(m0, m1, sh);
-        const bool valid = (q < npos) && ((mw & kmask) == 0u);
-        // 2 bit/base window
-        const uint64_t w0 = __ldg(p.pk + wi), w1 = __ldg(p.pk + wi + 1);
-        const uint64_t w = sh ? ((w0 >> (2 * sh)) | (w1 << (64 - 2 * sh))) : w0;
-        ci[0] = 0xFFFFFFF0u; ci[1] = 0xFFFFFFF1u; ci[2] = 0xFFFFFFF2u; ci[3] = 0xFFFFFFF3u;
-        if (valid) {
-          uint64_t fh = 0, rh = 0;
-          for (uint32_t m = 0; m < kq; m++) {
-            const uint32_t b = uint32_t(w >> (8 * m)) & 255u;
-            fh ^= tf[((kq - 1 - m) << 8) | b];
-            rh ^= tr[(m << 8) | b];
-          }
-          const uint64_t h0 = fh + rh;
-          uint64_t h1 = h0 * mul1, h2 = h0 * mul2, h3 = h0 * mul3;
-          h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
-          ci[0] = cbf_index(h0); ci[1] = cbf_index(h1); ci[2] = cbf_index(h2); ci[3] = cbf_index(h3);
-          bi[0] = bf_index(h0); bi[1] = bf_index(h1); bi[2] = bf_index(h2); bi[3] = bf_index(h3);
-        }
-        return valid;
-      };
+      if (len < sc.k) continue;
+      const uint64_t wbase = p.read_boff[ent.read_id] >> 5;
+      const uint32_t npos = len - sc.k + 1;
+      const uint32_t nwords = (len + 31u) >> 5;
+      SeqRegs sr;
+      seq_load_chunk(p, wbase, nwords, 0, lane, sr.pk_cur, sr.nm_cur);
+      seq_load_chunk(p, wbase, nwords, 1, lane, sr.pk_nxt, sr.nm_nxt);
       uint32_t ci[4], bi[4], c[4], nci[4], nbi[4];
-      bool valid = prepare(0, ci, bi), nvalid = false;
+      bool valid = hash_step(tf, tr, sr, 0, 0, npos, lane, sc, ci, bi), nvalid = false;
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 4; j++) c[j] = __ldcg(cbf + ci[j]);
       }
-      for (uint32_t p0 = 0; p0 < npos; p0 += 32) {
+      for (uint32_t p0 = 0, step = 0; p0 < npos; p0 += 32, step++) {
         const bool has_next = p0 + 32 < npos;
+#ifdef GP_BUILD_TIMING
+        const long long tA = clock64();
+#endif
         if (has_next) {
-          nvalid = prepare(p0 + 32, nci, nbi);
+          if (((step + 1) & 31u) == 0u) { // entering the next chunk of 32 steps
+            sr.pk_cur = sr.pk_nxt; sr.nm_cur = sr.nm_nxt;
+            seq_load_chunk(p, wbase, nwords, ((step + 1) >> 5) + 1, lane, sr.pk_nxt, sr.nm_nxt);
+          }
+          nvalid = hash_step(tf, tr, sr, step + 1, p0 + 32, npos, lane, sc, nci, nbi);
           if (nvalid) {
 #pragma unroll
             for (int j = 0; j < 4; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(cbf + nci[j]));
           }
         }
-
-        // Which lanes share a counter with a LOWER lane of this step?  Lanes publish themselves
-        // in a small direct-mapped table of lane masks (slot = hash of the counter index);
-        // slot sharing only nominates candidates, the counter indices themselves are then
-        // compared through shuffles, so the answer is exact whatever the table size.
-        uint32_t sl[4];
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            sl[j] = (ci[j] * 2654435761u) >> (32 - kTabBits);
-            atomicOr(&tab[sl[j]], 1u << lane);
-          }
-        }
-        __syncwarp();
-        uint32_t lower = 0;
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) lower |= tab[sl[j]];
-          lower &= (1u << lane) - 1u;
-        }
-        __syncwarp();
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) tab[sl[j]] = 0u; // leave the table clean for the next step
-        }
-        bool indep = true;
-        const uint32_t rounds = __reduce_max_sync(0xffffffffu, (uint32_t)__popc(lower));
-        for (uint32_t it = 0; it < rounds; it++) {
-          const uint32_t l = lower ? (uint32_t)__ffs(lower) - 1u : lane;
-          lower &= lower - 1u;
-          const uint32_t o0 = __shfl_sync(0xffffffffu, ci[0], l), o1 = __shfl_sync(0xffffffffu, ci[1], l);
-          const uint32_t o2 = __shfl_sync(0xffffffffu, ci[2], l), o3 = __shfl_sync(0xffffffffu, ci[3], l);
-          if (l != lane) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) indep &= (ci[j] != o0) & (ci[j] != o1) & (ci[j] != o2) & (ci[j] != o3);
-          }
-        }
-        if (valid) {
-          if (indep) cbf_bf_apply(cbf, bf, ci, bi, c, thr);
-          ops++;
-        }
-        uint32_t dep = __ballot_sync(0xffffffffu, valid && !indep);
-        while (dep) {
-          __syncwarp();
-          const uint32_t l = __ffs(dep) - 1;
-          if (lane == l) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) c[j] = __ldcg(cbf + ci[j]);
-            cbf_bf_apply(cbf, bf, ci, bi, c, thr);
-            serial++;
-          }
-          dep &= dep - 1;
-        }
-        __syncwarp(); // orders this step's counter stores before the next step's loads
+#ifdef GP_BUILD_TIMING
+        const long long tB = clock64();
+#endif
+        commit_step(cbf, bf, tab, lane, valid, ci, bi, c, thr, ops, serial);
+#ifdef GP_BUILD_TIMING
+        const long long tC = clock64();
+        tim[0] += tB - tA; tim[1] += tC - tB; tim[2]++;
+#endif
         if (has_next) {
           valid = nvalid;
 #pragma unroll
@@ -255,29 +361,199 @@ __global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildPa
       }
     }
   }
-  // per-warp totals
+#ifdef GP_BUILD_TIMING
+  if (lane == 0 && tim[2] > 1000)
+    printf("warp: %lld steps, hash %lld + commit %lld cycles/step\n", tim[2], tim[0] / tim[2], tim[1] / tim[2]);
+#endif
+  flush_counters(p, lane, ops, serial);
+}
+
+// ---- one HASH warp and one COMMIT warp per stream ---------------------------------------------
+// A lone stream is bound by the length of one warp's dependent instruction chain per step, not
+// by memory.  Splitting the step shortens that chain: the hash warp extracts, hashes, derives
+// the indices of 32 k-mers, prefetches the counter sectors into L2 and hands the indices over
+// through a shared-memory ring; the commit warp only loads, resolves intra-step sharing and
+// updates -- in stream order, exactly as build_filters_kernel does.
+constexpr int kPairs = 4;            // pairs per CTA (8 warps)
+constexpr int kRingDepth = 2;        // steps in flight between the two warps of a pair
+constexpr uint32_t kMsgStep = 0, kMsgBegin = 1, kMsgQuit = 2;
+
+struct PairSlot {
+  uint32_t type, valid_mask, thr, sid, batch, ki, pad0, pad1;
+  uint32_t ci[4][32];
+  uint32_t bi[4][32];
+};
+struct PairRing {
+  PairSlot slot[kRingDepth];
+  volatile uint32_t head, tail; // produced / consumed message counts
+  uint32_t pad[6];
+};
+constexpr size_t kPairSmem = 2 * 8 * 256 * sizeof(uint64_t) + size_t(kPairs) * kTabSlots * sizeof(uint32_t) +
+                             size_t(kPairs) * sizeof(PairRing);
+
+__device__ __forceinline__ PairSlot* ring_acquire(PairRing* r, uint32_t head)
+{ // producer: wait for a free slot
+  while (head - r->tail >= uint32_t(kRingDepth)) { }
+  return &r->slot[head % kRingDepth];
+}
+__device__ __forceinline__ void ring_publish(PairRing* r, uint32_t& head, uint32_t lane)
+{
+  // data and flag live in the same SM's shared memory, written in program order by one warp;
+  // __syncwarp orders the lanes' slot stores before lane 0 raises the flag.  (A CTA-scope
+  // membar here would also wait for this warp's outstanding global prefetches.)
+  __syncwarp();
+  head++;
+  if (lane == 0) r->head = head;
+}
+
+__global__ void __launch_bounds__(kPairs * 64) build_filters_paired_kernel(BuildParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* tf = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* tr = tf + 8 * 256;
+  uint32_t* tabs = reinterpret_cast<uint32_t*>(tr + 8 * 256);
+  PairRing* rings = reinterpret_cast<PairRing*>(tabs + kPairs * kTabSlots);
+  fill_hash_tables(tf, tr);
+  for (uint32_t i = threadIdx.x; i < kPairs * kTabSlots; i += blockDim.x) tabs[i] = 0u;
+  if (threadIdx.x < kPairs) { rings[threadIdx.x].head = 0; rings[threadIdx.x].tail = 0; }
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t pair = warp >> 1;
+  PairRing* ring = rings + pair;
+
+  if ((warp & 1u) == 0u) {
+    // ------------------------------- hash warp -------------------------------
+    uint32_t head = 0;
+    for (;;) {
+      uint32_t qslot = 0;
+      if (lane == 0) qslot = atomicAdd(p.next_stream, 1u);
+      qslot = __shfl_sync(0xffffffffu, qslot, 0);
+      if (qslot >= p.n_streams) break;
+      const uint32_t sid = p.stream_order[qslot];
+      const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk;
+      const uint32_t batch = p.first_batch + lb;
+      const StreamConsts sc = stream_consts(p.k[ki]);
+      const uint8_t* cbf = p.cbf_pool + uint64_t(sid) * kCbfCounters;
+      {
+        PairSlot* sl = ring_acquire(ring, head);
+        if (lane == 0) { sl->type = kMsgBegin; sl->sid = sid; sl->batch = batch; sl->ki = ki; }
+        ring_publish(ring, head, lane);
+      }
+      const uint64_t e0 = p.batch_entry_off[batch], e1 = p.batch_entry_off[batch + 1];
+      for (uint64_t e = e0; e < e1; e++) {
+        const gp_read_entry ent = p.entries[e];
+        const uint32_t thr = ent.kmer_threshold - 2u + ki; // utils.cpp:108,121
+        const uint32_t len = p.read_len[ent.read_id];
+        if (len < sc.k) continue;
+        const uint64_t wbase = p.read_boff[ent.read_id] >> 5;
+        const uint32_t npos = len - sc.k + 1;
+        const uint32_t nwords = (len + 31u) >> 5;
+        SeqRegs sr;
+        seq_load_chunk(p, wbase, nwords, 0, lane, sr.pk_cur, sr.nm_cur);
+        seq_load_chunk(p, wbase, nwords, 1, lane, sr.pk_nxt, sr.nm_nxt);
+        for (uint32_t p0 = 0, step = 0; p0 < npos; p0 += 32, step++) {
+          if (step && (step & 31u) == 0u) {
+            sr.pk_cur = sr.pk_nxt; sr.nm_cur = sr.nm_nxt;
+            seq_load_chunk(p, wbase, nwords, (step >> 5) + 1, lane, sr.pk_nxt, sr.nm_nxt);
+          }
+          uint32_t ci[4], bi[4];
+          const bool valid = hash_step(tf, tr, sr, step, p0, npos, lane, sc, ci, bi);
+          if (valid) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ops += __shfl_xor_sync(0xffffffffu, ops, o);
-    serial += __shfl_xor_sync(0xffffffffu, serial, o);
+            for (int j = 0; j < 4; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(cbf + ci[j]));
+          }
+          const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+          if (vmask == 0u) continue; // nothing to commit in this step
+          PairSlot* sl = ring_acquire(ring, head);
+#pragma unroll
+          for (int j = 0; j < 4; j++) { sl->ci[j][lane] = ci[j]; sl->bi[j][lane] = bi[j]; }
+          if (lane == 0) { sl->type = kMsgStep; sl->valid_mask = vmask; sl->thr = thr; }
+          ring_publish(ring, head, lane);
+        }
+      }
+    }
+    PairSlot* sl = ring_acquire(ring, head);
+    if (lane == 0) sl->type = kMsgQuit;
+    ring_publish(ring, head, lane);
+    return;
   }
-  if (lane == 0) {
-    if (ops) atomicAdd(p.counters + 0, ops);
-    if (serial) atomicAdd(p.counters + 1, serial);
+
+  // ------------------------------- commit warp -------------------------------
+  uint32_t* tab = tabs + pair * kTabSlots;
+  unsigned long long ops = 0, serial = 0;
+  uint32_t tail = 0;
+  uint8_t* cbf = nullptr;
+  uint32_t* bf = nullptr;
+  for (;;) {
+    while (ring->head == tail) { }
+    __syncwarp();
+    const volatile PairSlot* sl = &ring->slot[tail % kRingDepth];
+    const uint32_t type = sl->type;
+    if (type == kMsgQuit) break;
+    if (type == kMsgBegin) {
+      cbf = p.cbf_pool + uint64_t(sl->sid) * kCbfCounters;
+      bf = p.bf_pool + (uint64_t(sl->batch) * p.nk + sl->ki) * kBfWords;
+      __syncwarp();
+      tail++;
+      if (lane == 0) ring->tail = tail;
+      continue;
+    }
+    const uint32_t vmask = sl->valid_mask, thr = sl->thr;
+    uint32_t ci[4], bi[4], c[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { ci[j] = sl->ci[j][lane]; bi[j] = sl->bi[j][lane]; }
+    __syncwarp();
+    tail++;
+    if (lane == 0) ring->tail = tail; // the hash warp may reuse the slot
+    const bool valid = (vmask >> lane) & 1u;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) c[j] = __ldcg(cbf + ci[j]);
+    }
+    commit_step(cbf, bf, tab, lane, valid, ci, bi, c, thr, ops, serial);
   }
+  flush_counters(p, lane, ops, serial);
 }
 
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s)
 {
   if (p.n_streams == 0) return;
-  // persistent grid: as many 8-warp CTAs as can be resident, never more warps than streams
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(build_filters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBuildSmem));
+    cudaFuncSetAttribute(build_filters_paired_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPairSmem));
+    configured = true;
+  }
+  // One warp per stream.  With few streams the CTAs are made small so that the warps spread over
+  // all SMs (a lone warp per SM runs a step noticeably faster than eight sharing one SM).
+  uint32_t warps = kBuildWarps;
+  if (p.n_streams < uint32_t(sm_count) * kBuildWarps) {
+    warps = (p.n_streams + uint32_t(sm_count) - 1) / uint32_t(sm_count);
+    if (warps < 1) warps = 1;
+    if (warps > uint32_t(kBuildWarps)) warps = kBuildWarps;
+  }
+  bool paired = false; // the paired kernel is kept for experiments: GP_BUILD_KERNEL=p
+  if (const char* f = std::getenv("GP_BUILD_KERNEL")) paired = f[0] == 'p';
+  if (paired) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_filters_paired_kernel, kPairs * 64, kPairSmem);
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
+    const uint32_t need = (p.n_streams + kPairs - 1) / kPairs;
+    if (grid > need) grid = need;
+    build_filters_paired_kernel<<<grid, kPairs * 64, kPairSmem, s>>>(p);
+    return;
+  }
+  const size_t smem = 2 * 8 * 256 * sizeof(uint64_t) + size_t(warps) * kTabSlots * sizeof(uint32_t);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_filters_kernel, kBuildWarps * 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_filters_kernel, int(warps * 32), smem);
   if (per_sm < 1) per_sm = 1;
   uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
-  const uint32_t need = (p.n_streams + kBuildWarps - 1) / kBuildWarps;
+  const uint32_t need = (p.n_streams + warps - 1) / warps;
   if (grid > need) grid = need;
-  build_filters_kernel<<<grid, kBuildWarps * 32, 0, s>>>(p);
+  build_filters_kernel<<<grid, warps * 32, smem, s>>>(p);
 }
 
 // ------------------------------------------------------------------------------------

@@ -106,9 +106,11 @@ __host__ __device__ __forceinline__ uint64_t extra_hash(uint64_t base, uint32_t 
 // h mod 10485760 (= 5 * 2^21): low 21 bits unchanged, (h >> 21) mod 5 above them
 __host__ __device__ __forceinline__ uint32_t cbf_index(uint64_t h)
 {
-  // (h >> 21) mod 5 with 32-bit arithmetic: 2^32 == 1 (mod 5)
+  // (h >> 21) mod 5 by folding 16-bit limbs: 2^16 == 1 (mod 5), so the 43-bit value and the sum
+  // of its limbs (< 2^18) are congruent; one 32-bit remainder finishes it
   const uint64_t hi = h >> 21;
-  const uint32_t m = (uint32_t(hi) % 5u + uint32_t(hi >> 32) % 5u) % 5u;
+  const uint32_t lo32 = uint32_t(hi);
+  const uint32_t m = ((lo32 & 0xFFFFu) + (lo32 >> 16) + uint32_t(hi >> 32)) % 5u;
   return uint32_t(h & 0x1FFFFFu) | (m << 21);
 }
 __host__ __device__ __forceinline__ uint32_t bf_index(uint64_t h) { return uint32_t(h) & uint32_t(kBfBits - 1); }
