@@ -340,6 +340,11 @@ def ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item())
     launches_per_step = st["build_launches"] + st["polish_launches"]
+    total_bases = draft_bases
+    if dist is not None:
+        tb = torch.tensor([draft_bases], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        total_bases = int(tb.item())
 
     # ---- end to end through the C ABI with host buffers ----
     step_e2e()
@@ -403,7 +408,7 @@ def ours(args, rank, world, local_rank):
             finally:
                 shutil.rmtree(work, ignore_errors=True)
         line = {
-            "metric": METRIC, "value": draft_bases * world / 1e6 / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": total_bases / 1e6 / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer",
             "data": "synthetic (seeded simulator, sim/gpsim.c)",
@@ -411,7 +416,7 @@ def ours(args, rank, world, local_rank):
                            l2="inputs larger than L2: counting filters %.1f GB per step" % (n_batches * 4 * 10485760 / 1e9),
                            guard_rejected_batches=rejected, parallelism=f"batches sharded over {world} GPU(s), no collective"),
             "clocks": clocks,
-            "e2e": {"value": draft_bases * world / 1e6 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": total_bases / 1e6 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
                     "includes": "H2D reads+pack, build, D2H filter payloads, H2D contigs, polish, D2H polished"},
             "gpu_launches": launches_per_step * args.steps,
@@ -437,7 +442,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-roof", dest="roof", action="store_false")
     ap.add_argument("--ref-batches-per-core", type=int, default=2)
+    ap.add_argument("--bsize", type=int, default=WORKLOAD["bsize"], help="contigs per batch (parity/scale experiments)")
+    ap.add_argument("--coverage", type=float, default=WORKLOAD["coverage"])
     args = ap.parse_args()
+    WORKLOAD["bsize"] = args.bsize
+    WORKLOAD["coverage"] = args.coverage
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

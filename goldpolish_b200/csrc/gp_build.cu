@@ -277,7 +277,10 @@ __device__ __forceinline__ void flush_counters(const BuildParams& p, uint32_t la
 // Steps are software-pipelined: while step i waits for its counters, step i+1 is already hashed
 // and its counter sectors are prefetched into L2.  Loads of step i+1 are only ISSUED after step
 // i has stored.  Define GP_BUILD_TIMING to print the per-phase cycle budget of long streams.
-__global__ void __launch_bounds__(kBuildWarps * 32) build_filters_kernel(BuildParams p)
+#ifndef GP_BUILD_MIN_CTAS
+#define GP_BUILD_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kBuildWarps * 32, GP_BUILD_MIN_CTAS) build_filters_kernel(BuildParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* tf = reinterpret_cast<uint64_t*>(smem_raw);
@@ -560,7 +563,7 @@ void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s)
 // random-access roof: the build kernel's memory shape with the hashing taken out
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) roof_kernel(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region,
-                                                   uint32_t iters, uint32_t total_warps)
+                                                   uint32_t iters, uint32_t total_warps, int mode)
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -581,7 +584,9 @@ __global__ void __launch_bounds__(256) roof_kernel(uint8_t* cbf_pool, uint32_t* 
     const uint32_t mn = min(min(c[0], c[1]), min(c[2], c[3]));
     // alternate between the two halves of the algorithmic traffic: counter write-back below
     // the threshold, filter bit sets at it
-    if ((it & 1u) == 0u) {
+    if (mode == 1) { // loads only (experiment)
+      if (mn == 255u) bf[0] = 1u;
+    } else if ((it & 1u) == 0u || mode == 2) {
 #pragma unroll
       for (int j = 0; j < 4; j++)
         if (c[j] == mn) __stcg(cbf + ci[j], (uint8_t)((mn + 1) & 15u));
@@ -597,7 +602,9 @@ void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t
 {
   const uint32_t threads = 256;
   const uint32_t grid = (warps * 32 + threads - 1) / threads;
-  roof_kernel<<<grid, threads, 0, s>>>(cbf_pool, bf_pool, region, iters, warps);
+  int mode = 0; // 0: the build kernel's mix; GP_ROOF_MODE=1 loads only, 2 loads + counter stores (experiments)
+  if (const char* m = std::getenv("GP_ROOF_MODE")) mode = std::atoi(m);
+  roof_kernel<<<grid, threads, 0, s>>>(cbf_pool, bf_pool, region, iters, warps, mode);
 }
 
 } // namespace gp

@@ -1,0 +1,84 @@
+"""GPU, BASELINE.json configs[1] size (5 Mbp draft, 30x reads, 543 batches): size-independent
+properties, since the CPU oracle needs minutes at this size.  (Bit-exactness itself is pinned at
+oracle-sized inputs in test_gpu_parity.py / test_gpu_golden.py.)"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from util import KS, dataset, plan
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full():
+    import goldpolish_b200 as gp
+    d = dataset(genome_len=5_000_000)
+    pl = plan(d, bsize=1)
+    ctx = gp.Context()
+    ctx.upload_reads(d.read_seq, d.read_off)
+    yield gp, d, pl, ctx
+    ctx.close()
+
+
+def _valid_kmers_per_read(d, k):
+    """Number of k-mers made of ACGT/acgt only, per read (what btllib::NtHash::roll yields)."""
+    seq = d.read_seq
+    ok = np.isin(seq | 0x20, np.frombuffer(b"acgt", dtype=np.uint8))
+    # a k-mer starting at i is valid iff the k flags from i are all set: windowed sum via cumsum
+    cs = np.concatenate([[0], np.cumsum(ok, dtype=np.int64)])
+    out = np.zeros(d.n_reads, dtype=np.int64)
+    for r in range(d.n_reads):
+        a, b = int(d.read_off[r]), int(d.read_off[r + 1])
+        if b - a >= k:
+            w = cs[a + k:b + 1] - cs[a:b + 1 - k]
+            out[r] = int(np.count_nonzero(w == k))
+    return out
+
+
+def test_kmer_op_count_and_checksum_of_checksums(full):
+    gp, d, pl, ctx = full
+    bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    st = ctx.stats()
+    per_read = sum(_valid_kmers_per_read(d, k) for k in KS)
+    assert st["kmer_ops"] == int(per_read[pl.entries["read_id"]].sum())
+    assert st["serial_kmers"] < st["kmer_ops"] // 50
+    digest = hashlib.sha256(b"".join(hashlib.sha256(bfs[b].tobytes()).digest() for b in range(bfs.shape[0]))).hexdigest()
+    # waves (limited counting-filter residency) and a second context give the same bits
+    ctx2 = gp.Context(max_resident_batches=97)
+    ctx2.upload_reads(d.read_seq, d.read_off)
+    bfs2 = ctx2.build_filters(pl.batch_entry_off, pl.entries)
+    ctx2.close()
+    digest2 = hashlib.sha256(b"".join(hashlib.sha256(bfs2[b].tobytes()).digest() for b in range(bfs2.shape[0]))).hexdigest()
+    assert digest == digest2
+    # every filter of a batch with reads has bits, and never more than 4 per k-mer op
+    pop = np.unpackbits(bfs.reshape(bfs.shape[0], -1), axis=1).sum(axis=1)
+    has_reads = np.diff(pl.batch_entry_off.astype(np.int64)) > 0
+    assert np.all((pop > 0) == has_reads)
+
+
+def test_polish_subset_consistency_and_identity(full):
+    gp, d, pl, ctx = full
+    bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    out, off, dropped = ctx.polish(d.contig_seq, d.contig_off, pl.contig_batch)
+    st = ctx.stats()
+    assert st["edits"] > 1000 and st["masked"] > 1000
+    # batches are independent: polishing a handful of contigs alone gives the same records
+    pick = [0, 7, 100, 333, d.n_contigs - 1]
+    seq = np.concatenate([d.contig_seq[d.contig_off[c]:d.contig_off[c + 1]] for c in pick])
+    soff = np.cumsum([0] + [int(d.contig_off[c + 1] - d.contig_off[c]) for c in pick]).astype(np.uint64)
+    ctx3 = gp.Context()
+    ctx3.load_filters(np.stack([bfs[pl.contig_batch[c]] for c in pick]))
+    o3, f3, d3 = ctx3.polish(seq, soff, np.arange(len(pick), dtype=np.uint32))
+    for i, c in enumerate(pick):
+        assert d3[i] == dropped[c]
+        assert o3[int(f3[i]):int(f3[i + 1])].tobytes() == out[int(off[c]):int(off[c + 1])].tobytes()
+    # all-ones filters: nothing is absent, nothing changes (records < 100 bp are dropped)
+    ctx3.load_filters(np.full((1, 4, gp.BF_BYTES), 0xFF, dtype=np.uint8))
+    o4, f4, d4 = ctx3.polish(d.contig_seq, d.contig_off, np.zeros(d.n_contigs, dtype=np.uint32))
+    ctx3.close()
+    lens = np.diff(d.contig_off)
+    assert np.array_equal(d4 != 0, lens < 100)
+    kept = np.concatenate([d.contig_seq[d.contig_off[c]:d.contig_off[c + 1]] for c in range(d.n_contigs) if lens[c] >= 100])
+    assert np.array_equal(o4[:int(f4[-1])], kept)
