@@ -173,7 +173,7 @@ __device__ __forceinline__ uint32_t ahead_count(const WS& w) { return w.ve - (w.
 
 // Extend the stream buffer to absolute index `upto` by walking the rope from the
 // materialisation cursor exactly as successive roll() calls would move the tail cursor (:958-966).
-__device__ void stream_fill(WS& w, uint32_t upto)
+__device__ __forceinline__ void stream_fill(WS& w, uint32_t upto)
 {
   if (w.ve >= upto || w.exhausted) return;
   while (w.ve < upto && !w.exhausted) {
@@ -208,7 +208,7 @@ __device__ __forceinline__ uint64_t xor_scan_incl(uint64_t v, uint32_t lane)
 // W_i = srol^i(cseed(c_i)) over the 63 characters c_i = stream[Bp+i], a window's forward hash
 // is sror^(63-j-k) of the XOR of U over its k characters and its reverse hash sror^j of the
 // XOR of W, so two 64-element XOR scans give all 32 windows (nthash.hpp:100-119 restated).
-__device__ void compute_block(const WS& w, uint32_t Bp, uint64_t& fh, uint64_t& rh, uint32_t& pres, uint32_t& acc,
+__device__ __forceinline__ void compute_block(const WS& w, uint32_t Bp, uint64_t& fh, uint64_t& rh, uint32_t& pres, uint32_t& acc,
                               uint32_t& exist)
 {
   const uint32_t lane = w.lane, k = w.k;
@@ -509,7 +509,7 @@ struct Best {
 
 // tryIndels + tryDeletion, :1157-1411.  Lanes share the candidates; the reference's visiting
 // order (ins_0, del_0, ins_1, del_1, ..., ins_340) breaks support ties, later wins (:1347,:1384).
-__device__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint32_t& num_deletions, Best& best)
+__device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint32_t& num_deletions, Best& best)
 {
   const uint32_t ntry = num_tries(w.max_ins);
   const uint32_t k = w.k;
@@ -629,7 +629,7 @@ __device__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint
 }
 
 // makeEdit, :972-1154
-__device__ void make_edit(WS& w, uint32_t draft_char, const Best& best)
+__device__ __forceinline__ void make_edit(WS& w, uint32_t draft_char, const Best& best)
 {
   const uint32_t k = w.k;
   if (best.type == 0) {
@@ -734,7 +734,7 @@ __device__ void make_edit(WS& w, uint32_t draft_char, const Best& best)
 }
 
 // One contig through one k: kmerizeAndCorrect, :1414-1771.  Result is left in the rope.
-__device__ void edit_round(WS& w)
+__device__ __forceinline__ void edit_round(WS& w)
 {
   const uint32_t k = w.k, lane = w.lane, len = w.len;
   if (len == 0) { w.nn = 0; return; }
@@ -848,24 +848,49 @@ __device__ void edit_round(WS& w)
         }
         const uint32_t gate_bits = __ballot_sync(kFull, gate_l);
         uint32_t done = 0;
-        for (uint32_t s = 0; s < 10; s++) {
-          const uint32_t wq = j + s;
-          if (wq >= 32 || !((w.acc >> wq) & 1ull)) break;       // skip / end: generic path
-          if (uint64_t(w.h.pos) + k - 1 >= len) break;            // :1463
-          if (!((w.pres >> wq) & 1ull)) {
-            const bool att = (((w.acc >> wq) & kbits) == kbits) &&
-                             float((uint32_t)__popcll((~w.pres >> (wq + 1)) & w.samp)) >= w.thrM;
-            if (att) {
-              if ((gate_bits >> (3 * s)) & 7u) break;             // a candidate is present: full search
-              Best none = { 0, 0, 0, 0, 0, 0 };
-              make_edit(w, to_upper(v_at(w, w.hp + k - 1)), none);
-            }
-            w.n_trig++;
+        // commit: lane s decides position j+s; the run ends at the first position that needs
+        // the full search, a skip, the end of the block or the end of the contig
+        bool absent_s = false, att_s = false, stop_s = lane >= 10u;
+        if (lane < 10u) {
+          const uint32_t wq = j + lane;
+          stop_s = wq >= 32u || !((w.acc >> (wq & 63u)) & 1ull) || uint64_t(w.h.pos) + lane + k - 1 >= len;
+          if (!stop_s) {
+            absent_s = !((w.pres >> wq) & 1ull);
+            att_s = absent_s && (((w.acc >> wq) & kbits) == kbits) &&
+                    float((uint32_t)__popcll((~w.pres >> (wq + 1)) & w.samp)) >= w.thrM;
+            stop_s = att_s && ((gate_bits >> (3 * lane)) & 7u) != 0u; // a candidate is present: full search
           }
-          cur_increment(w, w.h);
-          cur_increment(w, w.t);
-          w.hp++;
-          done++;
+        }
+        const uint32_t n_run = uint32_t(__ffs(__ballot_sync(kFull, stop_s))) - 1u; // <= 10
+        const bool in_nodes = w.h.n.type == 0 && w.t.n.type == 0 && w.h.pos + n_run <= w.h.n.e &&
+                              w.t.pos + n_run <= w.t.n.e;
+        if (in_nodes) {
+          // both cursors stay inside their draft ranges: all positions of the run at once
+          const bool mine = lane < n_run;
+          if (mine && att_s && w.mask)
+            w.seq[w.t.pos + lane] = (char)to_lower(to_upper(v_at(w, w.hp + lane + k - 1))); // :1131-1146
+          w.n_trig += __popc(__ballot_sync(kFull, mine && absent_s));
+          if (w.mask) w.n_mask += __popc(__ballot_sync(kFull, mine && att_s));
+          w.h.pos += n_run; w.t.pos += n_run; w.hp += n_run;
+          done = n_run;
+        } else {
+          for (uint32_t s2 = 0; s2 < n_run; s2++) {
+            const uint32_t wq = j + s2;
+            if (uint64_t(w.h.pos) + k - 1 >= len) break; // :1463 with the real head cursor
+            if (!((w.pres >> wq) & 1ull)) {
+              const bool att = (((w.acc >> wq) & kbits) == kbits) &&
+                               float((uint32_t)__popcll((~w.pres >> (wq + 1)) & w.samp)) >= w.thrM;
+              if (att) {
+                Best none = { 0, 0, 0, 0, 0, 0 };
+                make_edit(w, to_upper(v_at(w, w.hp + k - 1)), none);
+              }
+              w.n_trig++;
+            }
+            cur_increment(w, w.h);
+            cur_increment(w, w.t);
+            w.hp++;
+            done++;
+          }
         }
         if (done) continue;
       }
@@ -944,7 +969,7 @@ __device__ void edit_round(WS& w)
 }
 
 // writeEditsToFile body (:797-935): walk the rope until the first unset node
-__device__ uint32_t emit_rope(const WS& w, char* dst, uint32_t cap, int& err)
+__device__ __forceinline__ uint32_t emit_rope(const WS& w, char* dst, uint32_t cap, int& err)
 {
   uint32_t o = 0;
   for (uint32_t i = 0; i < w.nn; i++) {
