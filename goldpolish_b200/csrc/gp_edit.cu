@@ -540,45 +540,77 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
     const uint32_t nsamp = (k - 2) / w.jump + 1;
     const uint32_t need = w.thrE > 0.0f ? (uint32_t)ceilf(w.thrE) : 0u;
     const uint32_t allowed = nsamp >= need ? nsamp - need : 0u;
-    for (uint32_t i = w.lane; i < ntry; i += 32) {
-      const uint32_t L = i < 1 ? 1 : i < 5 ? 2 : i < 21 ? 3 : i < 85 ? 4 : 5;
-      const uint32_t r = i - (L == 1 ? 0 : L == 2 ? 1 : L == 3 ? 5 : L == 4 ? 21 : 85); // base-4 digits of s[1..L-1]
-      HashState t = base;
-      uint32_t present = 0, misses = 0;
-      bool pend = false;
-      uint32_t pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pb0 = 0, pb1 = 0, pb2 = 0, pb3 = 0;
+    // Four candidates per lane are rolled side by side: their hash chains are independent, and
+    // the 16 filter words of a sample are in flight together instead of one lookup at a time.
+    constexpr int G = 4;
+    for (uint32_t c0 = 0; c0 * 32u < ntry; c0 += G) {
+      uint32_t Lq[G], rq[G], presq[G], missq[G], pbits[G];
+      uint32_t pw[G][4];
+      HashState tq[G];
+      bool act[G], pend[G];
+#pragma unroll
+      for (int q = 0; q < G; q++) {
+        const uint32_t i = w.lane + 32u * (c0 + q);
+        act[q] = i < ntry;
+        Lq[q] = i < 1 ? 1 : i < 5 ? 2 : i < 21 ? 3 : i < 85 ? 4 : 5;
+        rq[q] = i - (Lq[q] == 1 ? 0 : Lq[q] == 2 ? 1 : Lq[q] == 3 ? 5 : Lq[q] == 4 ? 21 : 85); // base-4 digits of s[1..L-1]
+        tq[q] = base;
+        presq[q] = 0; missq[q] = 0; pbits[q] = 0; pend[q] = false;
+        pw[q][0] = pw[q][1] = pw[q][2] = pw[q][3] = 0;
+      }
       for (uint32_t kk = 0; kk + 1 < k; kk++) { // :1294-1326
-        uint64_t inf, inr;
-        if (kk < L) {
-          if (kk + 1 < L) { // next base of the insertion string
-            const uint32_t d = (r >> (2 * (L - 2 - kk))) & 3u;
-            inf = w.seedt[d + 1];
-            inr = w.seedt[24 + ((0x4731u >> (4 * d)) & 7u)];
-          } else { inf = dF; inr = dRk; } // then the draft base (:1279)
-        } else { inf = inF[kk - L]; inr = inRk[kk - L]; }
-        t.fh = srol1(t.fh) ^ inf ^ outF[kk];
-        t.rh = sror1(t.rh ^ inr ^ outR[kk]);
+        const uint64_t of = outF[kk], orv = outR[kk];
+#pragma unroll
+        for (int q = 0; q < G; q++) {
+          if (!act[q]) continue;
+          uint64_t inf, inr;
+          const uint32_t L = Lq[q];
+          if (kk < L) {
+            if (kk + 1 < L) { // next base of the insertion string
+              const uint32_t d = (rq[q] >> (2 * (L - 2 - kk))) & 3u;
+              inf = w.seedt[d + 1];
+              inr = w.seedt[24 + ((0x4731u >> (4 * d)) & 7u)];
+            } else { inf = dF; inr = dRk; } // then the draft base (:1279)
+          } else { inf = inF[kk - L]; inr = inRk[kk - L]; }
+          tq[q].fh = srol1(tq[q].fh) ^ inf ^ of;
+          tq[q].rh = sror1(tq[q].rh ^ inr ^ orv);
+        }
         if (kk % w.jump == 0) {
-          if (pend) {
-            if (((pw0 >> pb0) & (pw1 >> pb1) & (pw2 >> pb2) & (pw3 >> pb3) & 1u) != 0u) present++; else misses++;
-            if (misses > allowed) { pend = false; break; }
+#pragma unroll
+          for (int q = 0; q < G; q++) {
+            if (!act[q]) continue;
+            if (pend[q]) {
+              const uint32_t pb = pbits[q];
+              if (((pw[q][0] >> (pb & 31u)) & (pw[q][1] >> ((pb >> 5) & 31u)) & (pw[q][2] >> ((pb >> 10) & 31u)) &
+                   (pw[q][3] >> ((pb >> 15) & 31u)) & 1u) != 0u) presq[q]++; else missq[q]++;
+              if (missq[q] > allowed) { act[q] = false; pend[q] = false; continue; } // cannot qualify any more
+            }
+            const uint64_t b = tq[q].fh + tq[q].rh;
+            uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
+            h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
+            const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
+            pw[q][0] = __ldg(w.bf + (n0 >> 5)); pw[q][1] = __ldg(w.bf + (n1 >> 5));
+            pw[q][2] = __ldg(w.bf + (n2 >> 5)); pw[q][3] = __ldg(w.bf + (n3 >> 5));
+            pbits[q] = (n0 & 31u) | ((n1 & 31u) << 5) | ((n2 & 31u) << 10) | ((n3 & 31u) << 15);
+            pend[q] = true;
           }
-          const uint64_t b = t.fh + t.rh;
-          uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
-          h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
-          const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
-          pw0 = __ldg(w.bf + (n0 >> 5)); pw1 = __ldg(w.bf + (n1 >> 5));
-          pw2 = __ldg(w.bf + (n2 >> 5)); pw3 = __ldg(w.bf + (n3 >> 5));
-          pb0 = n0 & 31u; pb1 = n1 & 31u; pb2 = n2 & 31u; pb3 = n3 & 31u;
-          pend = true;
+          if (!__any_sync(kFull, act[0] | act[1] | act[2] | act[3])) break;
         }
       }
-      if (pend && (((pw0 >> pb0) & (pw1 >> pb1) & (pw2 >> pb2) & (pw3 >> pb3) & 1u) != 0u)) present++;
-      if (float(present) >= w.thrE && (w.mode == 0 || present > 0)) { // :1333-1337, :1400
-        const uint32_t order = 2 * i;
-        const uint32_t key = (present << 12) | (order + 1);
-        best_key = max(best_key, key);
-        first_key = min(first_key, order);
+#pragma unroll
+      for (int q = 0; q < G; q++) {
+        if (pend[q]) {
+          const uint32_t pb = pbits[q];
+          if (((pw[q][0] >> (pb & 31u)) & (pw[q][1] >> ((pb >> 5) & 31u)) & (pw[q][2] >> ((pb >> 10) & 31u)) &
+               (pw[q][3] >> ((pb >> 15) & 31u)) & 1u) != 0u) presq[q]++;
+        }
+        const uint32_t i = w.lane + 32u * (c0 + q);
+        if (i < ntry && float(presq[q]) >= w.thrE && (w.mode == 0 || presq[q] > 0)) { // :1333-1337, :1400
+          const uint32_t order = 2 * i;
+          const uint32_t key = (presq[q] << 12) | (order + 1);
+          best_key = max(best_key, key);
+          first_key = min(first_key, order);
+        }
       }
     }
   }
