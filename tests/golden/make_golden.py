@@ -65,6 +65,15 @@ def ref_ntedit(seq: bytes, bf: np.ndarray, k: int, **o):
     return None if n < 0 else buf[:n].tobytes()
 
 
+def write_sam(d, path):
+    with open(path, "w") as f:
+        f.write("@HD\tVN:1.6\tSO:unsorted\n")
+        for c in range(d.n_contigs):
+            f.write(f"@SQ\tSN:{d.contig_name(c)}\tLN:{int(d.contig_off[c + 1] - d.contig_off[c])}\n")
+        for r, c in zip(d.map_read.tolist(), d.map_contig.tolist()):
+            f.write(f"{d.read_name(r)}\t0\t{d.contig_name(c)}\t1\t60\t*\t*\t0\t0\t*\t*\n")
+
+
 def main():
     assert rd.ref_available(), "build oracle/_ref first (make -C oracle ref)"
     rng = random.Random(20250607)
@@ -119,6 +128,17 @@ def main():
                         assert int(hdr["k"]) == k and int(hdr["hash_num"]) == 4 and int(hdr["bytes"]) == BF_BYTES
                     case["batches"][b]["server_bf_sha256"] = shas
                     assert shas == case["batches"][b]["bf_sha256"], "plan_batches disagrees with the reference server"
+            if name == "fastq_bsize1":
+                # the same mappings as SAM (query column 1, target column 3, '@' header lines
+                # skipped, mappings.cpp:112-162) must give the same filters
+                sam = os.path.join(w, "mappings.sam")
+                write_sam(d, sam)
+                with rd.BfServer(os.path.join(w, "bfs_sam"), os.path.join(w, "draft.fa"), os.path.join(w, "draft.fa.index"),
+                                 sam, reads, reads + ".index", threads=4) as srv:
+                    for b in range(len(pl.batch_entry_off) - 1):
+                        paths = srv.build(str(b), [d.contig_name(c) for c in range(b * bsize, min((b + 1) * bsize, d.n_contigs))])
+                        assert [sha(rd.parse_bf(paths[k])[1]) for k in KS] == case["batches"][b]["bf_sha256"]
+                case["sam_equals_paf"] = True
         filt["cases"].append(case)
     # ntLink-style triples: the minimizer filter (mappings.cpp:230-320) with a tight cap, s = 100
     kw = dict(genome_len=50000, seed=14)
@@ -216,6 +236,12 @@ def main():
             f.write(bfs[0].tobytes())
         res = rd.run_ntedit(fa, bfp, os.path.join(w, "out"))
         cli = {"input_fasta": open(fa).read(), "edited_fasta": open(res).read()}
+        # the -x/-y threshold form (no -X/-Y: use_ratio stays false, ntedit.cpp:1519-1520) with
+        # ntEdit's own defaults (mode 0, no masking) and with -m2 -i2 -d3 -z200 -a1
+        res = rd.run_ntedit(fa, bfp, os.path.join(w, "xy"), extra=("-t1",))
+        cli["edited_fasta_defaults_xy"] = open(res).read()
+        res = rd.run_ntedit(fa, bfp, os.path.join(w, "xy2"), extra=("-x4", "-y6", "-m2", "-i2", "-d3", "-z200", "-a1", "-t1"))
+        cli["edited_fasta_x4_y6_m2_i2_d3_z200_a1"] = open(res).read()
     json.dump(cli, open(os.path.join(HERE, "ntedit_cli.json"), "w"))
     print("golden vectors written to", HERE)
 

@@ -49,10 +49,18 @@ def test_fifo_server_matches_reference_server():
     from oracle import ref_driver as rd
     g = _load("filters.json")
     jobs = [(c, "mappings.paf", 150.0, 40.0) for c in g["cases"][:2]] + [(g["ntlink"], "mappings.tsv", g["ntlink"]["mx_max"], g["ntlink"]["subsample_max"])]
+    assert g["cases"][0].get("sam_equals_paf")
+    jobs.append((g["cases"][0], "mappings.sam", 150.0, 40.0))
     for case, mapfile, mx_max, sub in jobs:
         with _tmp() as w:
             d = sim.simulate(write_dir=w, **case["sim"])
             reads = os.path.join(w, "reads.fq" if d.fastq else "reads.fa")
+            if mapfile.endswith(".sam"):
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+                mg = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mg)
+                mg.write_sam(d, os.path.join(w, mapfile))
             for f in (os.path.join(w, "draft.fa"), reads):
                 subprocess.check_call([os.path.join(BIN, "goldpolish-index"), f, f + ".index"], env=ENV)
             bs = case["bsize"]
@@ -99,6 +107,12 @@ def test_ntedit_gr_cli_matches_reference_binary():
         subprocess.check_call([os.path.join(BIN, "ntedit-gr"), "-f", fa, "-r", bfs[0], "-d5", "-i5", "-m1", "-X0.5",
                                "-Y0.5", "-b", os.path.join(w, "out"), "-t1", "-a1"], env=ENV)
         assert open(os.path.join(w, "out_edited.fa")).read() == cli["edited_fasta"]
+        # -x/-y threshold form with ntEdit's own defaults, and a mode-2 / custom-limit run
+        subprocess.check_call([os.path.join(BIN, "ntedit-gr"), "-f", fa, "-r", bfs[0], "-b", os.path.join(w, "xy"), "-t1"], env=ENV)
+        assert open(os.path.join(w, "xy_edited.fa")).read() == cli["edited_fasta_defaults_xy"]
+        subprocess.check_call([os.path.join(BIN, "ntedit-gr"), "-f", fa, "-r", bfs[0], "-b", os.path.join(w, "xy2"), "-x4", "-y6",
+                               "-m2", "-i2", "-d3", "-z200", "-a1", "-t1"], env=ENV)
+        assert open(os.path.join(w, "xy2_edited.fa")).read() == cli["edited_fasta_x4_y6_m2_i2_d3_z200_a1"]
         # error behaviour of ntedit.cpp:346-353,1944-1947: unreadable file / malformed option -> exit 1
         assert subprocess.call([os.path.join(BIN, "ntedit-gr"), "-f", fa + ".missing", "-r", bfs[0]], env=ENV,
                                stderr=subprocess.DEVNULL) == 1
