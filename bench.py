@@ -124,12 +124,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the build kernel from the committed ncu summary, if any."""
+def ncu_traffic(kmer_ops_per_launch):
+    """DRAM bytes per launch of the build kernel: the committed `ncu --set full` capture
+    (profiles/build_kernel_dram.json, taken on the 1 Mbp profiling workload) gives bytes per k-mer
+    op; scaled to the k-mer ops of this launch.  None when no capture is committed."""
     p = os.path.join(ROOT, "profiles", "build_kernel_dram.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            per_op = json.load(open(p)).get("dram_bytes_per_kmer_op")
+            return None if per_op is None else per_op * kmer_ops_per_launch
         except Exception:
             return None
     return None
@@ -377,7 +380,8 @@ def ours(args, rank, world, local_rank):
         kops = st["kmer_ops"]
         achieved = kops * ALGO_BYTES_PER_KMER_OP / (build_kernel_ms * 1e-3) / 1e9 if build_kernel_ms > 0 else 0.0
         roof = {"bound": "hbm", "achieved": achieved, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
-                "frac": achieved / float(peaks["hbm_gbs"]), "traffic": ncu_traffic(),
+                "frac": achieved / float(peaks["hbm_gbs"]), "traffic": ncu_traffic(kops),
+                "traffic_source": "profiles/build_kernel_dram.json (ncu dram__bytes_read+write per k-mer op at 1 Mbp) x k-mer ops of this launch",
                 "kernel": "gp::build_filters_kernel", "kernel_ms": build_kernel_ms, "kmer_ops_per_launch": kops,
                 "algorithmic_bytes_per_kmer_op": ALGO_BYTES_PER_KMER_OP, "peak_source": peak_src,
                 "kmer_ops_per_s": kops / (build_kernel_ms * 1e-3) if build_kernel_ms > 0 else 0.0,
