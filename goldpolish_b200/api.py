@@ -30,7 +30,7 @@ class _Config(C.Structure):
                 ("mode", C.c_int32), ("mask", C.c_int32), ("missing_ratio", C.c_float),
                 ("edit_ratio", C.c_float), ("jump", C.c_uint32), ("min_contig_len", C.c_uint32),
                 ("max_resident_batches", C.c_uint32), ("use_ratio", C.c_int32),
-                ("missing_threshold", C.c_float), ("edit_threshold", C.c_float)]
+                ("missing_threshold", C.c_float), ("edit_threshold", C.c_float), ("keep_counters", C.c_int32)]
 
 
 class _Stats(C.Structure):
@@ -127,7 +127,8 @@ class Context:
     ``build_filters`` == goldpolish-targeted-bfs' serve_batch, ``polish`` == goldpolish-ntedit."""
 
     def __init__(self, device: int = 0, ks=DEFAULT_KS, max_insertions=5, max_deletions=5, mode=1, mask=1,
-                 missing_ratio=0.5, edit_ratio=0.5, jump=3, min_contig_len=100, max_resident_batches=0):
+                 missing_ratio=0.5, edit_ratio=0.5, jump=3, min_contig_len=100, max_resident_batches=0,
+                 keep_counters=0):
         self._l = load_library()
         cfg = _Config()
         self._l.gp_default_config(C.byref(cfg))
@@ -138,6 +139,7 @@ class Context:
         cfg.max_insertions, cfg.max_deletions, cfg.mode, cfg.mask = max_insertions, max_deletions, mode, mask
         cfg.missing_ratio, cfg.edit_ratio, cfg.jump, cfg.min_contig_len = missing_ratio, edit_ratio, jump, min_contig_len
         cfg.max_resident_batches = max_resident_batches
+        cfg.keep_counters = keep_counters
         h = C.c_void_p()
         rc = self._l.gp_ctx_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -57,6 +57,12 @@ struct gp_ctx {
   uint32_t wave_batches = 0;
   std::vector<uint32_t> wave_first, wave_count, wave_order_off;
   DevBuf d_batch_entry_off, d_entries, d_bf_pool, d_cbf_pool, d_stream_order, d_next, d_counters;
+  // level-synchronous build
+  DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive;
+  uint32_t alive_words = 0, n_entries = 0;
+  bool levels_ok = false; // every stream fits the 26-bit occurrence clock
+  int build_algo = 0;     // 0 = auto, 1 = warp per stream, 2 = level-synchronous
+  int build_algo_resolved = 1;
 
   // polish
   uint32_t n_contigs = 0;
@@ -189,7 +195,7 @@ void gp_ctx_destroy(gp_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = { &ctx->d_ascii, &ctx->d_ascii_off, &ctx->d_pk, &ctx->d_nm, &ctx->d_read_boff, &ctx->d_read_len,
                      &ctx->d_batch_entry_off, &ctx->d_entries, &ctx->d_bf_pool, &ctx->d_cbf_pool, &ctx->d_stream_order,
-                     &ctx->d_next, &ctx->d_counters, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
+                     &ctx->d_next, &ctx->d_counters, &ctx->d_step_pre, &ctx->d_batch_max_thr, &ctx->d_V, &ctx->d_alive, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
                      &ctx->d_cap_off, &ctx->d_cur_len, &ctx->d_which, &ctx->d_dropped, &ctx->d_nodes, &ctx->d_node_off,
                      &ctx->d_contig_batch, &ctx->d_order, &ctx->d_pnext, &ctx->d_pcounters, &ctx->d_error, &ctx->d_out,
                      &ctx->d_out_off };
@@ -316,13 +322,56 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
       work[b] += ctx->h_read_len[entries[e].read_id];
     }
   }
+  // level-synchronous form: steps (32 k-mer starts) before every entry, per k; largest threshold per batch
+  {
+    std::vector<uint32_t> pre(size_t(c.nk) * (n_entries + 1), 0u), maxthr(std::max<uint32_t>(n_batches, 1), 0u);
+    bool ok = true;
+    uint64_t max_steps = 0;
+    for (uint32_t ki = 0; ki < c.nk; ki++) {
+      uint32_t* pk = pre.data() + size_t(ki) * (n_entries + 1);
+      uint64_t acc = 0;
+      for (uint64_t e = 0; e < n_entries; e++) {
+        pk[e] = uint32_t(acc);
+        const uint32_t len = ctx->h_read_len[entries[e].read_id];
+        if (len >= c.k[ki]) acc += (uint64_t(len) - c.k[ki] + 1 + 31) / 32;
+      }
+      pk[n_entries] = uint32_t(acc);
+      if (acc >= 0xFFFFFFFFull) ok = false;
+      for (uint32_t b = 0; b < n_batches && ok; b++) {
+        const uint64_t st = uint64_t(pk[batch_entry_off[b + 1]]) - pk[batch_entry_off[b]];
+        max_steps = std::max(max_steps, st);
+        if (st * 32 >= (1ull << 26)) ok = false; // occurrence clock is 26 bits
+      }
+    }
+    for (uint32_t b = 0; b < n_batches; b++)
+      for (uint64_t e = batch_entry_off[b]; e < batch_entry_off[b + 1]; e++) maxthr[b] = std::max(maxthr[b], entries[e].kmer_threshold);
+    ctx->levels_ok = ok;
+    ctx->n_entries = uint32_t(n_entries);
+    ctx->alive_words = uint32_t(max_steps + 1);
+    GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
+    GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
+    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4));
+    GP_CUDA(ctx, ctx->d_alive.ensure(size_t(ctx->alive_words) * 2 * 4));
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_step_pre.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_max_thr.p, maxthr.data(), maxthr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  // which build kernel: 0 = auto (level-synchronous whenever the 26-bit occurrence clock suffices)
+  {
+    int algo = ctx->build_algo;
+    if (const char* f = std::getenv("GP_BUILD_KERNEL")) algo = f[0] == 'l' ? 2 : (f[0] == 's' || f[0] == 'p') ? 1 : algo;
+    if (algo == 0) algo = 2;
+    if (!ctx->levels_ok) algo = 1;
+    ctx->build_algo_resolved = algo;
+  }
+  const bool uses_cbf = ctx->build_algo_resolved == 1 || c.keep_counters;
   // how many batches can hold their counting filters at once
   const uint64_t per_batch = uint64_t(c.nk) * gp::kCbfCounters;
   const uint64_t bf_bytes = uint64_t(n_batches) * c.nk * gp::kBfBytes;
   GP_CUDA(ctx, ctx->d_bf_pool.ensure(std::max<uint64_t>(bf_bytes, 4)));
   uint32_t wave = n_batches;
   if (c.max_resident_batches) wave = std::min(wave, c.max_resident_batches);
-  {
+  if (uses_cbf) {
     size_t free_b = 0, total_b = 0;
     GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     const uint64_t usable = uint64_t(free_b) + ctx->d_cbf_pool.cap;
@@ -331,7 +380,7 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     if (fit == 0 && n_batches) GP_FAIL(ctx, GP_ERR_OOM, "not enough device memory for one batch of counting filters");
     wave = uint32_t(std::min<uint64_t>(wave, fit));
   }
-  if (n_batches) {
+  if (n_batches && uses_cbf) {
     cudaError_t e = ctx->d_cbf_pool.ensure(uint64_t(wave) * per_batch);
     while (e != cudaSuccess && wave > 1) { cudaGetLastError(); wave = (wave + 1) / 2; e = ctx->d_cbf_pool.ensure(uint64_t(wave) * per_batch); }
     GP_CUDA(ctx, e);
@@ -386,7 +435,39 @@ int gp_build_run(gp_ctx* ctx)
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_next.p, 0, ctx->wave_first.size() * 4, s));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->n_batches) * c.nk * gp::kBfBytes, s));
   }
-  for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
+  const int algo = ctx->build_algo_resolved;
+  for (size_t wv = 0; algo == 2 && wv < ctx->wave_first.size(); wv++) {
+    // level-synchronous: all SMs on one stream at a time, timestamps resident in L2
+    gp::LevelParams p;
+    std::memset(&p, 0, sizeof p);
+    p.pk = ctx->d_pk.as<uint64_t>();
+    p.nm = ctx->d_nm.as<uint32_t>();
+    p.read_boff = ctx->d_read_boff.as<uint64_t>();
+    p.read_len = ctx->d_read_len.as<uint32_t>();
+    p.batch_entry_off = ctx->d_batch_entry_off.as<uint64_t>();
+    p.entries = ctx->d_entries.as<gp_read_entry>();
+    p.step_pre = ctx->d_step_pre.as<uint32_t>();
+    p.batch_max_thr = ctx->d_batch_max_thr.as<uint32_t>();
+    p.V = ctx->d_V.as<uint32_t>();
+    p.alive = ctx->d_alive.as<uint32_t>();
+    p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
+    p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
+    p.counters = ctx->d_counters.as<unsigned long long>();
+    p.alive_words = ctx->alive_words;
+    p.n_entries = ctx->n_entries;
+    p.n_streams = ctx->wave_count[wv] * c.nk;
+    p.first_batch = ctx->wave_first[wv];
+    p.nk = c.nk;
+    for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
+    if (c.keep_counters) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4, s));
+    while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
+    GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
+    GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s));
+    GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
+    launches += 1;
+  }
+  for (size_t wv = 0; algo == 1 && wv < ctx->wave_first.size(); wv++) {
     gp::BuildParams p;
     p.pk = ctx->d_pk.as<uint64_t>();
     p.nm = ctx->d_nm.as<uint32_t>();
@@ -435,6 +516,8 @@ int gp_build_fetch_cbf(gp_ctx* ctx, uint32_t batch, uint32_t k_index, uint8_t* c
   if (!ctx || !cbf_out) return GP_ERR_ARG;
   if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
   if (batch >= ctx->n_batches || k_index >= ctx->cfg.nk) GP_FAIL(ctx, GP_ERR_ARG, "batch / k index out of range");
+  if (ctx->build_algo_resolved == 2 && !ctx->cfg.keep_counters)
+    GP_FAIL(ctx, GP_ERR_STATE, "counting-filter bytes were not materialised: create the context with keep_counters = 1");
   // counting filters of a wave are overwritten by the next wave: only the last wave is still resident
   const size_t last = ctx->wave_first.size() - 1;
   if (batch < ctx->wave_first[last]) GP_FAIL(ctx, GP_ERR_STATE, "counting filter of an earlier wave is no longer resident");

@@ -1,0 +1,218 @@
+// Counting-Bloom-gated filter build, level-synchronous form (sm_100a).
+//
+// Same result as fill_bfs (bcgsc/goldpolish src/utils.cpp:96-123) in the reference's order,
+// computed WITHOUT walking the stream in order.  The reference's update is
+//     c = min over the k-mer's 4 counters;  if (c < thr) every counter equal to c becomes c+1;
+//     the k-mer enters the Bloom filter iff the count after the update is >= thr.
+// Give every k-mer occurrence of a stream its position t in the reference's order and let
+// T_L(x) be the time at which counter x goes from L-1 to L.  Then
+//     T_{L+1}(x) = min { t : occurrence t touches x,  thr(t) > L,  t > max_j T_L(x_j(t)) }
+// (all four counters had reached L before t, so the minimum is >= L; those still at L move, and
+// the first such occurrence is the one that moves x), and occurrence t enters the filter iff
+//     t > max_j T_{thr(t)-1}(x_j(t)).
+// An occurrence that fails the test at level L fails it at every higher level.  So a stream is
+// Lmax = max thr rounds of: "survivors test against T_L" then "survivors atomicMin their time
+// into T_{L+1}" -- order-free inside a round, which lets ALL SMs work on ONE stream, whose single
+// 40 MiB timestamp array then lives in L2 instead of HBM.  One array serves every level: entries
+// carry a 6-bit epoch tag (newer epochs compare smaller, so atomicMin overwrites stale entries,
+// and readers treat a stale tag as "never"), so nothing is cleared between levels or streams.
+#include "gp_hashing.cuh"
+
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace gp {
+
+constexpr uint32_t kTimeBits = 26;
+constexpr uint32_t kTimeMask = (1u << kTimeBits) - 1u;
+constexpr uint32_t kMaxEpoch = 62; // tags 63 - epoch; tag 63 (epoch 0) is the cleared state
+constexpr int kLevelWarps = 8;
+
+struct LevelCtx {
+  const uint64_t* tf;
+  const uint64_t* tr;
+  uint32_t lane, gwarp, nwarps;
+};
+
+// Walk the steps [s_begin, s_end) of stream (batch, ki) in order and call f(step, entry thr, valid,
+// ci, bi) for each.  A step is 32 consecutive k-mer starts of one read; steps of a stream are
+// numbered in the reference's order, which makes (step * 32 + lane) the occurrence time.
+template<typename P, typename F>
+__device__ __forceinline__ void for_steps(const LevelParams& p, const LevelCtx& c, uint32_t batch, uint32_t ki,
+                                          const StreamConsts& sc, uint32_t s_begin, uint32_t s_end, P&& wanted, F&& f)
+{
+  if (s_begin >= s_end) return;
+  const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
+  const uint64_t e0 = p.batch_entry_off[batch], e1 = p.batch_entry_off[batch + 1];
+  const uint32_t base = pre[e0];
+  // entry that holds step s_begin: last e with pre[e] - base <= s_begin
+  uint64_t lo = e0, hi = e1;
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (pre[mid] - base <= s_begin) lo = mid; else hi = mid;
+  }
+  uint32_t s = s_begin;
+  for (uint64_t e = lo; e < e1 && s < s_end; e++) {
+    const uint32_t first = pre[e] - base, last = pre[e + 1] - base;
+    if (last <= s) continue;
+    const gp_read_entry ent = p.entries[e];
+    const uint32_t thr = ent.kmer_threshold - 2u + ki; // utils.cpp:108,121
+    const uint32_t len = p.read_len[ent.read_id];
+    const uint64_t wbase = p.read_boff[ent.read_id] >> 5;
+    const uint32_t npos = len - sc.k + 1;
+    for (; s < last && s < s_end; s++) {
+      if (!wanted(s)) continue;      // nothing of this step is still in play
+      const uint32_t rs = s - first; // step within the read
+      const uint64_t w0 = __ldg(p.pk + wbase + rs), w1 = __ldg(p.pk + wbase + rs + 1);
+      const uint32_t m0 = __ldg(p.nm + wbase + rs), m1 = __ldg(p.nm + wbase + rs + 1);
+      uint32_t ci[4], bi[4];
+      const bool valid = hash_from_words(c.tf, c.tr, w0, w1, m0, m1, rs * 32u, npos, c.lane, sc, ci, bi);
+      f(s, thr, valid, ci, bi);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kLevelWarps * 32) build_filters_levels_kernel(LevelParams p)
+{
+  __shared__ uint64_t tf[8 * 256];
+  __shared__ uint64_t tr[8 * 256];
+  cg::grid_group grid = cg::this_grid();
+  fill_hash_tables(tf, tr);
+  __syncthreads();
+  LevelCtx c;
+  c.tf = tf; c.tr = tr;
+  c.lane = threadIdx.x & 31u;
+  c.gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  c.nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  uint32_t* __restrict__ V = p.V;
+  unsigned long long ops = 0;
+  uint32_t epoch = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
+
+  for (uint32_t sid = 0; sid < p.n_streams; sid++) {
+    const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk;
+    const uint32_t batch = p.first_batch + lb;
+    const StreamConsts sc = stream_consts(p.k[ki]);
+    const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
+    const uint32_t n_steps = pre[p.batch_entry_off[batch + 1]] - pre[p.batch_entry_off[batch]];
+    if (n_steps == 0) continue;
+    const uint32_t lmax = p.batch_max_thr[batch] - 2u + ki; // largest thr of the stream
+    uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
+    uint8_t* __restrict__ cbf = p.cbf_pool ? p.cbf_pool + uint64_t(sid) * kCbfCounters : nullptr;
+    // contiguous share of the steps for this warp
+    const uint32_t per = (n_steps + c.nwarps - 1) / c.nwarps;
+    const uint32_t s_begin = min(n_steps, c.gwarp * per), s_end = min(n_steps, s_begin + per);
+    uint32_t* alive_cur = p.alive;
+    uint32_t* alive_nxt = p.alive + p.alive_words;
+
+    // make sure the epochs of this stream fit below the tag wrap
+    if (epoch + lmax + 1 > kMaxEpoch) {
+      for (uint64_t i = gtid; i < kCbfCounters; i += gthreads) V[i] = 0xFFFFFFFFu;
+      epoch = 0;
+      grid.sync();
+    }
+
+    // ---- level 0 -> 1: every occurrence writes its time (the first toucher of a counter wins) ----
+    epoch++;
+    uint32_t tag = (63u - epoch) << kTimeBits;
+    for_steps(p, c, batch, ki, sc, s_begin, s_end, [](uint32_t) { return true; },
+              [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+                const uint32_t t = s * 32u + c.lane;
+                const bool q = valid && thr > 0u;
+                if (q) {
+#pragma unroll
+                  for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
+                  if (thr == 1u) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
+                  }
+                }
+                if (valid) ops++;
+                const uint32_t m = __ballot_sync(0xffffffffu, q);
+                if (c.lane == 0) alive_cur[s] = m;
+              });
+    grid.sync();
+
+    // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
+    // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
+    const uint32_t lread = cbf ? lmax : lmax - 1u;
+    for (uint32_t L = 1; L <= lread; L++) {
+      // ---- read: who sees all four counters at >= L before its own time? ----
+      const bool last = L == lread;
+      for_steps(p, c, batch, ki, sc, s_begin, s_end,
+                [&](uint32_t s) {
+                  const bool on = alive_cur[s] != 0u;
+                  if (!on && c.lane == 0) alive_nxt[s] = 0u;
+                  return on;
+                },
+                [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+                  const uint32_t am = alive_cur[s];
+                  const uint32_t t = s * 32u + c.lane;
+                  bool q = false;
+                  if ((am >> c.lane) & 1u) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = __ldcg(V + ci[j]);
+                    bool reached = true;
+                    uint32_t mx = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                      reached &= (v[j] & ~kTimeMask) == tag;
+                      mx = max(mx, v[j] & kTimeMask);
+                      // this occurrence is the one that moved counter j to level L
+                      if (cbf && v[j] == (tag | t)) cbf[ci[j]] = (uint8_t)L;
+                    }
+                    q = reached && t > mx && thr > L;
+                    if (q && thr == L + 1u) { // count after the update reaches thr: Bloom filter insert
+#pragma unroll
+                      for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
+                    }
+                  }
+                  const uint32_t m = __ballot_sync(0xffffffffu, q);
+                  if (c.lane == 0) alive_nxt[s] = m;
+                  (void)valid;
+                });
+      grid.sync();
+      if (last) break;
+      // ---- write: survivors race for T_{L+1} of their counters ----
+      epoch++;
+      tag = (63u - epoch) << kTimeBits;
+      for_steps(p, c, batch, ki, sc, s_begin, s_end, [&](uint32_t s) { return alive_nxt[s] != 0u; },
+                [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+                  const uint32_t am = alive_nxt[s];
+                  if ((am >> c.lane) & 1u) {
+                    const uint32_t t = s * 32u + c.lane;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
+                  }
+                  (void)thr; (void)valid; (void)bi;
+                });
+      grid.sync();
+      uint32_t* tmp = alive_cur; alive_cur = alive_nxt; alive_nxt = tmp;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);
+  if (c.lane == 0 && ops) atomicAdd(p.counters + 0, ops);
+}
+
+int levels_max_grid(int sm_count)
+{
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_filters_levels_kernel, kLevelWarps * 32, 0);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  return sm_count * per_sm;
+}
+
+cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s)
+{
+  if (p.n_streams == 0) return cudaSuccess;
+  LevelParams lp = p;
+  void* args[] = { &lp };
+  return cudaLaunchCooperativeKernel((const void*)build_filters_levels_kernel, dim3(levels_max_grid(sm_count)),
+                                     dim3(kLevelWarps * 32), args, 0, s);
+}
+
+} // namespace gp

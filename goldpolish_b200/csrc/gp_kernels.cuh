@@ -24,6 +24,28 @@ struct BuildParams {
   uint32_t k[kMaxK];
 };
 
+struct LevelParams {              // level-synchronous filter build (gp_build_levels.cu)
+  const uint64_t* pk;
+  const uint32_t* nm;
+  const uint64_t* read_boff;
+  const uint32_t* read_len;
+  const uint64_t* batch_entry_off;
+  const gp_read_entry* entries;
+  const uint32_t* step_pre;       // [nk][n_entries + 1]: steps before entry e, for every k index
+  const uint32_t* batch_max_thr;  // per batch: largest kmer_threshold among its entries
+  uint32_t* V;                    // kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
+  uint32_t* alive;                // 2 * alive_words survivor masks, one word per step
+  uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
+  uint32_t* bf_pool;
+  unsigned long long* counters;
+  uint32_t alive_words;
+  uint32_t n_entries;
+  uint32_t n_streams;
+  uint32_t first_batch;
+  uint32_t nk;
+  uint32_t k[kMaxK];
+};
+
 struct EdNode {      // seqNode of ntedit.cpp:468-475 (num_support is never observable)
   int32_t type;      // -1 unset, 0 draft range [s, e], 1 inserted character c
   uint32_t s, e, c;
@@ -55,6 +77,7 @@ struct EditParams {
 void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint64_t* base_off, uint64_t* pk,
                        uint32_t* nm, uint32_t n_reads, cudaStream_t s);
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s);
 void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t iters, uint32_t warps, cudaStream_t s);
 void launch_edit(const EditParams& p, int sm_count, cudaStream_t s);
 

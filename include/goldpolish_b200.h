@@ -69,6 +69,7 @@ typedef struct {
   int32_t use_ratio;               /* 1: thresholds from -X/-Y (default); 0: from -x/-y below */
   float missing_threshold;         /* -x */
   float edit_threshold;            /* -y */
+  int32_t keep_counters;           /* 1: also materialise the counting-filter bytes (gp_build_fetch_cbf; parity tests) */
 } gp_config;
 
 /* one read handed to fill_bfs: index into the uploaded read store + the target's kmer_threshold */

@@ -28,7 +28,7 @@ def test_filters_golden(gp):
         pl = gp.plan_batches(np.diff(d.contig_off), [d.contig_name(i) for i in range(d.n_contigs)],
                              [d.read_name(i) for i in range(d.n_reads)], d.read_phred, np.diff(d.read_off),
                              d.map_read, d.map_contig, bsize=case["bsize"])
-        with gp.Context() as ctx:
+        with gp.Context(keep_counters=1) as ctx:
             ctx.upload_reads(d.read_seq, d.read_off)
             bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
             for b, rec in enumerate(case["batches"]):

@@ -16,14 +16,18 @@ def gp():
 @pytest.fixture(scope="module")
 def small(gp):
     d = dataset(genome_len=60000)
-    ctx = gp.Context()
+    ctx = gp.Context(keep_counters=1)
     ctx.upload_reads(d.read_seq, d.read_off)
     yield d, ctx
     ctx.close()
 
 
+@pytest.mark.parametrize("algo", ["l", "s", "p"])
 @pytest.mark.parametrize("bsize", [1, 3])
-def test_filters_match_oracle(gp, small, bsize):
+def test_filters_match_oracle(gp, small, bsize, algo, monkeypatch):
+    """Filter bits AND counter bytes, for each build kernel: level-synchronous (default), one warp
+    per stream, hash/commit warp pairs."""
+    monkeypatch.setenv("GP_BUILD_KERNEL", algo)
     d, ctx = small
     pl = plan(d, bsize=bsize)
     bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
