@@ -351,7 +351,7 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
     GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
     GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4));
-    GP_CUDA(ctx, ctx->d_alive.ensure(size_t(ctx->alive_words) * 2 * 4));
+    GP_CUDA(ctx, ctx->d_alive.ensure((size_t(ctx->alive_words) * 32 * 6 + 2) * 4)); // two survivor lists + their lengths
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_step_pre.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_max_thr.p, maxthr.data(), maxthr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -449,11 +449,12 @@ int gp_build_run(gp_ctx* ctx)
     p.step_pre = ctx->d_step_pre.as<uint32_t>();
     p.batch_max_thr = ctx->d_batch_max_thr.as<uint32_t>();
     p.V = ctx->d_V.as<uint32_t>();
-    p.alive = ctx->d_alive.as<uint32_t>();
+    p.surv = ctx->d_alive.as<uint32_t>();
+    p.surv_count = ctx->d_alive.as<uint32_t>() + size_t(6) * ctx->alive_words * 32;
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
     p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
     p.counters = ctx->d_counters.as<unsigned long long>();
-    p.alive_words = ctx->alive_words;
+    p.surv_cap = ctx->alive_words * 32;
     p.n_entries = ctx->n_entries;
     p.n_streams = ctx->wave_count[wv] * c.nk;
     p.first_batch = ctx->wave_first[wv];

@@ -36,7 +36,7 @@ struct LevelCtx {
 };
 
 // Walk the steps [s_begin, s_end) of stream (batch, ki) in order and call f(step, entry thr, valid,
-// ci, bi) for each.  A step is 32 consecutive k-mer starts of one read; steps of a stream are
+// base hash, ci, bi) for each.  A step is 32 consecutive k-mer starts of one read; steps of a stream are
 // numbered in the reference's order, which makes (step * 32 + lane) the occurrence time.
 template<typename P, typename F>
 __device__ __forceinline__ void for_steps(const LevelParams& p, const LevelCtx& c, uint32_t batch, uint32_t ki,
@@ -67,13 +67,58 @@ __device__ __forceinline__ void for_steps(const LevelParams& p, const LevelCtx& 
       const uint64_t w0 = __ldg(p.pk + wbase + rs), w1 = __ldg(p.pk + wbase + rs + 1);
       const uint32_t m0 = __ldg(p.nm + wbase + rs), m1 = __ldg(p.nm + wbase + rs + 1);
       uint32_t ci[4], bi[4];
-      const bool valid = hash_from_words(c.tf, c.tr, w0, w1, m0, m1, rs * 32u, npos, c.lane, sc, ci, bi);
-      f(s, thr, valid, ci, bi);
+      uint64_t h0 = 0;
+      const bool valid = hash_from_words(c.tf, c.tr, w0, w1, m0, m1, rs * 32u, npos, c.lane, sc, ci, bi, &h0);
+      f(s, thr, valid, h0, ci, bi);
     }
   }
 }
 
-__global__ void __launch_bounds__(kLevelWarps * 32) build_filters_levels_kernel(LevelParams p)
+// survivor lists: occurrences that passed level L, as (base hash, time | thr << 26)
+struct SurvList {
+  uint32_t* h0lo;
+  uint32_t* h0hi;
+  uint32_t* meta;
+  uint32_t* count;
+};
+__device__ __forceinline__ void surv_append(const SurvList& l, bool q, uint64_t h0, uint32_t meta, uint32_t lane)
+{
+  const uint32_t m = __ballot_sync(0xffffffffu, q);
+  if (m == 0u) return;
+  uint32_t base = 0;
+  if (lane == uint32_t(__ffs(m) - 1)) base = atomicAdd(l.count, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (q) {
+    const uint32_t i = base + __popc(m & ((1u << lane) - 1u));
+    l.h0lo[i] = uint32_t(h0); l.h0hi[i] = uint32_t(h0 >> 32); l.meta[i] = meta;
+  }
+}
+__device__ __forceinline__ void indices_from_h0(uint64_t h0, const StreamConsts& sc, uint32_t (&ci)[4], uint32_t (&bi)[4])
+{
+  uint64_t h1 = h0 * sc.mul1, h2 = h0 * sc.mul2, h3 = h0 * sc.mul3;
+  h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
+  ci[0] = cbf_index(h0); ci[1] = cbf_index(h1); ci[2] = cbf_index(h2); ci[3] = cbf_index(h3);
+  bi[0] = bf_index(h0); bi[1] = bf_index(h1); bi[2] = bf_index(h2); bi[3] = bf_index(h3);
+}
+// the level test: all four counters carry the current tag and a time before t
+__device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8_t* __restrict__ cbf, uint32_t tag, uint32_t t,
+                                           uint32_t L, const uint32_t (&ci)[4])
+{
+  uint32_t v[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) v[j] = __ldcg(V + ci[j]);
+  bool reached = true;
+  uint32_t mx = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    reached &= (v[j] & ~kTimeMask) == tag;
+    mx = max(mx, v[j] & kTimeMask);
+    if (cbf && v[j] == (tag | t)) cbf[ci[j]] = (uint8_t)L; // this occurrence moved counter j to level L
+  }
+  return reached && t > mx;
+}
+
+__global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kernel(LevelParams p)
 {
   __shared__ uint64_t tf[8 * 256];
   __shared__ uint64_t tr[8 * 256];
@@ -89,6 +134,8 @@ __global__ void __launch_bounds__(kLevelWarps * 32) build_filters_levels_kernel(
   uint32_t* __restrict__ V = p.V;
   unsigned long long ops = 0;
   uint32_t epoch = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
+  SurvList cur = { p.surv, p.surv + p.surv_cap, p.surv + 2 * size_t(p.surv_cap), p.surv_count };
+  SurvList nxt = { p.surv + 3 * size_t(p.surv_cap), p.surv + 4 * size_t(p.surv_cap), p.surv + 5 * size_t(p.surv_cap), p.surv_count + 1 };
 
   for (uint32_t sid = 0; sid < p.n_streams; sid++) {
     const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk;
@@ -103,8 +150,6 @@ __global__ void __launch_bounds__(kLevelWarps * 32) build_filters_levels_kernel(
     // contiguous share of the steps for this warp
     const uint32_t per = (n_steps + c.nwarps - 1) / c.nwarps;
     const uint32_t s_begin = min(n_steps, c.gwarp * per), s_end = min(n_steps, s_begin + per);
-    uint32_t* alive_cur = p.alive;
-    uint32_t* alive_nxt = p.alive + p.alive_words;
 
     // make sure the epochs of this stream fit below the tag wrap
     if (epoch + lmax + 1 > kMaxEpoch) {
@@ -116,11 +161,11 @@ __global__ void __launch_bounds__(kLevelWarps * 32) build_filters_levels_kernel(
     // ---- level 0 -> 1: every occurrence writes its time (the first toucher of a counter wins) ----
     epoch++;
     uint32_t tag = (63u - epoch) << kTimeBits;
+    if (gtid == 0) *cur.count = 0u;
     for_steps(p, c, batch, ki, sc, s_begin, s_end, [](uint32_t) { return true; },
-              [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+              [&](uint32_t s, uint32_t thr, bool valid, uint64_t h0, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
                 const uint32_t t = s * 32u + c.lane;
-                const bool q = valid && thr > 0u;
-                if (q) {
+                if (valid && thr > 0u) {
 #pragma unroll
                   for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
                   if (thr == 1u) {
@@ -129,67 +174,67 @@ __global__ void __launch_bounds__(kLevelWarps * 32) build_filters_levels_kernel(
                   }
                 }
                 if (valid) ops++;
-                const uint32_t m = __ballot_sync(0xffffffffu, q);
-                if (c.lane == 0) alive_cur[s] = m;
+                (void)h0;
               });
     grid.sync();
 
     // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
     // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
     const uint32_t lread = cbf ? lmax : lmax - 1u;
-    for (uint32_t L = 1; L <= lread; L++) {
-      // ---- read: who sees all four counters at >= L before its own time? ----
-      const bool last = L == lread;
-      for_steps(p, c, batch, ki, sc, s_begin, s_end,
-                [&](uint32_t s) {
-                  const bool on = alive_cur[s] != 0u;
-                  if (!on && c.lane == 0) alive_nxt[s] = 0u;
-                  return on;
-                },
-                [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
-                  const uint32_t am = alive_cur[s];
+    if (lread >= 1u) {
+      // ---- level 1 read, from the sequence: survivors go to a compact list ----
+      for_steps(p, c, batch, ki, sc, s_begin, s_end, [](uint32_t) { return true; },
+                [&](uint32_t s, uint32_t thr, bool valid, uint64_t h0, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
                   const uint32_t t = s * 32u + c.lane;
                   bool q = false;
-                  if ((am >> c.lane) & 1u) {
-                    uint32_t v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[j] = __ldcg(V + ci[j]);
-                    bool reached = true;
-                    uint32_t mx = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                      reached &= (v[j] & ~kTimeMask) == tag;
-                      mx = max(mx, v[j] & kTimeMask);
-                      // this occurrence is the one that moved counter j to level L
-                      if (cbf && v[j] == (tag | t)) cbf[ci[j]] = (uint8_t)L;
-                    }
-                    q = reached && t > mx && thr > L;
-                    if (q && thr == L + 1u) { // count after the update reaches thr: Bloom filter insert
+                  if (valid && thr > 0u) {
+                    q = level_test(V, cbf, tag, t, 1u, ci) && thr > 1u;
+                    if (q && thr == 2u) { // count after the update reaches thr: Bloom filter insert
 #pragma unroll
                       for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
                     }
                   }
-                  const uint32_t m = __ballot_sync(0xffffffffu, q);
-                  if (c.lane == 0) alive_nxt[s] = m;
-                  (void)valid;
+                  surv_append(cur, q, h0, t | (thr << kTimeBits), c.lane);
                 });
       grid.sync();
-      if (last) break;
-      // ---- write: survivors race for T_{L+1} of their counters ----
+    }
+    for (uint32_t L = 2; L <= lread; L++) {
+      // ---- write: survivors of level L-1 race for T_L of their counters ----
+      const uint32_t n_cur = *((volatile uint32_t*)cur.count);
       epoch++;
       tag = (63u - epoch) << kTimeBits;
-      for_steps(p, c, batch, ki, sc, s_begin, s_end, [&](uint32_t s) { return alive_nxt[s] != 0u; },
-                [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
-                  const uint32_t am = alive_nxt[s];
-                  if ((am >> c.lane) & 1u) {
-                    const uint32_t t = s * 32u + c.lane;
+      if (gtid == 0) *nxt.count = 0u;
+      for (uint32_t i = gtid; i < n_cur; i += gthreads) {
+        const uint64_t h0 = uint64_t(cur.h0lo[i]) | (uint64_t(cur.h0hi[i]) << 32);
+        const uint32_t t = cur.meta[i] & kTimeMask;
+        uint32_t ci[4], bi[4];
+        indices_from_h0(h0, sc, ci, bi);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
-                  }
-                  (void)thr; (void)valid; (void)bi;
-                });
+        for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
+      }
       grid.sync();
-      uint32_t* tmp = alive_cur; alive_cur = alive_nxt; alive_nxt = tmp;
+      // ---- read: who sees all four counters at >= L before its own time? ----
+      for (uint32_t i0 = gtid - c.lane; i0 < n_cur; i0 += gthreads) { // warp-uniform trip count
+        const uint32_t i = i0 + c.lane;
+        bool q = false;
+        uint64_t h0 = 0;
+        uint32_t meta = 0;
+        if (i < n_cur) {
+          h0 = uint64_t(cur.h0lo[i]) | (uint64_t(cur.h0hi[i]) << 32);
+          meta = cur.meta[i];
+          const uint32_t t = meta & kTimeMask, thr = meta >> kTimeBits;
+          uint32_t ci[4], bi[4];
+          indices_from_h0(h0, sc, ci, bi);
+          q = level_test(V, cbf, tag, t, L, ci) && thr > L;
+          if (q && thr == L + 1u) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
+          }
+        }
+        surv_append(nxt, q, h0, meta, c.lane);
+      }
+      grid.sync();
+      SurvList tmp = cur; cur = nxt; nxt = tmp;
     }
   }
 #pragma unroll

@@ -71,7 +71,7 @@ __device__ __forceinline__ void hash_bytes(const uint64_t* __restrict__ tf, cons
 __device__ __forceinline__ bool hash_from_words(const uint64_t* __restrict__ tf, const uint64_t* __restrict__ tr,
                                                 uint64_t w0, uint64_t w1, uint32_t m0, uint32_t m1, uint32_t p0,
                                                 uint32_t npos, uint32_t lane, const StreamConsts& sc, uint32_t (&ci)[4],
-                                                uint32_t (&bi)[4]);
+                                                uint32_t (&bi)[4], uint64_t* h0_out = nullptr);
 
 __device__ __forceinline__ bool hash_step(const uint64_t* __restrict__ tf, const uint64_t* __restrict__ tr,
                                           const SeqRegs& sr, uint32_t step, uint32_t p0, uint32_t npos, uint32_t lane,
@@ -92,7 +92,7 @@ __device__ __forceinline__ bool hash_step(const uint64_t* __restrict__ tf, const
 __device__ __forceinline__ bool hash_from_words(const uint64_t* __restrict__ tf, const uint64_t* __restrict__ tr,
                                                 uint64_t w0, uint64_t w1, uint32_t m0, uint32_t m1, uint32_t p0,
                                                 uint32_t npos, uint32_t lane, const StreamConsts& sc, uint32_t (&ci)[4],
-                                                uint32_t (&bi)[4])
+                                                uint32_t (&bi)[4], uint64_t* h0_out)
 {
   const uint32_t mw = __funnelshift_r(m0, m1, lane);
   const bool valid = (p0 + lane < npos) && ((mw & sc.kmask) == 0u);
@@ -112,6 +112,7 @@ __device__ __forceinline__ bool hash_from_words(const uint64_t* __restrict__ tf,
     default: hash_bytes<1>(tf, tr, w, fh, rh); break;
     }
     const uint64_t h0 = fh + rh;
+    if (h0_out) *h0_out = h0;
     uint64_t h1 = h0 * sc.mul1, h2 = h0 * sc.mul2, h3 = h0 * sc.mul3;
     h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
     ci[0] = cbf_index(h0); ci[1] = cbf_index(h1); ci[2] = cbf_index(h2); ci[3] = cbf_index(h3);

@@ -34,11 +34,12 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   const uint32_t* step_pre;       // [nk][n_entries + 1]: steps before entry e, for every k index
   const uint32_t* batch_max_thr;  // per batch: largest kmer_threshold among its entries
   uint32_t* V;                    // kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
-  uint32_t* alive;                // 2 * alive_words survivor masks, one word per step
+  uint32_t* surv;                 // survivor lists: 6 arrays of surv_cap words (2 lists x {h0 lo, h0 hi, time|thr})
+  uint32_t* surv_count;           // 2 list lengths
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
   uint32_t* bf_pool;
   unsigned long long* counters;
-  uint32_t alive_words;
+  uint32_t surv_cap;
   uint32_t n_entries;
   uint32_t n_streams;
   uint32_t first_batch;
