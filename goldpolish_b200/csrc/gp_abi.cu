@@ -59,7 +59,7 @@ struct gp_ctx {
   DevBuf d_batch_entry_off, d_entries, d_bf_pool, d_cbf_pool, d_stream_order, d_next, d_counters;
   // level-synchronous build
   DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive;
-  uint32_t alive_words = 0, n_entries = 0;
+  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0;
   bool levels_ok = false; // every stream fits the 26-bit occurrence clock
   int build_algo = 0;     // 0 = auto, 1 = warp per stream, 2 = level-synchronous
   int build_algo_resolved = 1;
@@ -351,7 +351,9 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
     GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
     GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4));
-    GP_CUDA(ctx, ctx->d_alive.ensure((size_t(ctx->alive_words) * 32 * 6 + 2) * 4)); // two survivor lists + their lengths
+    // two survivor lists of 5 words per entry, room for chunk-granular reservation, + their lengths
+    ctx->surv_cap = uint32_t(size_t(ctx->alive_words) * 32 + size_t(8192) * 256);
+    GP_CUDA(ctx, ctx->d_alive.ensure((size_t(ctx->surv_cap) * 10 + 2) * 4));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_step_pre.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_max_thr.p, maxthr.data(), maxthr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -450,11 +452,11 @@ int gp_build_run(gp_ctx* ctx)
     p.batch_max_thr = ctx->d_batch_max_thr.as<uint32_t>();
     p.V = ctx->d_V.as<uint32_t>();
     p.surv = ctx->d_alive.as<uint32_t>();
-    p.surv_count = ctx->d_alive.as<uint32_t>() + size_t(6) * ctx->alive_words * 32;
+    p.surv_count = ctx->d_alive.as<uint32_t>() + size_t(10) * ctx->surv_cap;
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
     p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
     p.counters = ctx->d_counters.as<unsigned long long>();
-    p.surv_cap = ctx->alive_words * 32;
+    p.surv_cap = ctx->surv_cap;
     p.n_entries = ctx->n_entries;
     p.n_streams = ctx->wave_count[wv] * c.nk;
     p.first_batch = ctx->wave_first[wv];

@@ -61,44 +61,74 @@ __device__ __forceinline__ void for_steps(const LevelParams& p, const LevelCtx& 
     const uint32_t len = p.read_len[ent.read_id];
     const uint64_t wbase = p.read_boff[ent.read_id] >> 5;
     const uint32_t npos = len - sc.k + 1;
+    // the words of step s+1 are requested before step s is processed (one read per warp is a
+    // dependent chain of HBM latencies otherwise)
+    uint32_t rs = s - first;
+    uint64_t w0 = __ldg(p.pk + wbase + rs), w1 = __ldg(p.pk + wbase + rs + 1);
+    uint32_t m0 = __ldg(p.nm + wbase + rs), m1 = __ldg(p.nm + wbase + rs + 1);
     for (; s < last && s < s_end; s++) {
-      if (!wanted(s)) continue;      // nothing of this step is still in play
-      const uint32_t rs = s - first; // step within the read
-      const uint64_t w0 = __ldg(p.pk + wbase + rs), w1 = __ldg(p.pk + wbase + rs + 1);
-      const uint32_t m0 = __ldg(p.nm + wbase + rs), m1 = __ldg(p.nm + wbase + rs + 1);
+      rs = s - first; // step within the read
+      const uint64_t cw0 = w0, cw1 = w1;
+      const uint32_t cm0 = m0, cm1 = m1;
+      if (s + 1 < last && s + 1 < s_end) {
+        w0 = cw1; m0 = cm1; // consecutive steps share a word
+        w1 = __ldg(p.pk + wbase + rs + 2);
+        m1 = __ldg(p.nm + wbase + rs + 2);
+      }
+      if (!wanted(s)) continue;
       uint32_t ci[4], bi[4];
       uint64_t h0 = 0;
-      const bool valid = hash_from_words(c.tf, c.tr, w0, w1, m0, m1, rs * 32u, npos, c.lane, sc, ci, bi, &h0);
+      const bool valid = hash_from_words(c.tf, c.tr, cw0, cw1, cm0, cm1, rs * 32u, npos, c.lane, sc, ci, bi, &h0);
       f(s, thr, valid, h0, ci, bi);
     }
   }
 }
 
-// survivor lists: occurrences that passed level L, as (base hash, time | thr << 26)
+// Survivor lists: occurrences that passed level L.  An entry is five words: the four counter
+// indices (24 bits; bit 24 carries bit 21 of the hash, so that the 22-bit filter index is
+// recoverable without re-hashing) and time | thr << 26.  Warps reserve list space in chunks of
+// kChunk entries (one atomicAdd per chunk instead of one per step); unused tail slots of a
+// chunk are marked invalid.
+constexpr uint32_t kChunk = 64;
+constexpr uint32_t kInvalidMeta = 0xFFFFFFFFu;
 struct SurvList {
-  uint32_t* h0lo;
-  uint32_t* h0hi;
-  uint32_t* meta;
-  uint32_t* count;
+  uint32_t* w[5];   // w[0..3] packed indices, w[4] meta
+  uint32_t* count;  // entries reserved so far (multiple of kChunk)
 };
-__device__ __forceinline__ void surv_append(const SurvList& l, bool q, uint64_t h0, uint32_t meta, uint32_t lane)
+struct SurvCursor {
+  uint32_t next, end; // this warp's current chunk [next, end)
+};
+__device__ __forceinline__ uint32_t pack_index(uint32_t ci, uint32_t bi) { return ci | ((bi >> 21) << 24); }
+__device__ __forceinline__ void unpack_index(uint32_t w, uint32_t& ci, uint32_t& bi)
+{
+  ci = w & 0xFFFFFFu;
+  bi = (w & 0x1FFFFFu) | ((w >> 24) << 21);
+}
+__device__ __forceinline__ void surv_close(const SurvList& l, SurvCursor& cur, uint32_t lane)
+{ // invalidate what is left of the warp's chunk
+  for (uint32_t i = cur.next + lane; i < cur.end; i += 32) l.w[4][i] = kInvalidMeta;
+  cur.next = cur.end = 0;
+}
+__device__ __forceinline__ void surv_append(const SurvList& l, SurvCursor& cur, bool q, const uint32_t (&ci)[4],
+                                            const uint32_t (&bi)[4], uint32_t meta, uint32_t lane)
 {
   const uint32_t m = __ballot_sync(0xffffffffu, q);
   if (m == 0u) return;
-  uint32_t base = 0;
-  if (lane == uint32_t(__ffs(m) - 1)) base = atomicAdd(l.count, (uint32_t)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (q) {
-    const uint32_t i = base + __popc(m & ((1u << lane) - 1u));
-    l.h0lo[i] = uint32_t(h0); l.h0hi[i] = uint32_t(h0 >> 32); l.meta[i] = meta;
+  const uint32_t n = __popc(m);
+  if (cur.end - cur.next < n) { // not enough room: retire the chunk, reserve a new one
+    surv_close(l, cur, lane);
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(l.count, kChunk);
+    cur.next = __shfl_sync(0xffffffffu, base, 0);
+    cur.end = cur.next + kChunk;
   }
-}
-__device__ __forceinline__ void indices_from_h0(uint64_t h0, const StreamConsts& sc, uint32_t (&ci)[4], uint32_t (&bi)[4])
-{
-  uint64_t h1 = h0 * sc.mul1, h2 = h0 * sc.mul2, h3 = h0 * sc.mul3;
-  h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
-  ci[0] = cbf_index(h0); ci[1] = cbf_index(h1); ci[2] = cbf_index(h2); ci[3] = cbf_index(h3);
-  bi[0] = bf_index(h0); bi[1] = bf_index(h1); bi[2] = bf_index(h2); bi[3] = bf_index(h3);
+  if (q) {
+    const uint32_t i = cur.next + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+    for (int j = 0; j < 4; j++) l.w[j][i] = pack_index(ci[j], bi[j]);
+    l.w[4][i] = meta;
+  }
+  cur.next += n;
 }
 // the level test: all four counters carry the current tag and a time before t
 __device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8_t* __restrict__ cbf, uint32_t tag, uint32_t t,
@@ -134,8 +164,9 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   uint32_t* __restrict__ V = p.V;
   unsigned long long ops = 0;
   uint32_t epoch = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
-  SurvList cur = { p.surv, p.surv + p.surv_cap, p.surv + 2 * size_t(p.surv_cap), p.surv_count };
-  SurvList nxt = { p.surv + 3 * size_t(p.surv_cap), p.surv + 4 * size_t(p.surv_cap), p.surv + 5 * size_t(p.surv_cap), p.surv_count + 1 };
+  SurvList cur, nxt;
+  for (int j = 0; j < 5; j++) { cur.w[j] = p.surv + size_t(j) * p.surv_cap; nxt.w[j] = p.surv + size_t(5 + j) * p.surv_cap; }
+  cur.count = p.surv_count; nxt.count = p.surv_count + 1;
 
   for (uint32_t sid = 0; sid < p.n_streams; sid++) {
     const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk;
@@ -183,6 +214,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
     const uint32_t lread = cbf ? lmax : lmax - 1u;
     if (lread >= 1u) {
       // ---- level 1 read, from the sequence: survivors go to a compact list ----
+      SurvCursor sc1 = { 0, 0 };
       for_steps(p, c, batch, ki, sc, s_begin, s_end, [](uint32_t) { return true; },
                 [&](uint32_t s, uint32_t thr, bool valid, uint64_t h0, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
                   const uint32_t t = s * 32u + c.lane;
@@ -194,8 +226,10 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
                       for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
                     }
                   }
-                  surv_append(cur, q, h0, t | (thr << kTimeBits), c.lane);
+                  surv_append(cur, sc1, q, ci, bi, t | (thr << kTimeBits), c.lane);
+                  (void)h0;
                 });
+      surv_close(cur, sc1, c.lane);
       grid.sync();
     }
     for (uint32_t L = 2; L <= lread; L++) {
@@ -205,34 +239,34 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       tag = (63u - epoch) << kTimeBits;
       if (gtid == 0) *nxt.count = 0u;
       for (uint32_t i = gtid; i < n_cur; i += gthreads) {
-        const uint64_t h0 = uint64_t(cur.h0lo[i]) | (uint64_t(cur.h0hi[i]) << 32);
-        const uint32_t t = cur.meta[i] & kTimeMask;
-        uint32_t ci[4], bi[4];
-        indices_from_h0(h0, sc, ci, bi);
+        const uint32_t meta = cur.w[4][i];
+        if (meta == kInvalidMeta) continue;
+        const uint32_t t = meta & kTimeMask;
 #pragma unroll
-        for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
+        for (int j = 0; j < 4; j++) atomicMin(V + (cur.w[j][i] & 0xFFFFFFu), tag | t);
       }
       grid.sync();
       // ---- read: who sees all four counters at >= L before its own time? ----
+      SurvCursor scn = { 0, 0 };
       for (uint32_t i0 = gtid - c.lane; i0 < n_cur; i0 += gthreads) { // warp-uniform trip count
         const uint32_t i = i0 + c.lane;
         bool q = false;
-        uint64_t h0 = 0;
-        uint32_t meta = 0;
-        if (i < n_cur) {
-          h0 = uint64_t(cur.h0lo[i]) | (uint64_t(cur.h0hi[i]) << 32);
-          meta = cur.meta[i];
+        uint32_t meta = kInvalidMeta;
+        uint32_t ci[4] = { 0, 0, 0, 0 }, bi[4] = { 0, 0, 0, 0 };
+        if (i < n_cur) meta = cur.w[4][i];
+        if (meta != kInvalidMeta) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) unpack_index(cur.w[j][i], ci[j], bi[j]);
           const uint32_t t = meta & kTimeMask, thr = meta >> kTimeBits;
-          uint32_t ci[4], bi[4];
-          indices_from_h0(h0, sc, ci, bi);
           q = level_test(V, cbf, tag, t, L, ci) && thr > L;
           if (q && thr == L + 1u) {
 #pragma unroll
             for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
           }
         }
-        surv_append(nxt, q, h0, meta, c.lane);
+        surv_append(nxt, scn, q, ci, bi, meta, c.lane);
       }
+      surv_close(nxt, scn, c.lane);
       grid.sync();
       SurvList tmp = cur; cur = nxt; nxt = tmp;
     }
