@@ -784,7 +784,7 @@ int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t reg
   if (!ctx || !sectors_per_s || warps == 0 || iters == 0 || region_bytes < 4096) return GP_ERR_ARG;
   cudaSetDevice(ctx->cfg.device);
   DevBuf cbf, bf;
-  GP_CUDA(ctx, cbf.ensure(uint64_t(warps) * region_bytes));
+  GP_CUDA(ctx, cbf.ensure(std::max<uint64_t>(uint64_t(warps) * region_bytes, gp::kCbfCounters * 4)));
   cudaError_t e = bf.ensure(uint64_t(warps) * gp::kBfBytes);
   if (e != cudaSuccess) { cbf.release(); GP_CUDA(ctx, e); }
   cudaStream_t s = ctx->stream;

@@ -477,6 +477,29 @@ __global__ void __launch_bounds__(256) roof_kernel(uint8_t* cbf_pool, uint32_t* 
   uint8_t* cbf = cbf_pool + uint64_t(gw) * region;
   uint32_t* bf = bf_pool + uint64_t(gw) * kBfWords;
   uint64_t x = 0x9e3779b97f4a7c15ULL * (uint64_t(gw) * 32 + lane + 1);
+  if (mode == 3) {
+    // the level-synchronous kernel's shape: ALL warps share one array of 32-bit timestamps the
+    // size of one counting filter (40 MiB, L2 resident); a round is 4 atomicMin, the next 4 loads
+    uint32_t* V = reinterpret_cast<uint32_t*>(cbf_pool);
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+      uint32_t ci[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        ci[j] = uint32_t((x >> 11) % kCbfCounters);
+      }
+      if ((it & 1u) == 0u) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) atomicMin(V + ci[j], uint32_t(x >> 32) | (it << 26));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc ^= __ldcg(V + ci[j]);
+      }
+    }
+    if (acc == 0x12345678u) bf[0] = acc;
+    return;
+  }
   for (uint32_t it = 0; it < iters; it++) {
     uint32_t ci[4], bi[4], c[4];
 #pragma unroll
@@ -508,7 +531,9 @@ void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t
 {
   const uint32_t threads = 256;
   const uint32_t grid = (warps * 32 + threads - 1) / threads;
-  int mode = 0; // 0: the build kernel's mix; GP_ROOF_MODE=1 loads only, 2 loads + counter stores (experiments)
+  // 0: the warp-per-stream kernel's mix (private 10 MiB regions); 3: the level-synchronous kernel's
+  // shape (one shared 40 MiB array in L2); GP_ROOF_MODE=1 loads only, 2 loads + counter stores
+  int mode = 0;
   if (const char* m = std::getenv("GP_ROOF_MODE")) mode = std::atoi(m);
   roof_kernel<<<grid, threads, 0, s>>>(cbf_pool, bf_pool, region, iters, warps, mode);
 }
