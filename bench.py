@@ -379,18 +379,33 @@ def ours(args, rank, world, local_rank):
         peaks, peak_src = measured_peaks()
         kops = st["kmer_ops"]
         achieved = kops * ALGO_BYTES_PER_KMER_OP / (build_kernel_ms * 1e-3) / 1e9 if build_kernel_ms > 0 else 0.0
+        kname = {1: "gp::build_filters_kernel (one warp per stream, counters in HBM)",
+                 2: "gp::build_filters_levels_kernel (level-synchronous rounds, timestamps in L2)"}.get(st["build_kernel"], "?")
         roof = {"bound": "hbm", "achieved": achieved, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
                 "frac": achieved / float(peaks["hbm_gbs"]), "traffic": ncu_traffic(kops),
                 "traffic_source": "profiles/build_kernel_dram.json (ncu dram__bytes_read+write per k-mer op at 1 Mbp) x k-mer ops of this launch",
-                "kernel": "gp::build_filters_kernel", "kernel_ms": build_kernel_ms, "kmer_ops_per_launch": kops,
+                "kernel": kname, "kernel_ms": build_kernel_ms, "kmer_ops_per_launch": kops,
                 "algorithmic_bytes_per_kmer_op": ALGO_BYTES_PER_KMER_OP, "peak_source": peak_src,
                 "kmer_ops_per_s": kops / (build_kernel_ms * 1e-3) if build_kernel_ms > 0 else 0.0,
-                "edit_kernel_ms": edit_kernel_ms}
+                "build_slots": st["build_slots"], "edit_kernel_ms": edit_kernel_ms}
         if args.roof:
+            # measured random-access roofs (sector touches / s), same access shapes as the kernels:
+            #   hbm : private 10 MiB counter regions per warp (the one-warp-per-stream kernel's mix)
+            #   l2_ld / l2_red : random 4-byte loads / atomicMin over one shared 40 MiB array
+            # a k-mer op needs at least 4 loads + 4 atomics -> ops/s roof = 1 / (4/ld + 4/red)
             try:
-                sps, rms = ctx.roof_microbench(148 * 32, 2000)
-                roof["random_access_roof_sectors_per_s"] = sps
-                roof["frac_of_random_access_roof"] = (roof["kmer_ops_per_s"] * 8) / sps if sps else None
+                r = {}
+                for name, mode, region in (("hbm", "0", gp.CBF_BYTES), ("l2_ld", "5", 4096), ("l2_red", "4", 4096)):
+                    os.environ["GP_ROOF_MODE"] = mode
+                    r[name], _ = ctx.roof_microbench(148 * 24, 4000 if mode != "0" else 2000, region)
+                os.environ.pop("GP_ROOF_MODE", None)
+                roof["random_access_roof_sectors_per_s"] = r
+                if st["build_kernel"] == 2:
+                    ops_roof = 1.0 / (4.0 / r["l2_ld"] + 4.0 / r["l2_red"])
+                else:
+                    ops_roof = r["hbm"] / 8.0
+                roof["random_access_roof_kmer_ops_per_s"] = ops_roof
+                roof["frac_of_random_access_roof"] = roof["kmer_ops_per_s"] / ops_roof if ops_roof else None
             except Exception as e:  # measurement aid only
                 roof["random_access_roof_error"] = str(e)
         cpu = None

@@ -38,7 +38,8 @@ class _Stats(C.Structure):
                 ("edits", C.c_uint64), ("masked", C.c_uint64), ("rollbacks", C.c_uint64),
                 ("build_ms", C.c_float), ("polish_ms", C.c_float), ("pack_ms", C.c_float),
                 ("build_kernel_ms", C.c_float), ("edit_kernel_ms", C.c_float),
-                ("build_launches", C.c_uint32), ("polish_launches", C.c_uint32), ("pack_launches", C.c_uint32)]
+                ("build_launches", C.c_uint32), ("polish_launches", C.c_uint32), ("pack_launches", C.c_uint32),
+                ("build_kernel", C.c_uint32), ("build_slots", C.c_uint32)]
 
 
 READ_ENTRY_DTYPE = np.dtype([("read_id", np.uint32), ("kmer_threshold", np.uint32)])
@@ -49,7 +50,7 @@ EXPORTS = ["gp_default_config", "gp_ctx_create", "gp_ctx_destroy", "gp_last_erro
            "gp_ctx_synchronize", "gp_get_stats", "gp_reads_upload", "gp_build_filters", "gp_build_stage",
            "gp_build_run", "gp_build_fetch", "gp_build_fetch_cbf", "gp_filters_load", "gp_polish",
            "gp_polish_stage", "gp_polish_run", "gp_polish_fetch", "gp_kmer_threshold", "gp_mappings_cap",
-           "gp_guard_rejects", "gp_roof_microbench"]
+           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times"]
 
 
 def load_library():
@@ -91,6 +92,7 @@ def load_library():
     l.gp_guard_rejects.argtypes = [u64, u64]
     l.gp_guard_rejects.restype = C.c_int
     l.gp_roof_microbench.argtypes = [vp, u32, u32, u64, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    l.gp_build_round_times.argtypes = [vp, C.POINTER(u64)]
     _lib = l
     return l
 
@@ -252,6 +254,15 @@ class Context:
         return self.polish_fetch(out=out)
 
     # ---- measurement ----
+    def build_round_times(self):
+        """Level-synchronous build kernel, CTA 0: {round kind: (barrier wait ms, work ms, rounds)}."""
+        out = (C.c_uint64 * 16)()
+        self._ck(self._l.gp_build_round_times(self._h, out))
+        names = ("clear", "level0_write", "level1_read", "list_write", "list_read")
+        r = {n: (out[3 * i] / 1e6, out[3 * i + 1] / 1e6, int(out[3 * i + 2])) for i, n in enumerate(names)}
+        r["list_entries"] = int(out[15])
+        return r
+
     def roof_microbench(self, warps: int, iters: int, region_bytes: int = CBF_BYTES):
         sps, ms = C.c_double(), C.c_float()
         self._ck(self._l.gp_roof_microbench(self._h, warps, iters, region_bytes, C.byref(sps), C.byref(ms)))

@@ -58,8 +58,9 @@ struct gp_ctx {
   std::vector<uint32_t> wave_first, wave_count, wave_order_off;
   DevBuf d_batch_entry_off, d_entries, d_bf_pool, d_cbf_pool, d_stream_order, d_next, d_counters;
   // level-synchronous build
-  DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive;
-  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0;
+  DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel;
+  uint64_t anchor_stride = 0;
+  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 2;
   bool levels_ok = false; // every stream fits the 26-bit occurrence clock
   int build_algo = 0;     // 0 = auto, 1 = warp per stream, 2 = level-synchronous
   int build_algo_resolved = 1;
@@ -195,7 +196,7 @@ void gp_ctx_destroy(gp_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = { &ctx->d_ascii, &ctx->d_ascii_off, &ctx->d_pk, &ctx->d_nm, &ctx->d_read_boff, &ctx->d_read_len,
                      &ctx->d_batch_entry_off, &ctx->d_entries, &ctx->d_bf_pool, &ctx->d_cbf_pool, &ctx->d_stream_order,
-                     &ctx->d_next, &ctx->d_counters, &ctx->d_step_pre, &ctx->d_batch_max_thr, &ctx->d_V, &ctx->d_alive, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
+                     &ctx->d_next, &ctx->d_counters, &ctx->d_step_pre, &ctx->d_batch_max_thr, &ctx->d_V, &ctx->d_alive, &ctx->d_anchor, &ctx->d_entry_rel, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
                      &ctx->d_cap_off, &ctx->d_cur_len, &ctx->d_which, &ctx->d_dropped, &ctx->d_nodes, &ctx->d_node_off,
                      &ctx->d_contig_batch, &ctx->d_order, &ctx->d_pnext, &ctx->d_pcounters, &ctx->d_error, &ctx->d_out,
                      &ctx->d_out_off };
@@ -343,19 +344,42 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
         if (st * 32 >= (1ull << 26)) ok = false; // occurrence clock is 26 bits
       }
     }
-    for (uint32_t b = 0; b < n_batches; b++)
-      for (uint64_t e = batch_entry_off[b]; e < batch_entry_off[b + 1]; e++) maxthr[b] = std::max(maxthr[b], entries[e].kmer_threshold);
+    std::vector<uint16_t> entry_rel(std::max<uint64_t>(n_entries, 1), 0);
+    for (uint32_t b = 0; b < n_batches; b++) {
+      if (batch_entry_off[b + 1] - batch_entry_off[b] > 0xFFFFull) ok = false; // step -> entry anchors are 16 bits
+      for (uint64_t e = batch_entry_off[b]; e < batch_entry_off[b + 1]; e++) {
+        maxthr[b] = std::max(maxthr[b], entries[e].kmer_threshold);
+        entry_rel[e] = uint16_t(e - batch_entry_off[b]);
+      }
+    }
+    ctx->anchor_stride = 1;
+    for (uint32_t ki = 0; ki < c.nk; ki++)
+      ctx->anchor_stride = std::max<uint64_t>(ctx->anchor_stride, uint64_t(pre[size_t(ki) * (n_entries + 1) + n_entries]) + 1);
     ctx->levels_ok = ok;
     ctx->n_entries = uint32_t(n_entries);
     ctx->alive_words = uint32_t(max_steps + 1);
     GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
     GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
-    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4));
-    // two survivor lists of 5 words per entry, room for chunk-granular reservation, + their lengths
-    ctx->surv_cap = uint32_t(size_t(ctx->alive_words) * 32 + size_t(8192) * 256);
-    GP_CUDA(ctx, ctx->d_alive.ensure((size_t(ctx->surv_cap) * 10 + 2) * 4));
+    // streams in flight in the level-synchronous kernel: each has its own timestamp array and
+    // survivor lists; two arrays (80 MiB) still sit in L2
+    ctx->level_slots = 2;
+    if (const char* f = std::getenv("GP_LEVEL_SLOTS")) ctx->level_slots = uint32_t(std::atoi(f));
+    ctx->level_slots = std::max(1u, std::min(ctx->level_slots, uint32_t(gp::levels_max_slots())));
+    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * ctx->level_slots));
+    // per slot: warp-private survivor lists, 5 words per entry (a warp's region is its share of
+    // the steps, rounded up, x 32); then the barrier counters
+    ctx->surv_cap = uint32_t(size_t(ctx->alive_words) * 32 + size_t(8192) * 4 * 32);
+    GP_CUDA(ctx, ctx->d_alive.ensure(size_t(ctx->surv_cap) * 5 * ctx->level_slots * 4 + 64));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_step_pre.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_max_thr.p, maxthr.data(), maxthr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ok) {
+      GP_CUDA(ctx, ctx->d_entry_rel.ensure(entry_rel.size() * 2));
+      GP_CUDA(ctx, ctx->d_anchor.ensure(ctx->anchor_stride * c.nk * 2));
+      GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_entry_rel.p, entry_rel.data(), entry_rel.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+      gp::launch_fill_anchor(ctx->d_step_pre.as<uint32_t>(), ctx->d_entry_rel.as<uint16_t>(), ctx->d_anchor.as<uint16_t>(),
+                             uint32_t(n_entries), c.nk, ctx->anchor_stride, ctx->stream);
+      GP_CUDA(ctx, cudaGetLastError());
+    }
     GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   // which build kernel: 0 = auto (level-synchronous whenever the 26-bit occurrence clock suffices)
@@ -409,7 +433,7 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
   GP_CUDA(ctx, ctx->d_entries.ensure(std::max<size_t>(n_entries, 1) * sizeof(gp_read_entry)));
   GP_CUDA(ctx, ctx->d_stream_order.ensure(std::max<size_t>(order_all.size(), 1) * 4));
   GP_CUDA(ctx, ctx->d_next.ensure(std::max<size_t>(n_waves, 1) * 4));
-  GP_CUDA(ctx, ctx->d_counters.ensure(16));
+  GP_CUDA(ctx, ctx->d_counters.ensure(gp::kBuildCounters * 8));
   cudaStream_t s = ctx->stream;
   GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_entry_off.p, batch_entry_off, (size_t(n_batches) + 1) * 8, cudaMemcpyHostToDevice, s));
   if (n_entries)
@@ -432,7 +456,7 @@ int gp_build_run(gp_ctx* ctx)
   cudaStream_t s = ctx->stream;
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
   uint32_t launches = 0;
-  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, gp::kBuildCounters * 8, s));
   if (ctx->n_batches) {
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_next.p, 0, ctx->wave_first.size() * 4, s));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->n_batches) * c.nk * gp::kBfBytes, s));
@@ -450,9 +474,12 @@ int gp_build_run(gp_ctx* ctx)
     p.entries = ctx->d_entries.as<gp_read_entry>();
     p.step_pre = ctx->d_step_pre.as<uint32_t>();
     p.batch_max_thr = ctx->d_batch_max_thr.as<uint32_t>();
+    p.anchor = ctx->d_anchor.as<uint16_t>();
+    p.anchor_stride = ctx->anchor_stride;
     p.V = ctx->d_V.as<uint32_t>();
     p.surv = ctx->d_alive.as<uint32_t>();
-    p.surv_count = ctx->d_alive.as<uint32_t>() + size_t(10) * ctx->surv_cap;
+    p.bars = reinterpret_cast<unsigned long long*>(ctx->d_alive.as<uint32_t>() + size_t(5) * ctx->surv_cap * ctx->level_slots);
+    p.n_slots = ctx->level_slots;
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
     p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
     p.counters = ctx->d_counters.as<unsigned long long>();
@@ -463,7 +490,8 @@ int gp_build_run(gp_ctx* ctx)
     p.nk = c.nk;
     for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
     if (c.keep_counters) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4, s));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * ctx->level_slots, s));
+    GP_CUDA(ctx, cudaMemsetAsync(p.bars, 0, 64, s));
     while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
     GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
     GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s));
@@ -498,7 +526,19 @@ int gp_build_run(gp_ctx* ctx)
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
   ctx->build_timed = true;
   ctx->stats.build_launches = launches;
+  ctx->stats.build_kernel = uint32_t(algo);
+  ctx->stats.build_slots = algo == 2 ? ctx->level_slots : 0;
   ctx->filters_ready = true;
+  return GP_OK;
+}
+
+int gp_build_round_times(gp_ctx* ctx, uint64_t out[16])
+{
+  if (!ctx || !out) return GP_ERR_ARG;
+  if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
+  cudaSetDevice(ctx->cfg.device);
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  GP_CUDA(ctx, cudaMemcpy(out, ctx->d_counters.as<unsigned long long>() + 2, 16 * 8, cudaMemcpyDeviceToHost));
   return GP_OK;
 }
 
@@ -803,7 +843,10 @@ int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t reg
   cbf.release(); bf.release();
   GP_CUDA(ctx, e);
   if (ms) *ms = t;
-  *sectors_per_s = double(warps) * iters * 32.0 * 8.0 / (double(t) * 1e-3);
+  // modes 3..5 touch 4 sectors per iteration (one round), the build-kernel mix 8
+  int touches = 8;
+  if (const char* m = std::getenv("GP_ROOF_MODE")) touches = std::atoi(m) >= 3 ? 4 : 8;
+  *sectors_per_s = double(warps) * iters * 32.0 * touches / (double(t) * 1e-3);
   return GP_OK;
 }
 

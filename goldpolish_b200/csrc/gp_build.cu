@@ -477,7 +477,8 @@ __global__ void __launch_bounds__(256) roof_kernel(uint8_t* cbf_pool, uint32_t* 
   uint8_t* cbf = cbf_pool + uint64_t(gw) * region;
   uint32_t* bf = bf_pool + uint64_t(gw) * kBfWords;
   uint64_t x = 0x9e3779b97f4a7c15ULL * (uint64_t(gw) * 32 + lane + 1);
-  if (mode == 3) {
+  if (mode >= 3) {
+    // (mode 4: atomicMin rounds only, mode 5: load rounds only)
     // the level-synchronous kernel's shape: ALL warps share one array of 32-bit timestamps the
     // size of one counting filter (40 MiB, L2 resident); a round is 4 atomicMin, the next 4 loads
     uint32_t* V = reinterpret_cast<uint32_t*>(cbf_pool);
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(256) roof_kernel(uint8_t* cbf_pool, uint32_t* 
         x ^= x << 13; x ^= x >> 7; x ^= x << 17;
         ci[j] = uint32_t((x >> 11) % kCbfCounters);
       }
-      if ((it & 1u) == 0u) {
+      if (mode == 4 || (mode == 3 && (it & 1u) == 0u)) {
 #pragma unroll
         for (int j = 0; j < 4; j++) atomicMin(V + ci[j], uint32_t(x >> 32) | (it << 26));
       } else {

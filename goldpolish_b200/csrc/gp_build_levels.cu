@@ -16,11 +16,14 @@
 // 40 MiB timestamp array then lives in L2 instead of HBM.  One array serves every level: entries
 // carry a 6-bit epoch tag (newer epochs compare smaller, so atomicMin overwrites stale entries,
 // and readers treat a stale tag as "never"), so nothing is cleared between levels or streams.
+//
+// Rounds of one stream are separated by grid-wide barriers.  To keep the SMs busy while a barrier
+// drains, the grid works on `n_slots` streams at a time (each with its own timestamp array and
+// survivor lists; 2 x 40 MiB still sits in the 126 MB L2): a CTA runs one round of slot 0,
+// ARRIVES at slot 0's barrier, runs one round of slot 1, arrives, and only then WAITS for slot
+// 0's barrier -- by which time the other CTAs have normally arrived (split-phase barrier).  Every
+// CTA takes the same deterministic sequence of (slot, stream, round) decisions from uniform data.
 #include "gp_hashing.cuh"
-
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 namespace gp {
 
@@ -35,68 +38,113 @@ struct LevelCtx {
   uint32_t lane, gwarp, nwarps;
 };
 
-// Walk the steps [s_begin, s_end) of stream (batch, ki) in order and call f(step, entry thr, valid,
-// base hash, ci, bi) for each.  A step is 32 consecutive k-mer starts of one read; steps of a stream are
-// numbered in the reference's order, which makes (step * 32 + lane) the occurrence time.
-template<typename P, typename F>
-__device__ __forceinline__ void for_steps(const LevelParams& p, const LevelCtx& c, uint32_t batch, uint32_t ki,
-                                          const StreamConsts& sc, uint32_t s_begin, uint32_t s_end, P&& wanted, F&& f)
+// A step is 32 consecutive k-mer starts of one read; steps of a stream are numbered in the
+// reference's order, which makes (step * 32 + lane) the occurrence time.  A warp's share of a
+// stream is kRuns runs of `len` consecutive steps, run r of warp w starting at step
+// (r * nwarps + w) * len: every warp samples the whole time axis, so that the survivors -- which
+// crowd towards late times -- spread evenly over the warps.  anchor[] maps a step to its read
+// entry; lane r fetches the head of run r, so the dependent loads of all runs overlap.
+constexpr uint32_t kRuns = 4;
+__device__ __forceinline__ uint32_t run_len(uint32_t n_steps, uint32_t nwarps)
 {
-  if (s_begin >= s_end) return;
+  return (n_steps + nwarps * kRuns - 1u) / (nwarps * kRuns);
+}
+
+// Calls f(step, entry thr, valid, ci, bi) for every step of this warp's runs.
+template<typename F>
+__device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c, uint32_t batch, uint32_t ki,
+                                         const StreamConsts& sc, uint32_t n_steps, F&& f)
+{
   const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
   const uint64_t e0 = p.batch_entry_off[batch], e1 = p.batch_entry_off[batch + 1];
-  const uint32_t base = pre[e0];
-  // entry that holds step s_begin: last e with pre[e] - base <= s_begin
-  uint64_t lo = e0, hi = e1;
-  while (hi - lo > 1) {
-    const uint64_t mid = (lo + hi) >> 1;
-    if (pre[mid] - base <= s_begin) lo = mid; else hi = mid;
+  const uint32_t base = __ldg(pre + e0);
+  const uint16_t* anchor = p.anchor + uint64_t(ki) * p.anchor_stride + base;
+  const uint32_t len = run_len(n_steps, c.nwarps);
+  uint32_t h_e = 0, h_first = 0, h_last = 0, h_thr = 0, h_len = 0, h_wlo = 0, h_whi = 0;
+  {
+    const uint32_t s0 = (c.lane * c.nwarps + c.gwarp) * len;
+    if (c.lane < kRuns && s0 < n_steps) {
+      h_e = __ldg(anchor + s0);
+      const uint64_t e = e0 + h_e;
+      h_first = __ldg(pre + e) - base; h_last = __ldg(pre + e + 1) - base;
+      const gp_read_entry ent = p.entries[e];
+      h_thr = ent.kmer_threshold;
+      h_len = p.read_len[ent.read_id];
+      const uint64_t wb = p.read_boff[ent.read_id] >> 5;
+      h_wlo = uint32_t(wb); h_whi = uint32_t(wb >> 32);
+    }
   }
-  uint32_t s = s_begin;
-  for (uint64_t e = lo; e < e1 && s < s_end; e++) {
-    const uint32_t first = pre[e] - base, last = pre[e + 1] - base;
-    if (last <= s) continue;
-    const gp_read_entry ent = p.entries[e];
-    const uint32_t thr = ent.kmer_threshold - 2u + ki; // utils.cpp:108,121
-    const uint32_t len = p.read_len[ent.read_id];
-    const uint64_t wbase = p.read_boff[ent.read_id] >> 5;
-    const uint32_t npos = len - sc.k + 1;
-    // the words of step s+1 are requested before step s is processed (one read per warp is a
-    // dependent chain of HBM latencies otherwise)
-    uint32_t rs = s - first;
-    uint64_t w0 = __ldg(p.pk + wbase + rs), w1 = __ldg(p.pk + wbase + rs + 1);
-    uint32_t m0 = __ldg(p.nm + wbase + rs), m1 = __ldg(p.nm + wbase + rs + 1);
-    for (; s < last && s < s_end; s++) {
-      rs = s - first; // step within the read
-      const uint64_t cw0 = w0, cw1 = w1;
-      const uint32_t cm0 = m0, cm1 = m1;
-      if (s + 1 < last && s + 1 < s_end) {
-        w0 = cw1; m0 = cm1; // consecutive steps share a word
-        w1 = __ldg(p.pk + wbase + rs + 2);
-        m1 = __ldg(p.nm + wbase + rs + 2);
+#pragma unroll 1
+  for (uint32_t r = 0; r < kRuns; r++) {
+    const uint32_t s0 = (r * c.nwarps + c.gwarp) * len;
+    if (s0 >= n_steps) break;
+    const uint32_t s_end = min(n_steps, s0 + len);
+    const uint64_t e_head = e0 + __shfl_sync(0xffffffffu, h_e, r);
+    uint32_t first = __shfl_sync(0xffffffffu, h_first, r), last = __shfl_sync(0xffffffffu, h_last, r);
+    uint32_t kthr = __shfl_sync(0xffffffffu, h_thr, r), len_r = __shfl_sync(0xffffffffu, h_len, r);
+    uint64_t wbase = uint64_t(__shfl_sync(0xffffffffu, h_wlo, r)) | (uint64_t(__shfl_sync(0xffffffffu, h_whi, r)) << 32);
+    uint32_t s = s0;
+    for (uint64_t e = e_head; e < e1 && s < s_end; e++) {
+      if (e != e_head) { // the run crosses into the next read
+        first = __ldg(pre + e) - base; last = __ldg(pre + e + 1) - base;
+        if (last <= s) continue;
+        const gp_read_entry ent = p.entries[e];
+        kthr = ent.kmer_threshold;
+        len_r = p.read_len[ent.read_id];
+        wbase = p.read_boff[ent.read_id] >> 5;
       }
-      if (!wanted(s)) continue;
-      uint32_t ci[4], bi[4];
-      uint64_t h0 = 0;
-      const bool valid = hash_from_words(c.tf, c.tr, cw0, cw1, cm0, cm1, rs * 32u, npos, c.lane, sc, ci, bi, &h0);
-      f(s, thr, valid, h0, ci, bi);
+      const uint32_t thr = kthr - 2u + ki; // utils.cpp:108,121
+      const uint32_t npos = len_r - sc.k + 1;
+      // the words of step s+1 are requested before step s is processed
+      uint32_t rs = s - first;
+      uint64_t w0 = __ldg(p.pk + wbase + rs), w1 = __ldg(p.pk + wbase + rs + 1);
+      uint32_t m0 = __ldg(p.nm + wbase + rs), m1 = __ldg(p.nm + wbase + rs + 1);
+      for (; s < last && s < s_end; s++) {
+        rs = s - first; // step within the read
+        const uint64_t cw0 = w0, cw1 = w1;
+        const uint32_t cm0 = m0, cm1 = m1;
+        if (s + 1 < last && s + 1 < s_end) {
+          w0 = cw1; m0 = cm1; // consecutive steps share a word
+          w1 = __ldg(p.pk + wbase + rs + 2);
+          m1 = __ldg(p.nm + wbase + rs + 2);
+        }
+        uint32_t ci[4], bi[4];
+        const bool valid = hash_from_words(c.tf, c.tr, cw0, cw1, cm0, cm1, rs * 32u, npos, c.lane, sc, ci, bi);
+        f(s, thr, valid, ci, bi);
+      }
     }
   }
 }
 
+// anchor[ki][s] = entry (relative to its batch's first entry) that holds global step s of k index ki
+__global__ void fill_anchor_kernel(const uint32_t* __restrict__ step_pre, const uint16_t* __restrict__ entry_rel,
+                                   uint16_t* __restrict__ anchor, uint32_t n_entries, uint32_t nk, uint64_t anchor_stride)
+{
+  const uint64_t w = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (w >= uint64_t(n_entries) * nk) return;
+  const uint32_t ki = uint32_t(w / n_entries), e = uint32_t(w - uint64_t(ki) * n_entries);
+  const uint32_t* pre = step_pre + uint64_t(ki) * (n_entries + 1);
+  const uint32_t a = pre[e], b = pre[e + 1];
+  const uint16_t v = entry_rel[e];
+  for (uint32_t s = a + lane; s < b; s += 32) anchor[uint64_t(ki) * anchor_stride + s] = v;
+}
+
+void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uint16_t* anchor, uint32_t n_entries,
+                        uint32_t nk, uint64_t anchor_stride, cudaStream_t s)
+{
+  const uint64_t warps = uint64_t(n_entries) * nk;
+  if (warps == 0) return;
+  fill_anchor_kernel<<<uint32_t((warps + 7) / 8), 256, 0, s>>>(step_pre, entry_rel, anchor, n_entries, nk, anchor_stride);
+}
+
 // Survivor lists: occurrences that passed level L.  An entry is five words: the four counter
 // indices (24 bits; bit 24 carries bit 21 of the hash, so that the 22-bit filter index is
-// recoverable without re-hashing) and time | thr << 26.  Warps reserve list space in chunks of
-// kChunk entries (one atomicAdd per chunk instead of one per step); unused tail slots of a
-// chunk are marked invalid.
-constexpr uint32_t kChunk = 64;
-constexpr uint32_t kInvalidMeta = 0xFFFFFFFFu;
+// recoverable without re-hashing) and time | thr << 26.  Lists are WARP-PRIVATE: a warp keeps the
+// survivors of its own share of the stream in its own region (share * 32 entries) and compacts
+// them in place level after level -- no list counters, no reservation atomics, no second buffer.
 struct SurvList {
-  uint32_t* w[5];   // w[0..3] packed indices, w[4] meta
-  uint32_t* count;  // entries reserved so far (multiple of kChunk)
-};
-struct SurvCursor {
-  uint32_t next, end; // this warp's current chunk [next, end)
+  uint32_t* w[5];   // w[0..3] packed indices, w[4] meta; already offset to the warp's region
 };
 __device__ __forceinline__ uint32_t pack_index(uint32_t ci, uint32_t bi) { return ci | ((bi >> 21) << 24); }
 __device__ __forceinline__ void unpack_index(uint32_t w, uint32_t& ci, uint32_t& bi)
@@ -104,31 +152,18 @@ __device__ __forceinline__ void unpack_index(uint32_t w, uint32_t& ci, uint32_t&
   ci = w & 0xFFFFFFu;
   bi = (w & 0x1FFFFFu) | ((w >> 24) << 21);
 }
-__device__ __forceinline__ void surv_close(const SurvList& l, SurvCursor& cur, uint32_t lane)
-{ // invalidate what is left of the warp's chunk
-  for (uint32_t i = cur.next + lane; i < cur.end; i += 32) l.w[4][i] = kInvalidMeta;
-  cur.next = cur.end = 0;
-}
-__device__ __forceinline__ void surv_append(const SurvList& l, SurvCursor& cur, bool q, const uint32_t (&ci)[4],
+// append the lanes with q set at position cnt of the warp's list
+__device__ __forceinline__ void surv_append(const SurvList& l, uint32_t& cnt, bool q, const uint32_t (&ci)[4],
                                             const uint32_t (&bi)[4], uint32_t meta, uint32_t lane)
 {
   const uint32_t m = __ballot_sync(0xffffffffu, q);
-  if (m == 0u) return;
-  const uint32_t n = __popc(m);
-  if (cur.end - cur.next < n) { // not enough room: retire the chunk, reserve a new one
-    surv_close(l, cur, lane);
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(l.count, kChunk);
-    cur.next = __shfl_sync(0xffffffffu, base, 0);
-    cur.end = cur.next + kChunk;
-  }
   if (q) {
-    const uint32_t i = cur.next + __popc(m & ((1u << lane) - 1u));
+    const uint32_t i = cnt + __popc(m & ((1u << lane) - 1u));
 #pragma unroll
     for (int j = 0; j < 4; j++) l.w[j][i] = pack_index(ci[j], bi[j]);
     l.w[4][i] = meta;
   }
-  cur.next += n;
+  cnt += __popc(m);
 }
 // the level test: all four counters carry the current tag and a time before t
 __device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8_t* __restrict__ cbf, uint32_t tag, uint32_t t,
@@ -147,129 +182,241 @@ __device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8
   }
   return reached && t > mx;
 }
+// the same test for occurrences that mostly fail it (level 1 from the sequence: most k-mers of
+// noisy reads are seen once, and such an occurrence is the first toucher of its own counters):
+// look at one counter, fetch the other three only if that one was reached before t
+__device__ __forceinline__ bool level_test_early(const uint32_t* __restrict__ V, uint32_t tag, uint32_t t, const uint32_t (&ci)[4])
+{
+  const uint32_t v0 = __ldcg(V + ci[0]);
+  if ((v0 & ~kTimeMask) != tag || (v0 & kTimeMask) >= t) return false;
+  uint32_t v[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) v[j] = __ldcg(V + ci[j + 1]);
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 3; j++) ok &= (v[j] & ~kTimeMask) == tag && (v[j] & kTimeMask) < t;
+  return ok;
+}
+__device__ __forceinline__ void bf_insert(uint32_t* __restrict__ bf, const uint32_t (&bi)[4])
+{
+  uint32_t w[4]; // the filter is 512 KiB and mostly hit by repeats of the same k-mers: look first
+#pragma unroll
+  for (int j = 0; j < 4; j++) w[j] = __ldcg(bf + (bi[j] >> 5));
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (!(w[j] & (1u << (bi[j] & 31u)))) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
+}
 
+// ---- split-phase grid barrier: one monotone counter per slot ----
+// polling uses a relaxed load (an acquire load costs an L1 invalidate -- CCTL.IVALL -- per poll);
+// one fence after the loop orders the data reads of the next round behind it
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_L1 = 2, PH_WRITE = 3, PH_READ = 4 };
+
+struct SlotState {      // uniform over the grid; written by thread 0 of each CTA between rounds
+  uint32_t sid;         // wave-local stream, >= n_streams when the slot has run dry
+  uint32_t phase, L, lread, epoch, tag, n_steps;
+  unsigned long long target; // barrier count that must be reached before the slot's next round
+};
+
+constexpr int kMaxSlots = 3;
+
+// 3 CTAs of 8 warps per SM (80 registers); a 64-register build with 4 CTAs spills and measured 8 % slower
 __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kernel(LevelParams p)
 {
   __shared__ uint64_t tf[8 * 256];
   __shared__ uint64_t tr[8 * 256];
-  cg::grid_group grid = cg::this_grid();
+  __shared__ SlotState slots[kMaxSlots];
+  __shared__ uint32_t next_sid;
+  __shared__ uint32_t warp_cnt[kMaxSlots][kLevelWarps]; // survivors in each warp's private list
   fill_hash_tables(tf, tr);
-  __syncthreads();
   LevelCtx c;
   c.tf = tf; c.tr = tr;
   c.lane = threadIdx.x & 31u;
   c.gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   c.nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  uint32_t* __restrict__ V = p.V;
   unsigned long long ops = 0;
-  uint32_t epoch = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
-  SurvList cur, nxt;
-  for (int j = 0; j < 5; j++) { cur.w[j] = p.surv + size_t(j) * p.surv_cap; nxt.w[j] = p.surv + size_t(5 + j) * p.surv_cap; }
-  cur.count = p.surv_count; nxt.count = p.surv_count + 1;
 
-  for (uint32_t sid = 0; sid < p.n_streams; sid++) {
-    const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk;
-    const uint32_t batch = p.first_batch + lb;
-    const StreamConsts sc = stream_consts(p.k[ki]);
-    const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
-    const uint32_t n_steps = pre[p.batch_entry_off[batch + 1]] - pre[p.batch_entry_off[batch]];
-    if (n_steps == 0) continue;
-    const uint32_t lmax = p.batch_max_thr[batch] - 2u + ki; // largest thr of the stream
-    uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
-    uint8_t* __restrict__ cbf = p.cbf_pool ? p.cbf_pool + uint64_t(sid) * kCbfCounters : nullptr;
-    // contiguous share of the steps for this warp
-    const uint32_t per = (n_steps + c.nwarps - 1) / c.nwarps;
-    const uint32_t s_begin = min(n_steps, c.gwarp * per), s_end = min(n_steps, s_begin + per);
-
-    // make sure the epochs of this stream fit below the tag wrap
-    if (epoch + lmax + 1 > kMaxEpoch) {
-      for (uint64_t i = gtid; i < kCbfCounters; i += gthreads) V[i] = 0xFFFFFFFFu;
-      epoch = 0;
-      grid.sync();
+  // stream -> (n_steps, lread); called by thread 0 only
+  auto begin_stream = [&](SlotState& S) {
+    for (;;) {
+      S.sid = next_sid++;
+      if (S.sid >= p.n_streams) return;
+      const uint32_t lb = S.sid / p.nk, ki = S.sid - lb * p.nk, batch = p.first_batch + lb;
+      const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
+      S.n_steps = pre[p.batch_entry_off[batch + 1]] - pre[p.batch_entry_off[batch]];
+      if (S.n_steps == 0) continue;
+      const uint32_t lmax = p.batch_max_thr[batch] - 2u + ki; // largest thr of the stream
+      // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
+      // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
+      S.lread = p.cbf_pool ? lmax : lmax - 1u;
+      if (S.epoch + lmax + 1 > kMaxEpoch) { S.phase = PH_CLEAR; return; } // the tags of this stream would wrap
+      S.phase = PH_L0;
+      S.epoch++;
+      S.tag = (63u - S.epoch) << kTimeBits;
+      return;
     }
-
-    // ---- level 0 -> 1: every occurrence writes its time (the first toucher of a counter wins) ----
-    epoch++;
-    uint32_t tag = (63u - epoch) << kTimeBits;
-    if (gtid == 0) *cur.count = 0u;
-    for_steps(p, c, batch, ki, sc, s_begin, s_end, [](uint32_t) { return true; },
-              [&](uint32_t s, uint32_t thr, bool valid, uint64_t h0, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
-                const uint32_t t = s * 32u + c.lane;
-                if (valid && thr > 0u) {
-#pragma unroll
-                  for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
-                  if (thr == 1u) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
-                  }
-                }
-                if (valid) ops++;
-                (void)h0;
-              });
-    grid.sync();
-
-    // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
-    // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
-    const uint32_t lread = cbf ? lmax : lmax - 1u;
-    if (lread >= 1u) {
-      // ---- level 1 read, from the sequence: survivors go to a compact list ----
-      SurvCursor sc1 = { 0, 0 };
-      for_steps(p, c, batch, ki, sc, s_begin, s_end, [](uint32_t) { return true; },
-                [&](uint32_t s, uint32_t thr, bool valid, uint64_t h0, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
-                  const uint32_t t = s * 32u + c.lane;
-                  bool q = false;
-                  if (valid && thr > 0u) {
-                    q = level_test(V, cbf, tag, t, 1u, ci) && thr > 1u;
-                    if (q && thr == 2u) { // count after the update reaches thr: Bloom filter insert
-#pragma unroll
-                      for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
-                    }
-                  }
-                  surv_append(cur, sc1, q, ci, bi, t | (thr << kTimeBits), c.lane);
-                  (void)h0;
-                });
-      surv_close(cur, sc1, c.lane);
-      grid.sync();
+  };
+  if (threadIdx.x == 0) {
+    next_sid = 0;
+    for (uint32_t s = 0; s < p.n_slots; s++) {
+      slots[s].epoch = 0; slots[s].target = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
+      begin_stream(slots[s]);
     }
-    for (uint32_t L = 2; L <= lread; L++) {
-      // ---- write: survivors of level L-1 race for T_L of their counters ----
-      const uint32_t n_cur = *((volatile uint32_t*)cur.count);
-      epoch++;
-      tag = (63u - epoch) << kTimeBits;
-      if (gtid == 0) *nxt.count = 0u;
-      for (uint32_t i = gtid; i < n_cur; i += gthreads) {
-        const uint32_t meta = cur.w[4][i];
-        if (meta == kInvalidMeta) continue;
-        const uint32_t t = meta & kTimeMask;
-#pragma unroll
-        for (int j = 0; j < 4; j++) atomicMin(V + (cur.w[j][i] & 0xFFFFFFu), tag | t);
+  }
+
+  for (;;) {
+    bool any = false;
+    for (uint32_t sl = 0; sl < p.n_slots; sl++) {
+      __syncthreads(); // slot states are stable from here to the next __syncthreads
+      SlotState& S = slots[sl];
+      if (S.sid >= p.n_streams) continue;
+      any = true;
+      unsigned long long* bar = p.bars + sl;
+      unsigned long long t_a = 0, t_b = 0;
+      if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) t_a = globaltimer_ns();
+        const unsigned long long target = S.target;
+        while (ld_relaxed_u64(bar) < target) { }
+        __threadfence();
+        if (blockIdx.x == 0) t_b = globaltimer_ns();
       }
-      grid.sync();
-      // ---- read: who sees all four counters at >= L before its own time? ----
-      SurvCursor scn = { 0, 0 };
-      for (uint32_t i0 = gtid - c.lane; i0 < n_cur; i0 += gthreads) { // warp-uniform trip count
-        const uint32_t i = i0 + c.lane;
-        bool q = false;
-        uint32_t meta = kInvalidMeta;
-        uint32_t ci[4] = { 0, 0, 0, 0 }, bi[4] = { 0, 0, 0, 0 };
-        if (i < n_cur) meta = cur.w[4][i];
-        if (meta != kInvalidMeta) {
+      __syncthreads(); // the slot's previous round is complete everywhere
+
+      const uint32_t sid = S.sid, phase = S.phase, tag = S.tag, L = S.L, n_steps = S.n_steps;
+      const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk, batch = p.first_batch + lb;
+      uint32_t* __restrict__ V = p.V + uint64_t(sl) * kCbfCounters;
+      uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
+      uint8_t* __restrict__ cbf = p.cbf_pool ? p.cbf_pool + uint64_t(sid) * kCbfCounters : nullptr;
+      const uint32_t wib = threadIdx.x >> 5;
+      // the warp's survivor list has room for every occurrence of its runs
+      SurvList lst;
+      {
+        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + uint64_t(c.gwarp) * (kRuns * run_len(n_steps, c.nwarps) * 32u);
 #pragma unroll
-          for (int j = 0; j < 4; j++) unpack_index(cur.w[j][i], ci[j], bi[j]);
-          const uint32_t t = meta & kTimeMask, thr = meta >> kTimeBits;
-          q = level_test(V, cbf, tag, t, L, ci) && thr > L;
-          if (q && thr == L + 1u) {
+        for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
+      }
+
+      if (phase == PH_CLEAR) {
+        for (uint64_t i = gtid; i < kCbfCounters; i += gthreads) V[i] = 0xFFFFFFFFu;
+      } else if (phase == PH_L0 || phase == PH_L1) {
+        const StreamConsts sc = stream_consts(p.k[ki]);
+        if (phase == PH_L0) {
+          // ---- level 0 -> 1: every occurrence writes its time (the first toucher of a counter wins) ----
+          for_runs(p, c, batch, ki, sc, n_steps,
+                    [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+                      const uint32_t t = s * 32u + c.lane;
+                      if (valid && thr > 0u) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
-          }
+                        for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
+                        if (thr == 1u) bf_insert(bf, bi);
+                      }
+                      if (valid) ops++;
+                    });
+        } else {
+          // ---- level 1 read, from the sequence: survivors go to the warp's list ----
+          uint32_t cnt = 0;
+          for_runs(p, c, batch, ki, sc, n_steps,
+                    [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+                      const uint32_t t = s * 32u + c.lane;
+                      bool q = false;
+                      if (valid && thr > 0u) {
+                        q = (cbf ? level_test(V, cbf, tag, t, 1u, ci) : level_test_early(V, tag, t, ci)) && thr > 1u;
+                        if (q && thr == 2u) bf_insert(bf, bi); // count after the update reaches thr
+                      }
+                      surv_append(lst, cnt, q, ci, bi, t | (thr << kTimeBits), c.lane);
+                    });
+          if (c.lane == 0) warp_cnt[sl][wib] = cnt;
         }
-        surv_append(nxt, scn, q, ci, bi, meta, c.lane);
+      } else if (phase == PH_WRITE) {
+        // ---- write: survivors of level L-1 race for T_L of their counters ----
+        const uint32_t cnt = warp_cnt[sl][wib];
+        if (c.lane == 0 && cnt) atomicAdd(p.counters + 17, (unsigned long long)cnt);
+        for (uint32_t i = c.lane; i < cnt; i += 32) {
+          const uint32_t t = __ldcg(lst.w[4] + i) & kTimeMask;
+          // survivors are mostly the many occurrences of the same true k-mers: look before the
+          // atomic, an entry that already holds an earlier time of this round cannot be lowered
+          uint32_t x[4], v[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) x[j] = __ldcg(lst.w[j] + i) & 0xFFFFFFu;
+#pragma unroll
+          for (int j = 0; j < 4; j++) v[j] = __ldcg(V + x[j]);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (v[j] > (tag | t)) atomicMin(V + x[j], tag | t);
+        }
+      } else {
+        // ---- read: who sees all four counters at >= L before its own time?  compact in place ----
+        const uint32_t cnt = warp_cnt[sl][wib];
+        uint32_t kept = 0;
+        for (uint32_t r = 0; r < cnt; r += 32) {
+          const uint32_t i = r + c.lane;
+          bool q = false;
+          uint32_t meta = 0;
+          uint32_t ci[4] = { 0, 0, 0, 0 }, bi[4] = { 0, 0, 0, 0 };
+          if (i < cnt) {
+            meta = __ldcg(lst.w[4] + i);
+#pragma unroll
+            for (int j = 0; j < 4; j++) unpack_index(__ldcg(lst.w[j] + i), ci[j], bi[j]);
+            const uint32_t t = meta & kTimeMask, thr = meta >> kTimeBits;
+            q = level_test(V, cbf, tag, t, L, ci) && thr > L;
+            if (q && thr == L + 1u) bf_insert(bf, bi);
+          }
+          // every lane has its entry in registers before the ballot inside returns; kept <= r
+          surv_append(lst, kept, q, ci, bi, meta, c.lane);
+        }
+        __syncwarp();
+        if (c.lane == 0) warp_cnt[sl][wib] = kept;
       }
-      surv_close(nxt, scn, c.lane);
-      grid.sync();
-      SurvList tmp = cur; cur = nxt; nxt = tmp;
+
+      __syncthreads(); // every thread of the CTA has issued its part of the round
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ull);
+        if (blockIdx.x == 0) { // where the time of CTA 0 goes, per kind of round: barrier wait, work, rounds
+          const unsigned long long t_c = globaltimer_ns();
+          p.counters[2 + phase * 3 + 0] += t_b - t_a;
+          p.counters[2 + phase * 3 + 1] += t_c - t_b;
+          p.counters[2 + phase * 3 + 2] += 1;
+        }
+        S.target += gridDim.x;
+        // next round of this slot (same decision in every CTA)
+        switch (phase) {
+        case PH_CLEAR:
+          S.epoch = 1; S.tag = (63u - 1u) << kTimeBits; S.phase = PH_L0;
+          break;
+        case PH_L0:
+          if (S.lread >= 1u) S.phase = PH_L1; else begin_stream(S);
+          break;
+        case PH_L1:
+          if (S.lread >= 2u) { S.phase = PH_WRITE; S.L = 2; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
+          else begin_stream(S);
+          break;
+        case PH_WRITE:
+          S.phase = PH_READ;
+          break;
+        default: // PH_READ
+          if (L < S.lread) { S.phase = PH_WRITE; S.L = L + 1u; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
+          else begin_stream(S);
+          break;
+        }
+      }
     }
+    if (!any) break;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);
@@ -285,11 +432,14 @@ int levels_max_grid(int sm_count)
   return sm_count * per_sm;
 }
 
+int levels_max_slots() { return kMaxSlots; }
+
 cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s)
 {
   if (p.n_streams == 0) return cudaSuccess;
   LevelParams lp = p;
   void* args[] = { &lp };
+  // cooperative launch: the barriers need every CTA resident
   return cudaLaunchCooperativeKernel((const void*)build_filters_levels_kernel, dim3(levels_max_grid(sm_count)),
                                      dim3(kLevelWarps * 32), args, 0, s);
 }

@@ -6,6 +6,8 @@
 
 namespace gp {
 
+constexpr int kBuildCounters = 32; // [0] k-mer ops, [1] serially resolved k-mers, [2..16] round times (levels kernel)
+
 struct BuildParams {
   const uint64_t* pk;               // packed reads, 32 bases per word
   const uint32_t* nm;               // "no seed" mask, 32 bases per word
@@ -33,13 +35,16 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   const gp_read_entry* entries;
   const uint32_t* step_pre;       // [nk][n_entries + 1]: steps before entry e, for every k index
   const uint32_t* batch_max_thr;  // per batch: largest kmer_threshold among its entries
-  uint32_t* V;                    // kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
-  uint32_t* surv;                 // survivor lists: 6 arrays of surv_cap words (2 lists x {h0 lo, h0 hi, time|thr})
-  uint32_t* surv_count;           // 2 list lengths
+  const uint16_t* anchor;         // [nk][anchor_stride]: global step of k index -> entry, relative to its batch
+  uint64_t anchor_stride;
+  uint32_t* V;                    // per slot: kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
+  uint32_t* surv;                 // per slot: 5 arrays of surv_cap words ({4 packed indices, time|thr}), warp-private regions
+  unsigned long long* bars;       // per slot: barrier arrival counter (zeroed before a launch)
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
   uint32_t* bf_pool;
   unsigned long long* counters;
   uint32_t surv_cap;
+  uint32_t n_slots;               // streams in flight (1..levels_max_slots())
   uint32_t n_entries;
   uint32_t n_streams;
   uint32_t first_batch;
@@ -79,6 +84,9 @@ void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint6
                        uint32_t* nm, uint32_t n_reads, cudaStream_t s);
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s);
+int levels_max_slots();
+void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uint16_t* anchor, uint32_t n_entries,
+                        uint32_t nk, uint64_t anchor_stride, cudaStream_t s);
 void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t iters, uint32_t warps, cudaStream_t s);
 void launch_edit(const EditParams& p, int sm_count, cudaStream_t s);
 

@@ -93,6 +93,9 @@ typedef struct {
   uint32_t build_launches;  /* kernels (not memsets) launched by the last build */
   uint32_t polish_launches; /* kernels launched by the last polish */
   uint32_t pack_launches;
+  uint32_t build_kernel;    /* which filter-build kernel ran: 1 = one warp per stream (in order, counters in HBM),
+                               2 = level-synchronous (order-free rounds, timestamps in L2) */
+  uint32_t build_slots;     /* level-synchronous kernel: streams in flight */
 } gp_stats;
 
 void gp_default_config(gp_config* cfg);
@@ -157,6 +160,13 @@ int gp_guard_rejects(uint64_t input_bytes, uint64_t output_bytes);
  * touches per second (8 per k-mer op) in *sectors_per_s. */
 int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t region_bytes, double* sectors_per_s,
                        float* ms);
+
+/* Diagnostic (no reference counterpart): where the time of one CTA of the level-synchronous build
+ * kernel went during the last gp_build_run, per kind of round r = 0 clear, 1 level-0 write,
+ * 2 level-1 read, 3 list write, 4 list read: out[3r] = ns waiting at the round barrier,
+ * out[3r+1] = ns working, out[3r+2] = rounds; out[15] = survivor-list entries visited by all
+ * list-write rounds of the launch. */
+int gp_build_round_times(gp_ctx* ctx, uint64_t out[16]);
 
 #ifdef __cplusplus
 }

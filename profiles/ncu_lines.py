@@ -56,5 +56,5 @@ def text(f, l):
             if os.path.exists(p): srcs[f] = open(p).read().splitlines(); break
         else: srcs[f] = []
     return srcs[f][l - 1].strip()[:90] if 0 < l <= len(srcs[f]) else ""
-for (f, l), (s, e) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+for (f, l), (s, e) in sorted(agg.items(), key=lambda kv: -kv[1][int(os.environ.get("SORT_SAMPLES","0")) ^ 1])[:top]:
     print(f"{100*e/E:5.1f}% instr {100*s/S:5.1f}% samples  {f}:{l}  {text(f, l)}")

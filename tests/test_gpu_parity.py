@@ -45,6 +45,24 @@ def test_filters_match_oracle(gp, small, bsize, algo, monkeypatch):
     assert st["build_launches"] > 0
 
 
+@pytest.mark.parametrize("slots", ["1", "2", "3"])
+@pytest.mark.parametrize("bsize", [1, 8])
+def test_level_slots_match_oracle(gp, small, bsize, slots, monkeypatch):
+    """The level-synchronous kernel with 1, 2 or 3 streams in flight (split-phase barriers); the
+    many small streams of bsize 1 also drive the epoch tags through their wrap (clear round)."""
+    monkeypatch.setenv("GP_BUILD_KERNEL", "l")
+    monkeypatch.setenv("GP_LEVEL_SLOTS", slots)
+    d, ctx = small
+    pl = plan(d, bsize=bsize)
+    bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    ref = oracle_build(d, pl)
+    for b in range(len(pl.batch_entry_off) - 1):
+        for ki in range(4):
+            assert np.array_equal(bfs[b, ki], ref[b].bfs[ki]), f"BF payload differs: batch {b} k={KS[ki]}"
+            if b == len(pl.batch_entry_off) - 2:
+                assert np.array_equal(ctx.fetch_cbf(b, ki), ref[b].cbfs[ki]), f"CBF differs: batch {b} k={KS[ki]}"
+
+
 def test_filters_wave_invariance(gp, small):
     """Splitting the batches into waves (limited counting-filter residency) changes nothing."""
     d, ctx = small
