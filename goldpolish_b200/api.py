@@ -50,7 +50,7 @@ EXPORTS = ["gp_default_config", "gp_ctx_create", "gp_ctx_destroy", "gp_last_erro
            "gp_ctx_synchronize", "gp_get_stats", "gp_reads_upload", "gp_build_filters", "gp_build_stage",
            "gp_build_run", "gp_build_fetch", "gp_build_fetch_cbf", "gp_filters_load", "gp_polish",
            "gp_polish_stage", "gp_polish_run", "gp_polish_fetch", "gp_kmer_threshold", "gp_mappings_cap",
-           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times"]
+           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run"]
 
 
 def load_library():
@@ -93,6 +93,7 @@ def load_library():
     l.gp_guard_rejects.restype = C.c_int
     l.gp_roof_microbench.argtypes = [vp, u32, u32, u64, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     l.gp_build_round_times.argtypes = [vp, C.POINTER(u64)]
+    l.gp_pipeline_run.argtypes = [vp]
     _lib = l
     return l
 
@@ -233,6 +234,10 @@ class Context:
 
     def polish_run(self):
         self._ck(self._l.gp_polish_run(self._h))
+
+    def pipeline_run(self):
+        """build_run + polish_run of the staged work as one overlapped pass (gp_pipeline_run)."""
+        self._ck(self._l.gp_pipeline_run(self._h))
 
     def polish_fetch(self, out=None):
         n = self._n_contigs

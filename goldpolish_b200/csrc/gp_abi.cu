@@ -38,6 +38,8 @@ struct gp_ctx {
   gp_config cfg;
   int sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  bool edit_ev_valid = false;                         // edit_ev[] were recorded by the last polish
+  bool pipelined = false;                             // last run was gp_pipeline_run's overlapped pass (device timers)
   cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // pack, build, polish (start, stop)
   std::vector<cudaEvent_t> wave_ev;  // build kernel only: (start, stop) per wave
   cudaEvent_t edit_ev[2] = { nullptr, nullptr }; // edit kernel only
@@ -71,6 +73,8 @@ struct gp_ctx {
   uint32_t grow = 0; // overflow retries enlarge the buffers
   std::vector<uint64_t> h_in_off, h_cap_off, h_node_off;
   std::vector<uint32_t> h_len, h_order, h_batch;
+  std::vector<uint32_t> h_batch_order, h_order_pipe;  // gp_pipeline_run: batches / contigs in build order
+  DevBuf d_batch_order, d_batch_done, d_order_pipe;
   DevBuf d_input, d_in_off, d_buf0, d_buf1, d_cap_off, d_cur_len, d_which, d_dropped, d_nodes, d_node_off,
     d_contig_batch, d_order, d_pnext, d_pcounters, d_error, d_out, d_out_off;
 };
@@ -199,7 +203,7 @@ void gp_ctx_destroy(gp_ctx* ctx)
                      &ctx->d_next, &ctx->d_counters, &ctx->d_step_pre, &ctx->d_batch_max_thr, &ctx->d_V, &ctx->d_alive, &ctx->d_anchor, &ctx->d_entry_rel, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
                      &ctx->d_cap_off, &ctx->d_cur_len, &ctx->d_which, &ctx->d_dropped, &ctx->d_nodes, &ctx->d_node_off,
                      &ctx->d_contig_batch, &ctx->d_order, &ctx->d_pnext, &ctx->d_pcounters, &ctx->d_error, &ctx->d_out,
-                     &ctx->d_out_off };
+                     &ctx->d_out_off, &ctx->d_batch_order, &ctx->d_batch_done, &ctx->d_order_pipe };
   for (auto* b : bufs) b->release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->edit_ev) if (ev) cudaEventDestroy(ev);
@@ -232,6 +236,21 @@ int gp_get_stats(const gp_ctx* cctx, gp_stats* out)
   cudaSetDevice(ctx->cfg.device);
   GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->pack_timed) cudaEventElapsedTime(&ctx->stats.pack_ms, ctx->ev[0], ctx->ev[1]);
+  if (ctx->build_timed && ctx->pipelined) {
+    // overlapped pass: one span for both stages by events, the kernels' own spans from their device timers
+    cudaEventElapsedTime(&ctx->stats.build_ms, ctx->ev[2], ctx->ev[3]);
+    unsigned long long c[gp::kBuildCounters], pc[8];
+    GP_CUDA(ctx, cudaMemcpy(c, ctx->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
+    GP_CUDA(ctx, cudaMemcpy(pc, ctx->d_pcounters.p, sizeof pc, cudaMemcpyDeviceToHost));
+    ctx->stats.kmer_ops = c[0];
+    ctx->stats.serial_kmers = c[1];
+    ctx->stats.build_kernel_ms = float(double(c[21] - c[20]) * 1e-6);
+    ctx->stats.edit_kernel_ms = float(double(pc[5] - pc[4]) * 1e-6);
+    ctx->stats.polish_ms = ctx->stats.edit_kernel_ms;
+    ctx->stats.triggers = pc[0]; ctx->stats.edits = pc[1]; ctx->stats.masked = pc[2]; ctx->stats.rollbacks = pc[3];
+    *out = ctx->stats;
+    return GP_OK;
+  }
   if (ctx->build_timed) {
     cudaEventElapsedTime(&ctx->stats.build_ms, ctx->ev[2], ctx->ev[3]);
     ctx->stats.build_kernel_ms = 0;
@@ -244,7 +263,7 @@ int gp_get_stats(const gp_ctx* cctx, gp_stats* out)
     ctx->stats.kmer_ops = c[0];
     ctx->stats.serial_kmers = c[1];
   }
-  if (ctx->polish_timed) {
+  if (ctx->polish_timed && ctx->edit_ev_valid) { // (a pipelined polish has no events of its own)
     cudaEventElapsedTime(&ctx->stats.polish_ms, ctx->ev[4], ctx->ev[5]);
     ctx->stats.edit_kernel_ms = 0;
     if (ctx->n_contigs) cudaEventElapsedTime(&ctx->stats.edit_kernel_ms, ctx->edit_ev[0], ctx->edit_ev[1]);
@@ -447,22 +466,14 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
   return GP_OK;
 }
 
-int gp_build_run(gp_ctx* ctx)
+// level-synchronous build of every wave on stream s; batch_order / batch_done / ctas_per_sm are
+// gp_pipeline_run's (NULL, NULL, 0 otherwise)
+static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batch_order, uint32_t* batch_done,
+                               int ctas_per_sm, uint32_t* launches_out)
 {
-  if (!ctx) return GP_ERR_ARG;
-  if (!ctx->build_staged) GP_FAIL(ctx, GP_ERR_STATE, "gp_build_run before gp_build_stage");
-  cudaSetDevice(ctx->cfg.device);
   const gp_config& c = ctx->cfg;
-  cudaStream_t s = ctx->stream;
-  GP_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
   uint32_t launches = 0;
-  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, gp::kBuildCounters * 8, s));
-  if (ctx->n_batches) {
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_next.p, 0, ctx->wave_first.size() * 4, s));
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->n_batches) * c.nk * gp::kBfBytes, s));
-  }
-  const int algo = ctx->build_algo_resolved;
-  for (size_t wv = 0; algo == 2 && wv < ctx->wave_first.size(); wv++) {
+  for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
     // level-synchronous: all SMs on one stream at a time, timestamps resident in L2
     gp::LevelParams p;
     std::memset(&p, 0, sizeof p);
@@ -493,10 +504,36 @@ int gp_build_run(gp_ctx* ctx)
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * ctx->level_slots, s));
     GP_CUDA(ctx, cudaMemsetAsync(p.bars, 0, 64, s));
     while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
-    GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
-    GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s));
-    GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
+    if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
+    p.batch_order = batch_order;
+    p.batch_done = batch_done;
+    GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s, ctas_per_sm));
+    if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
     launches += 1;
+  }
+  *launches_out = launches;
+  return GP_OK;
+}
+
+int gp_build_run(gp_ctx* ctx)
+{
+  if (!ctx) return GP_ERR_ARG;
+  if (!ctx->build_staged) GP_FAIL(ctx, GP_ERR_STATE, "gp_build_run before gp_build_stage");
+  cudaSetDevice(ctx->cfg.device);
+  const gp_config& c = ctx->cfg;
+  cudaStream_t s = ctx->stream;
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+  ctx->pipelined = false;
+  uint32_t launches = 0;
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, gp::kBuildCounters * 8, s));
+  if (ctx->n_batches) {
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_next.p, 0, ctx->wave_first.size() * 4, s));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->n_batches) * c.nk * gp::kBfBytes, s));
+  }
+  const int algo = ctx->build_algo_resolved;
+  if (algo == 2) {
+    // level-synchronous: all SMs on one stream at a time, timestamps resident in L2
+    if (int rc = build_launch_levels(ctx, s, nullptr, nullptr, 0, &launches)) return rc;
   }
   for (size_t wv = 0; algo == 1 && wv < ctx->wave_first.size(); wv++) {
     gp::BuildParams p;
@@ -628,7 +665,8 @@ static int polish_layout(gp_ctx* ctx)
 int gp_polish_stage(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uint64_t* offsets, const uint32_t* contig_batch)
 {
   if (!ctx || !offsets || (!seqs && n_contigs && offsets[n_contigs]) || (!contig_batch && n_contigs)) return GP_ERR_ARG;
-  if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "gp_polish needs filters (gp_build_filters or gp_filters_load)");
+  if (!ctx->filters_ready && !ctx->build_staged)
+    GP_FAIL(ctx, GP_ERR_STATE, "gp_polish needs filters (gp_build_filters, gp_build_stage or gp_filters_load)");
   cudaSetDevice(ctx->cfg.device);
   const uint32_t n = n_contigs;
   ctx->n_contigs = n;
@@ -653,7 +691,7 @@ int gp_polish_stage(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uin
   GP_CUDA(ctx, ctx->d_contig_batch.ensure(std::max<size_t>(n, 1) * 4));
   GP_CUDA(ctx, ctx->d_order.ensure(std::max<size_t>(n, 1) * 4));
   GP_CUDA(ctx, ctx->d_pnext.ensure(4));
-  GP_CUDA(ctx, ctx->d_pcounters.ensure(32));
+  GP_CUDA(ctx, ctx->d_pcounters.ensure(64));
   GP_CUDA(ctx, ctx->d_error.ensure(4));
   cudaStream_t s = ctx->stream;
   if (total) GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_input.p, seqs, total, cudaMemcpyHostToDevice, s));
@@ -669,19 +707,29 @@ int gp_polish_stage(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uin
   return GP_OK;
 }
 
-static int polish_launch(gp_ctx* ctx)
+// counters + contigs into their working buffers (stream s)
+static int polish_prepare(gp_ctx* ctx)
 {
-  const gp_config& c = ctx->cfg;
   cudaStream_t s = ctx->stream;
   const uint32_t n = ctx->n_contigs;
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pnext.p, 0, 4, s));
-  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pcounters.p, 0, 32, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pcounters.p, 0, 64, s));
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_error.p, 0, 4, s));
   if (n == 0) return GP_OK;
   const uint32_t grid = std::min<uint32_t>(n, uint32_t(ctx->sm_count) * 8u);
   scatter_contigs_kernel<<<grid, 256, 0, s>>>(ctx->d_input.as<char>(), ctx->d_in_off.as<uint64_t>(), ctx->d_buf0.as<char>(),
                                               ctx->d_cap_off.as<uint64_t>(), ctx->d_cur_len.as<uint32_t>(), n);
   GP_CUDA(ctx, cudaGetLastError());
+  return GP_OK;
+}
+
+// the edit kernel on stream es (the context's stream unless pipelined: then `order`, `batch_done` and
+// alongside are gp_pipeline_run's)
+static int polish_edit(gp_ctx* ctx, cudaStream_t es, const uint32_t* order, const uint32_t* batch_done, bool alongside)
+{
+  const gp_config& c = ctx->cfg;
+  const uint32_t n = ctx->n_contigs;
+  if (n == 0) return GP_OK;
   gp::EditParams p;
   std::memset(&p, 0, sizeof p);
   p.n_contigs = n;
@@ -695,7 +743,8 @@ static int polish_launch(gp_ctx* ctx)
   p.node_off = ctx->d_node_off.as<uint64_t>();
   p.contig_batch = ctx->d_contig_batch.as<uint32_t>();
   p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
-  p.order = ctx->d_order.as<uint32_t>();
+  p.order = order ? order : ctx->d_order.as<uint32_t>();
+  p.batch_done = batch_done;
   p.next_contig = ctx->d_pnext.as<uint32_t>();
   p.counters = ctx->d_pcounters.as<unsigned long long>();
   p.error = ctx->d_error.as<int>();
@@ -719,11 +768,17 @@ static int polish_launch(gp_ctx* ctx)
   }
   p.max_insertions = c.max_insertions; p.max_deletions = c.max_deletions; p.jump = c.jump;
   p.min_contig_len = c.min_contig_len; p.mode = c.mode; p.mask = c.mask;
-  GP_CUDA(ctx, cudaEventRecord(ctx->edit_ev[0], s));
-  gp::launch_edit(p, ctx->sm_count, s);
-  GP_CUDA(ctx, cudaGetLastError());
-  GP_CUDA(ctx, cudaEventRecord(ctx->edit_ev[1], s));
+  if (!alongside) GP_CUDA(ctx, cudaEventRecord(ctx->edit_ev[0], es));
+  GP_CUDA(ctx, gp::launch_edit(p, ctx->sm_count, es, alongside));
+  if (!alongside) GP_CUDA(ctx, cudaEventRecord(ctx->edit_ev[1], es));
+  ctx->edit_ev_valid = !alongside;
   return GP_OK;
+}
+
+static int polish_launch(gp_ctx* ctx)
+{
+  if (int rc = polish_prepare(ctx)) return rc;
+  return polish_edit(ctx, ctx->stream, nullptr, nullptr, false);
 }
 
 int gp_polish_run(gp_ctx* ctx)
@@ -736,6 +791,67 @@ int gp_polish_run(gp_ctx* ctx)
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   ctx->polish_timed = true;
   ctx->stats.polish_launches = ctx->n_contigs ? 2 : 0; // scatter + edit kernels
+  ctx->polish_done = true;
+  return GP_OK;
+}
+
+int gp_pipeline_run(gp_ctx* ctx)
+{
+  if (!ctx) return GP_ERR_ARG;
+  if (!ctx->build_staged) GP_FAIL(ctx, GP_ERR_STATE, "gp_pipeline_run before gp_build_stage");
+  if (!ctx->polish_staged) GP_FAIL(ctx, GP_ERR_STATE, "gp_pipeline_run before gp_polish_stage");
+  cudaSetDevice(ctx->cfg.device);
+  const gp_config& c = ctx->cfg;
+  const uint32_t n = ctx->n_contigs, nb = ctx->n_batches;
+  const bool overlap = ctx->build_algo_resolved == 2 && ctx->wave_first.size() == 1 && n && nb && !c.keep_counters &&
+                       !std::getenv("GP_NO_OVERLAP");
+  if (!overlap) { // nothing to overlap with (or the in-order kernel, which fills the SMs): one after the other
+    if (int rc = gp_build_run(ctx)) return rc;
+    return gp_polish_run(ctx);
+  }
+  // build order: batches with the longest contigs first (their edit chains are the critical path);
+  // contigs in the build order of their batches, longest first inside a batch
+  {
+    std::vector<uint32_t> maxlen(nb, 0), pos(nb, 0);
+    for (uint32_t i = 0; i < n; i++) maxlen[ctx->h_batch[i]] = std::max(maxlen[ctx->h_batch[i]], ctx->h_len[i]);
+    ctx->h_batch_order.resize(nb);
+    std::iota(ctx->h_batch_order.begin(), ctx->h_batch_order.end(), 0u);
+    std::stable_sort(ctx->h_batch_order.begin(), ctx->h_batch_order.end(), [&](uint32_t a, uint32_t b) { return maxlen[a] > maxlen[b]; });
+    for (uint32_t i = 0; i < nb; i++) pos[ctx->h_batch_order[i]] = i;
+    ctx->h_order_pipe.resize(n);
+    std::iota(ctx->h_order_pipe.begin(), ctx->h_order_pipe.end(), 0u);
+    std::stable_sort(ctx->h_order_pipe.begin(), ctx->h_order_pipe.end(), [&](uint32_t a, uint32_t b) {
+      const uint32_t pa = pos[ctx->h_batch[a]], pb = pos[ctx->h_batch[b]];
+      return pa != pb ? pa < pb : ctx->h_len[a] > ctx->h_len[b];
+    });
+  }
+  cudaStream_t s = ctx->stream;
+  GP_CUDA(ctx, ctx->d_batch_order.ensure(size_t(nb) * 4));
+  GP_CUDA(ctx, ctx->d_batch_done.ensure(size_t(nb) * 4));
+  GP_CUDA(ctx, ctx->d_order_pipe.ensure(size_t(n) * 4));
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_order.p, ctx->h_batch_order.data(), size_t(nb) * 4, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_order_pipe.p, ctx->h_order_pipe.data(), size_t(n) * 4, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_batch_done.p, 0, size_t(nb) * 4, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, gp::kBuildCounters * 8, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(nb) * c.nk * gp::kBfBytes, s));
+  if (int rc = polish_prepare(ctx)) return rc;
+  // the build kernel (2 CTAs per SM) signals `launch_dependents` as it starts; the edit kernel (persistent,
+  // one 3-warp CTA per SM) is launched behind it in the SAME stream with programmatic stream serialization, so
+  // it becomes resident next to the running build, takes the contigs in build order and waits for each one's
+  // filters.  No event may sit between the two launches; their durations come from device timers.
+  uint32_t launches = 0;
+  if (int rc = build_launch_levels(ctx, s, ctx->d_batch_order.as<uint32_t>(), ctx->d_batch_done.as<uint32_t>(), 2, &launches)) return rc;
+  if (int rc = polish_edit(ctx, s, ctx->d_order_pipe.as<uint32_t>(), ctx->d_batch_done.as<uint32_t>(), true)) return rc;
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+  ctx->pipelined = true;
+  ctx->build_timed = true;
+  ctx->polish_timed = true;
+  ctx->stats.build_launches = launches;
+  ctx->stats.build_kernel = 2;
+  ctx->stats.build_slots = ctx->level_slots;
+  ctx->stats.polish_launches = 2;
+  ctx->filters_ready = true;
   ctx->polish_done = true;
   return GP_OK;
 }
@@ -758,6 +874,10 @@ int gp_polish_fetch(gp_ctx* ctx, char* out_seqs, uint64_t out_cap, uint64_t* out
     }
     GP_CUDA(ctx, cudaStreamSynchronize(s));
     if (!err) break;
+    if (err == 2) { // pipelined edit kernel gave up waiting for filters (no co-residency): plain re-run, filters are final now
+      if (int rc = polish_launch(ctx)) return rc;
+      continue;
+    }
     // an edited contig outgrew its buffers: enlarge them and run the polish again on the device
     if (ctx->grow >= 4) GP_FAIL(ctx, GP_ERR_OVERFLOW, "edited contig outgrew its device buffers");
     ctx->grow++;

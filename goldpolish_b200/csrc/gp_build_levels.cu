@@ -25,6 +25,9 @@
 // CTA takes the same deterministic sequence of (slot, stream, round) decisions from uniform data.
 #include "gp_hashing.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace gp {
 
 constexpr uint32_t kTimeBits = 26;
@@ -165,6 +168,17 @@ __device__ __forceinline__ void surv_append(const SurvList& l, uint32_t& cnt, bo
   }
   cnt += __popc(m);
 }
+// fire-and-forget atomics (REDG): spelled in PTX because ptxas keeps the returning form (ATOMG
+// with a dead destination) for atomicMin/atomicOr in this kernel
+__device__ __forceinline__ void red_min(uint32_t* p, uint32_t v)
+{
+  asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or(uint32_t* p, uint32_t v)
+{
+  asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // the level test: all four counters carry the current tag and a time before t
 __device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8_t* __restrict__ cbf, uint32_t tag, uint32_t t,
                                            uint32_t L, const uint32_t (&ci)[4])
@@ -204,7 +218,7 @@ __device__ __forceinline__ void bf_insert(uint32_t* __restrict__ bf, const uint3
   for (int j = 0; j < 4; j++) w[j] = __ldcg(bf + (bi[j] >> 5));
 #pragma unroll
   for (int j = 0; j < 4; j++)
-    if (!(w[j] & (1u << (bi[j] & 31u)))) atomicOr(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
+    if (!(w[j] & (1u << (bi[j] & 31u)))) red_or(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
 }
 
 // ---- split-phase grid barrier: one monotone counter per slot ----
@@ -224,6 +238,12 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
   return t;
 }
 
+// wave-local batch index -> batch (the pipeline builds the batches with the longest contigs first)
+__device__ __forceinline__ uint32_t stream_batch(const LevelParams& p, uint32_t lb)
+{
+  return p.batch_order ? p.batch_order[p.first_batch + lb] : p.first_batch + lb;
+}
+
 enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_L1 = 2, PH_WRITE = 3, PH_READ = 4 };
 
 struct SlotState {      // uniform over the grid; written by thread 0 of each CTA between rounds
@@ -241,7 +261,10 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   __shared__ uint64_t tr[8 * 256];
   __shared__ SlotState slots[kMaxSlots];
   __shared__ uint32_t next_sid;
+  __shared__ uint32_t pend[kMaxSlots]; // CTA 0: batch + 1 of a finished stream whose last barrier is still draining
   __shared__ uint32_t warp_cnt[kMaxSlots][kLevelWarps]; // survivors in each warp's private list
+  if (p.batch_done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the edit kernel may join us now
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[20] = globaltimer_ns();
   fill_hash_tables(tf, tr);
   LevelCtx c;
   c.tf = tf; c.tr = tr;
@@ -256,10 +279,13 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
     for (;;) {
       S.sid = next_sid++;
       if (S.sid >= p.n_streams) return;
-      const uint32_t lb = S.sid / p.nk, ki = S.sid - lb * p.nk, batch = p.first_batch + lb;
+      const uint32_t lb = S.sid / p.nk, ki = S.sid - lb * p.nk, batch = stream_batch(p, lb);
       const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
       S.n_steps = pre[p.batch_entry_off[batch + 1]] - pre[p.batch_entry_off[batch]];
-      if (S.n_steps == 0) continue;
+      if (S.n_steps == 0) { // nothing to insert: the (zeroed) filter is final
+        if (p.batch_done && blockIdx.x == 0) atomicAdd(p.batch_done + batch, 1u);
+        continue;
+      }
       const uint32_t lmax = p.batch_max_thr[batch] - 2u + ki; // largest thr of the stream
       // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
       // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
@@ -275,6 +301,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
     next_sid = 0;
     for (uint32_t s = 0; s < p.n_slots; s++) {
       slots[s].epoch = 0; slots[s].target = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
+      pend[s] = 0;
       begin_stream(slots[s]);
     }
   }
@@ -293,12 +320,18 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         const unsigned long long target = S.target;
         while (ld_relaxed_u64(bar) < target) { }
         __threadfence();
-        if (blockIdx.x == 0) t_b = globaltimer_ns();
+        if (blockIdx.x == 0) {
+          t_b = globaltimer_ns();
+          if (pend[sl]) { // the slot's previous stream is complete on every CTA: its filter is final
+            if (p.batch_done) atomicAdd(p.batch_done + (pend[sl] - 1u), 1u);
+            pend[sl] = 0;
+          }
+        }
       }
       __syncthreads(); // the slot's previous round is complete everywhere
 
       const uint32_t sid = S.sid, phase = S.phase, tag = S.tag, L = S.L, n_steps = S.n_steps;
-      const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk, batch = p.first_batch + lb;
+      const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk, batch = stream_batch(p, lb);
       uint32_t* __restrict__ V = p.V + uint64_t(sl) * kCbfCounters;
       uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
       uint8_t* __restrict__ cbf = p.cbf_pool ? p.cbf_pool + uint64_t(sid) * kCbfCounters : nullptr;
@@ -322,7 +355,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
                       const uint32_t t = s * 32u + c.lane;
                       if (valid && thr > 0u) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) atomicMin(V + ci[j], tag | t);
+                        for (int j = 0; j < 4; j++) red_min(V + ci[j], tag | t);
                         if (thr == 1u) bf_insert(bf, bi);
                       }
                       if (valid) ops++;
@@ -357,7 +390,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
           for (int j = 0; j < 4; j++) v[j] = __ldcg(V + x[j]);
 #pragma unroll
           for (int j = 0; j < 4; j++)
-            if (v[j] > (tag | t)) atomicMin(V + x[j], tag | t);
+            if (v[j] > (tag | t)) red_min(V + x[j], tag | t);
         }
       } else {
         // ---- read: who sees all four counters at >= L before its own time?  compact in place ----
@@ -400,47 +433,63 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
           S.epoch = 1; S.tag = (63u - 1u) << kTimeBits; S.phase = PH_L0;
           break;
         case PH_L0:
-          if (S.lread >= 1u) S.phase = PH_L1; else begin_stream(S);
+          if (S.lread >= 1u) S.phase = PH_L1; else { pend[sl] = batch + 1u; begin_stream(S); }
           break;
         case PH_L1:
           if (S.lread >= 2u) { S.phase = PH_WRITE; S.L = 2; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
-          else begin_stream(S);
+          else { pend[sl] = batch + 1u; begin_stream(S); }
           break;
         case PH_WRITE:
           S.phase = PH_READ;
           break;
         default: // PH_READ
           if (L < S.lread) { S.phase = PH_WRITE; S.L = L + 1u; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
-          else begin_stream(S);
+          else { pend[sl] = batch + 1u; begin_stream(S); }
           break;
         }
       }
     }
     if (!any) break;
   }
+  if (p.batch_done && blockIdx.x == 0 && threadIdx.x == 0) { // last streams of the slots
+    for (uint32_t sl = 0; sl < p.n_slots; sl++) {
+      if (!pend[sl]) continue;
+      while (ld_relaxed_u64(p.bars + sl) < slots[sl].target) { }
+      __threadfence();
+      atomicAdd(p.batch_done + (pend[sl] - 1u), 1u);
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);
   if (c.lane == 0 && ops) atomicAdd(p.counters + 0, ops);
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[21] = globaltimer_ns();
 }
 
-int levels_max_grid(int sm_count)
+int levels_max_grid(int sm_count, int ctas_per_sm)
 {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_filters_levels_kernel, kLevelWarps * 32, 0);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
+  if (ctas_per_sm > 0) per_sm = std::min(per_sm, ctas_per_sm);
+  if (const char* e = std::getenv("GP_LEVEL_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e))); // experiments
   return sm_count * per_sm;
 }
 
 int levels_max_slots() { return kMaxSlots; }
 
-cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s)
+cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s, int ctas_per_sm)
 {
   if (p.n_streams == 0) return cudaSuccess;
+  static bool carve = false;
+  if (!carve) { // 132 KB of shared memory (3 CTAs x 33 KB), the rest L1; the edit kernel asks for the same
+    cudaFuncSetAttribute((const void*)build_filters_levels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
+    carve = true;
+  }
   LevelParams lp = p;
   void* args[] = { &lp };
   // cooperative launch: the barriers need every CTA resident
-  return cudaLaunchCooperativeKernel((const void*)build_filters_levels_kernel, dim3(levels_max_grid(sm_count)),
+  return cudaLaunchCooperativeKernel((const void*)build_filters_levels_kernel, dim3(levels_max_grid(sm_count, ctas_per_sm)),
                                      dim3(kLevelWarps * 32), args, 0, s);
 }
 

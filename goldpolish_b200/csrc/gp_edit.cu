@@ -1024,7 +1024,7 @@ __device__ __forceinline__ uint32_t emit_rope(const WS& w, char* dst, uint32_t c
   return o;
 }
 
-__global__ void __launch_bounds__(kEditWarps * 32) edit_kernel(EditParams p)
+__global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
 {
   __shared__ unsigned char vb_sh[kEditWarps][kVBuf];
   __shared__ unsigned char code_sh[256];
@@ -1036,6 +1036,11 @@ __global__ void __launch_bounds__(kEditWarps * 32) edit_kernel(EditParams p)
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.counters[4] = t;
+  }
   unsigned long long n_trig = 0, n_edit = 0, n_mask = 0, n_roll = 0;
   for (;;) {
     uint32_t slot = 0;
@@ -1043,6 +1048,22 @@ __global__ void __launch_bounds__(kEditWarps * 32) edit_kernel(EditParams p)
     slot = __shfl_sync(kFull, slot, 0);
     if (slot >= p.n_contigs) break;
     const uint32_t ci = p.order[slot];
+    if (p.batch_done) { // pipelined with the filter build: wait until the contig's batch has its nk filters
+      uint32_t ok = 1;
+      if (lane == 0) {
+        const volatile uint32_t* flag = p.batch_done + p.contig_batch[ci];
+        unsigned long long t0 = 0, t1 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*flag < p.nk) {
+          __nanosleep(256);
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 4000000000ull) { ok = 0; break; } // 4 s without the filters: the build is not running beside us
+        }
+        __threadfence();
+      }
+      ok = __shfl_sync(kFull, ok, 0);
+      if (!ok) { if (lane == 0) atomicExch(p.error, 2); break; } // the host re-runs the polish after the build
+    }
     const uint64_t off = p.cap_off[ci];
     const uint32_t cap = uint32_t(p.cap_off[ci + 1] - off);
     uint32_t len = p.cur_len[ci];
@@ -1093,12 +1114,42 @@ __global__ void __launch_bounds__(kEditWarps * 32) edit_kernel(EditParams p)
     if (n_edit) atomicAdd(p.counters + 1, n_edit);
     if (n_mask) atomicAdd(p.counters + 2, n_mask);
     if (n_roll) atomicAdd(p.counters + 3, n_roll);
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(p.counters + 5, t);
   }
 }
 
-void launch_edit(const EditParams& p, int sm_count, cudaStream_t s)
+// alongside_build (gp_pipeline_run): launched right behind the level-synchronous build kernel in the same
+// stream with programmatic stream serialization -- it starts once every build CTA has signalled
+// launch_dependents, i.e. when the build is resident, and fills what that leaves free: one 3-warp CTA per SM
+// (per scheduler: 2 build CTAs x 2 warps x 80 registers + one edit warp x 168 registers <= 16384).
+constexpr int kAlongsideWarps = 3;
+
+cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool alongside_build)
 {
-  if (p.n_contigs == 0) return;
+  if (p.n_contigs == 0) return cudaSuccess;
+  static bool attr = false;
+  if (!attr) { // same shared-memory carve-out as the build kernel (132 KB), so that the two can share an SM
+    cudaFuncSetAttribute((const void*)edit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
+    attr = true;
+  }
+  if (alongside_build) {
+    uint32_t grid = uint32_t(sm_count);
+    const uint32_t need = (p.n_contigs + kAlongsideWarps - 1) / kAlongsideWarps;
+    if (grid > need) grid = need;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kAlongsideWarps * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, edit_kernel, p);
+  }
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edit_kernel, kEditWarps * 32, 0);
   if (per_sm < 1) per_sm = 1;
@@ -1106,6 +1157,7 @@ void launch_edit(const EditParams& p, int sm_count, cudaStream_t s)
   const uint32_t need = (p.n_contigs + kEditWarps - 1) / kEditWarps;
   if (grid > need) grid = need;
   edit_kernel<<<grid, kEditWarps * 32, 0, s>>>(p);
+  return cudaGetLastError();
 }
 
 } // namespace gp

@@ -35,6 +35,8 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   const gp_read_entry* entries;
   const uint32_t* step_pre;       // [nk][n_entries + 1]: steps before entry e, for every k index
   const uint32_t* batch_max_thr;  // per batch: largest kmer_threshold among its entries
+  const uint32_t* batch_order;    // optional: build order -> batch (NULL = identity)
+  uint32_t* batch_done;           // optional: per batch, streams whose filter is final (gp_pipeline_run)
   const uint16_t* anchor;         // [nk][anchor_stride]: global step of k index -> entry, relative to its batch
   uint64_t anchor_stride;
   uint32_t* V;                    // per slot: kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
@@ -68,9 +70,10 @@ struct EditParams {
   const uint64_t* node_off;     // n_contigs + 1
   const uint32_t* contig_batch;
   const uint32_t* bf_pool;      // (batch * nk + ki) * kBfWords
+  const uint32_t* batch_done;   // optional: per batch, finished filter streams; a contig waits for nk of them
   const uint32_t* order;        // contig ids, longest first
   uint32_t* next_contig;
-  unsigned long long* counters; // [0] triggers [1] edits [2] masked [3] rollbacks
+  unsigned long long* counters; // [0] triggers [1] edits [2] masked [3] rollbacks [4] first / [5] last globaltimer ns
   int* error;                   // set to 1 on buffer overflow
   uint32_t nk;
   uint32_t k[kMaxK];
@@ -83,11 +86,11 @@ struct EditParams {
 void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint64_t* base_off, uint64_t* pk,
                        uint32_t* nm, uint32_t n_reads, cudaStream_t s);
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
-cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s, int ctas_per_sm = 0);
 int levels_max_slots();
 void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uint16_t* anchor, uint32_t n_entries,
                         uint32_t nk, uint64_t anchor_stride, cudaStream_t s);
 void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t iters, uint32_t warps, cudaStream_t s);
-void launch_edit(const EditParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool alongside_build = false);
 
 } // namespace gp

@@ -148,6 +148,16 @@ int gp_polish_stage(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uin
 int gp_polish_run(gp_ctx* ctx);
 int gp_polish_fetch(gp_ctx* ctx, char* out_seqs, uint64_t out_cap, uint64_t* out_offsets, uint8_t* out_dropped);
 
+/* gp_build_run + gp_polish_run of the staged work as ONE overlapped pass (needs gp_build_stage and
+ * gp_polish_stage first; results are fetched with gp_build_fetch / gp_polish_fetch as usual and are
+ * identical to the two separate calls).  The batches holding the longest contigs are built first, and a
+ * persistent edit kernel on a second internal stream starts on each contig as soon as the nk filters of
+ * its batch are final, next to the build kernel -- the reference's per-batch order "BF server answers,
+ * then goldpolish-ntedit runs" (scripts/goldpolish-polish-batch:62-105), kept per batch instead of per run.
+ * Falls back to the two calls in sequence when there is nothing to overlap (in-order build kernel,
+ * several waves, keep_counters). */
+int gp_pipeline_run(gp_ctx* ctx);
+
 /* ---- host-side rules shared with the reference ------------------------------------ */
 int gp_kmer_threshold(uint64_t mappings_bases);
 uint64_t gp_mappings_cap(uint64_t target_len, double subsample_max_per_10kbp);

@@ -94,6 +94,32 @@ def test_polish_matches_oracle(gp, small, bsize):
     assert st["edits"] > 0 and st["masked"] > 0
 
 
+@pytest.mark.parametrize("bsize", [1, 4])
+def test_pipeline_matches_separate_calls(gp, bsize):
+    """gp_pipeline_run (edit kernel beside the build kernel, batches built longest-contig first) gives the
+    same filters and the same polished sequences as gp_build_run followed by gp_polish_run, run twice."""
+    d = dataset(genome_len=150000)
+    pl = plan(d, bsize=bsize)
+    with gp.Context() as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+        out, off, dropped = ctx.polish(d.contig_seq, d.contig_off, pl.contig_batch)
+        out = out[:int(off[-1])].copy()
+    with gp.Context() as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        ctx.build_stage(pl.batch_entry_off, pl.entries)
+        ctx.polish_stage(d.contig_seq, d.contig_off, pl.contig_batch)
+        for _ in range(2):
+            ctx.pipeline_run()
+            bfs2 = ctx.build_fetch()
+            out2, off2, dropped2 = ctx.polish_fetch()
+            st = ctx.stats()
+            assert np.array_equal(bfs, bfs2)
+            assert np.array_equal(off, off2) and np.array_equal(dropped, dropped2)
+            assert np.array_equal(out, out2[:int(off2[-1])])
+            assert st["build_kernel"] == 2 and st["edits"] > 0
+
+
 def test_polish_identity_filters(gp, small):
     """All-ones filter: every k-mer present, nothing is edited.  All-zero filter: every position that
     passes the look-ahead is soft-masked and nothing else changes (size-independent properties)."""
