@@ -62,7 +62,7 @@ struct gp_ctx {
   // level-synchronous build
   DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel;
   uint64_t anchor_stride = 0;
-  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 2;
+  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_fused = 1;
   bool levels_ok = false; // every stream fits the 26-bit occurrence clock
   int build_algo = 0;     // 0 = auto, 1 = warp per stream, 2 = level-synchronous
   int build_algo_resolved = 1;
@@ -379,12 +379,15 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     ctx->alive_words = uint32_t(max_steps + 1);
     GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
     GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
-    // streams in flight in the level-synchronous kernel: each has its own timestamp array and
-    // survivor lists; two arrays (80 MiB) still sit in L2
-    ctx->level_slots = 2;
+    // level-synchronous kernel: streams in flight (each with two timestamp arrays and its survivor lists)
+    // and whether "read level L" and "write level L+1" are one round.  Default = one stream, fused rounds:
+    // 80 MiB of timestamps sit in L2; two streams with fused rounds (160 MiB) do not, and measured slower
+    ctx->level_slots = 1;
+    ctx->level_fused = 1;
     if (const char* f = std::getenv("GP_LEVEL_SLOTS")) ctx->level_slots = uint32_t(std::atoi(f));
     ctx->level_slots = std::max(1u, std::min(ctx->level_slots, uint32_t(gp::levels_max_slots())));
-    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * ctx->level_slots));
+    if (const char* f = std::getenv("GP_LEVEL_FUSED")) ctx->level_fused = std::atoi(f) ? 1u : 0u;
+    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * 2 * ctx->level_slots));
     // per slot: warp-private survivor lists, 5 words per entry (a warp's region is its share of
     // the steps, rounded up, x 32); then the barrier counters
     ctx->surv_cap = uint32_t(size_t(ctx->alive_words) * 32 + size_t(8192) * 4 * 32);
@@ -491,6 +494,7 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     p.surv = ctx->d_alive.as<uint32_t>();
     p.bars = reinterpret_cast<unsigned long long*>(ctx->d_alive.as<uint32_t>() + size_t(5) * ctx->surv_cap * ctx->level_slots);
     p.n_slots = ctx->level_slots;
+    p.fused = ctx->level_fused;
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
     p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
     p.counters = ctx->d_counters.as<unsigned long long>();
@@ -501,7 +505,7 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     p.nk = c.nk;
     for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
     if (c.keep_counters) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * ctx->level_slots, s));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * 2 * ctx->level_slots, s));
     GP_CUDA(ctx, cudaMemsetAsync(p.bars, 0, 64, s));
     while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));

@@ -248,7 +248,7 @@ enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_L1 = 2, PH_WRITE = 3, PH_READ = 4 
 
 struct SlotState {      // uniform over the grid; written by thread 0 of each CTA between rounds
   uint32_t sid;         // wave-local stream, >= n_streams when the slot has run dry
-  uint32_t phase, L, lread, epoch, tag, n_steps;
+  uint32_t phase, L, lread, epoch, tag, tag_next, n_steps;
   unsigned long long target; // barrier count that must be reached before the slot's next round
 };
 
@@ -330,9 +330,13 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       }
       __syncthreads(); // the slot's previous round is complete everywhere
 
-      const uint32_t sid = S.sid, phase = S.phase, tag = S.tag, L = S.L, n_steps = S.n_steps;
+      const uint32_t sid = S.sid, phase = S.phase, tag = S.tag, L = S.L, n_steps = S.n_steps, lread = S.lread;
       const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk, batch = stream_batch(p, lb);
-      uint32_t* __restrict__ V = p.V + uint64_t(sl) * kCbfCounters;
+      // two timestamp arrays per slot: T_L lives in array (L + 1) & 1 (the second one is used by the fused rounds only)
+      uint32_t* __restrict__ V0 = p.V + uint64_t(sl) * 2u * kCbfCounters;
+      uint32_t* __restrict__ V = V0 + ((p.fused && phase == PH_READ) ? ((L + 1u) & 1u) * kCbfCounters : 0u);
+      uint32_t* __restrict__ Vn = V0 + (L & 1u) * kCbfCounters; // T_{L+1} (fused rounds)
+      const uint32_t tag_next = S.tag_next;
       uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
       uint8_t* __restrict__ cbf = p.cbf_pool ? p.cbf_pool + uint64_t(sid) * kCbfCounters : nullptr;
       const uint32_t wib = threadIdx.x >> 5;
@@ -345,10 +349,27 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       }
 
       if (phase == PH_CLEAR) {
-        for (uint64_t i = gtid; i < kCbfCounters; i += gthreads) V[i] = 0xFFFFFFFFu;
+        for (uint64_t i = gtid; i < kCbfCounters * (p.fused ? 2u : 1u); i += gthreads) V0[i] = 0xFFFFFFFFu;
       } else if (phase == PH_L0 || phase == PH_L1) {
         const StreamConsts sc = stream_consts(p.k[ki]);
-        if (phase == PH_L0) {
+        if (phase == PH_L0 && p.fused) {
+          // ---- level 0 -> 1, fused form: every occurrence writes its time AND goes to the warp's list, so that
+          // level 1 is an ordinary list round (no second hashing pass) ----
+          uint32_t cnt = 0;
+          for_runs(p, c, batch, ki, sc, n_steps,
+                    [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+                      const uint32_t t = s * 32u + c.lane;
+                      const bool q = valid && thr > 0u;
+                      if (q) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) red_min(V + ci[j], tag | t);
+                        if (thr == 1u) bf_insert(bf, bi);
+                      }
+                      if (valid) ops++;
+                      surv_append(lst, cnt, q && thr > 1u, ci, bi, t | (thr << kTimeBits), c.lane);
+                    });
+          if (c.lane == 0) warp_cnt[sl][wib] = cnt;
+        } else if (phase == PH_L0) {
           // ---- level 0 -> 1: every occurrence writes its time (the first toucher of a counter wins) ----
           for_runs(p, c, batch, ki, sc, n_steps,
                     [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
@@ -406,8 +427,12 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
 #pragma unroll
             for (int j = 0; j < 4; j++) unpack_index(__ldcg(lst.w[j] + i), ci[j], bi[j]);
             const uint32_t t = meta & kTimeMask, thr = meta >> kTimeBits;
-            q = level_test(V, cbf, tag, t, L, ci) && thr > L;
+            q = ((cbf || L > 1u) ? level_test(V, cbf, tag, t, L, ci) : level_test_early(V, tag, t, ci)) && thr > L;
             if (q && thr == L + 1u) bf_insert(bf, bi);
+            if (q && p.fused && L < lread) { // fused rounds: the survivor races for T_{L+1} right away, in the other array
+#pragma unroll
+              for (int j = 0; j < 4; j++) red_min(Vn + ci[j], tag_next | t);
+            }
           }
           // every lane has its entry in registers before the ballot inside returns; kept <= r
           surv_append(lst, kept, q, ci, bi, meta, c.lane);
@@ -433,7 +458,10 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
           S.epoch = 1; S.tag = (63u - 1u) << kTimeBits; S.phase = PH_L0;
           break;
         case PH_L0:
-          if (S.lread >= 1u) S.phase = PH_L1; else { pend[sl] = batch + 1u; begin_stream(S); }
+          if (S.lread >= 1u && p.fused) { // T_1 carries S.tag; the round that reads it writes T_2 under the next tag
+            S.phase = PH_READ; S.L = 1; S.epoch++; S.tag_next = (63u - S.epoch) << kTimeBits;
+          } else if (S.lread >= 1u) S.phase = PH_L1;
+          else { pend[sl] = batch + 1u; begin_stream(S); }
           break;
         case PH_L1:
           if (S.lread >= 2u) { S.phase = PH_WRITE; S.L = 2; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
@@ -443,7 +471,8 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
           S.phase = PH_READ;
           break;
         default: // PH_READ
-          if (L < S.lread) { S.phase = PH_WRITE; S.L = L + 1u; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
+          if (L < S.lread && p.fused) { S.L = L + 1u; S.tag = S.tag_next; S.epoch++; S.tag_next = (63u - S.epoch) << kTimeBits; }
+          else if (L < S.lread) { S.phase = PH_WRITE; S.L = L + 1u; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
           else { pend[sl] = batch + 1u; begin_stream(S); }
           break;
         }

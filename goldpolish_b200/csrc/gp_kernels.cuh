@@ -39,7 +39,7 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   uint32_t* batch_done;           // optional: per batch, streams whose filter is final (gp_pipeline_run)
   const uint16_t* anchor;         // [nk][anchor_stride]: global step of k index -> entry, relative to its batch
   uint64_t anchor_stride;
-  uint32_t* V;                    // per slot: kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
+  uint32_t* V;                    // per slot: 2 x kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
   uint32_t* surv;                 // per slot: 5 arrays of surv_cap words ({4 packed indices, time|thr}), warp-private regions
   unsigned long long* bars;       // per slot: barrier arrival counter (zeroed before a launch)
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
@@ -47,6 +47,7 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   unsigned long long* counters;
   uint32_t surv_cap;
   uint32_t n_slots;               // streams in flight (1..levels_max_slots())
+  uint32_t fused;                 // 1: two timestamp arrays per slot, "read level L" and "write level L+1" are one round
   uint32_t n_entries;
   uint32_t n_streams;
   uint32_t first_batch;
