@@ -82,3 +82,28 @@ def test_polish_subset_consistency_and_identity(full):
     assert np.array_equal(d4 != 0, lens < 100)
     kept = np.concatenate([d.contig_seq[d.contig_off[c]:d.contig_off[c + 1]] for c in range(d.n_contigs) if lens[c] >= 100])
     assert np.array_equal(o4[:int(f4[-1])], kept)
+
+
+def test_three_device_paths_agree(full, monkeypatch):
+    """The oracle is too slow at this size, but three independent device paths must agree bit for bit:
+    the in-order one-warp-per-stream kernel (counters in HBM, sequential semantics inside a warp), the
+    level-synchronous kernel (order-free rounds over timestamps), and the overlapped pipeline (batches
+    built longest-contig first, edit kernel beside the build kernel)."""
+    gp, d, pl, ctx = full
+    monkeypatch.setenv("GP_BUILD_KERNEL", "s")
+    a = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    assert ctx.stats()["build_kernel"] == 1
+    monkeypatch.setenv("GP_BUILD_KERNEL", "l")
+    b = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    assert ctx.stats()["build_kernel"] == 2
+    assert np.array_equal(a, b)
+    out, off, dropped = ctx.polish(d.contig_seq, d.contig_off, pl.contig_batch)
+    out = out[:int(off[-1])].copy()
+    ctx.build_stage(pl.batch_entry_off, pl.entries)
+    ctx.polish_stage(d.contig_seq, d.contig_off, pl.contig_batch)
+    ctx.pipeline_run()
+    c = ctx.build_fetch()
+    out2, off2, dropped2 = ctx.polish_fetch()
+    assert np.array_equal(a, c)
+    assert np.array_equal(off, off2) and np.array_equal(dropped, dropped2)
+    assert np.array_equal(out, out2[:int(off2[-1])])
