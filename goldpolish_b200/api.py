@@ -30,7 +30,8 @@ class _Config(C.Structure):
                 ("mode", C.c_int32), ("mask", C.c_int32), ("missing_ratio", C.c_float),
                 ("edit_ratio", C.c_float), ("jump", C.c_uint32), ("min_contig_len", C.c_uint32),
                 ("max_resident_batches", C.c_uint32), ("use_ratio", C.c_int32),
-                ("missing_threshold", C.c_float), ("edit_threshold", C.c_float), ("keep_counters", C.c_int32)]
+                ("missing_threshold", C.c_float), ("edit_threshold", C.c_float), ("keep_counters", C.c_int32),
+                ("prep_mode", C.c_int32), ("prep_k", C.c_uint32), ("to_upper", C.c_int32)]
 
 
 class _Stats(C.Structure):
@@ -50,7 +51,7 @@ EXPORTS = ["gp_default_config", "gp_ctx_create", "gp_ctx_destroy", "gp_last_erro
            "gp_ctx_synchronize", "gp_get_stats", "gp_reads_upload", "gp_build_filters", "gp_build_stage",
            "gp_build_run", "gp_build_fetch", "gp_build_fetch_cbf", "gp_filters_load", "gp_polish",
            "gp_polish_stage", "gp_polish_run", "gp_polish_fetch", "gp_kmer_threshold", "gp_mappings_cap",
-           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run"]
+           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep"]
 
 
 def load_library():
@@ -94,6 +95,7 @@ def load_library():
     l.gp_roof_microbench.argtypes = [vp, u32, u32, u64, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     l.gp_build_round_times.argtypes = [vp, C.POINTER(u64)]
     l.gp_pipeline_run.argtypes = [vp]
+    l.gp_prep.argtypes = [vp, u32, vp, vp, C.c_int32, u32, C.c_int32, vp, u64, vp]
     _lib = l
     return l
 
@@ -131,7 +133,7 @@ class Context:
 
     def __init__(self, device: int = 0, ks=DEFAULT_KS, max_insertions=5, max_deletions=5, mode=1, mask=1,
                  missing_ratio=0.5, edit_ratio=0.5, jump=3, min_contig_len=100, max_resident_batches=0,
-                 keep_counters=0):
+                 keep_counters=0, prep_mode=0, prep_k=0, to_upper=0):
         self._l = load_library()
         cfg = _Config()
         self._l.gp_default_config(C.byref(cfg))
@@ -143,6 +145,7 @@ class Context:
         cfg.missing_ratio, cfg.edit_ratio, cfg.jump, cfg.min_contig_len = missing_ratio, edit_ratio, jump, min_contig_len
         cfg.max_resident_batches = max_resident_batches
         cfg.keep_counters = keep_counters
+        cfg.prep_mode, cfg.prep_k, cfg.to_upper = prep_mode, prep_k, to_upper
         h = C.c_void_p()
         rc = self._l.gp_ctx_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -257,6 +260,16 @@ class Context:
         self.polish_stage(seqs, offsets, contig_batch)
         self.polish_run()
         return self.polish_fetch(out=out)
+
+    # ---- goldpolish-mask / goldpolish-to-upper alone ----
+    def prep(self, seqs, offsets, mode: int, k: int = 0, to_upper: int = 0):
+        """mode 1 = `goldpolish-mask -s -k K`, 2 = `-n`, 0 = to-upper only.  Returns (bytes array, offsets)."""
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(off) - 1
+        out = np.empty(int(off[-1]) + n + 16, dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        self._ck(self._l.gp_prep(self._h, n, _ptr(seqs), _ptr(off), mode, k, to_upper, _ptr(out), out.nbytes, _ptr(out_off)))
+        return out, out_off
 
     # ---- measurement ----
     def build_round_times(self):

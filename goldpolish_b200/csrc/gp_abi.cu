@@ -132,6 +132,8 @@ int validate_config(const gp_config& c, std::string& why)
   if (c.max_deletions > 10) { why = "max_deletions must be <= 10"; return GP_ERR_ARG; }
   if (c.mode < 0 || c.mode > 2) { why = "mode must be 0..2"; return GP_ERR_ARG; }
   if (c.jump == 0) { why = "jump must be >= 1"; return GP_ERR_ARG; }
+  if (c.prep_mode < 0 || c.prep_mode > 2) { why = "prep_mode must be 0..2"; return GP_ERR_ARG; }
+  if (c.prep_mode && (c.prep_k == 0 || c.prep_k > 64)) { why = "prep_k must be within 1..64"; return GP_ERR_ARG; }
   if (!c.use_ratio && (!(c.missing_threshold > 0) || !(c.edit_threshold > 0))) { why = "x / y thresholds must be > 0"; return GP_ERR_ARG; }
   return GP_OK;
 }
@@ -779,10 +781,29 @@ static int polish_edit(gp_ctx* ctx, cudaStream_t es, const uint32_t* order, cons
   return GP_OK;
 }
 
+// goldpolish-mask / to-upper over the records resident after the edit kernel (or after gp_prep's staging)
+static int prep_launch(gp_ctx* ctx, int32_t mode, uint32_t k, int32_t to_upper)
+{
+  if (ctx->n_contigs == 0 || (!mode && !to_upper)) return GP_OK;
+  gp::PrepParams q;
+  std::memset(&q, 0, sizeof q);
+  q.n_contigs = ctx->n_contigs;
+  q.buf[0] = ctx->d_buf0.as<char>();
+  q.buf[1] = ctx->d_buf1.as<char>();
+  q.cap_off = ctx->d_cap_off.as<uint64_t>();
+  q.cur_len = ctx->d_cur_len.as<uint32_t>();
+  q.which = ctx->d_which.as<uint8_t>();
+  q.dropped = ctx->d_dropped.as<uint8_t>();
+  q.k = k; q.mode = mode; q.to_upper = to_upper;
+  GP_CUDA(ctx, gp::launch_prep(q, ctx->sm_count, ctx->stream));
+  return GP_OK;
+}
+
 static int polish_launch(gp_ctx* ctx)
 {
   if (int rc = polish_prepare(ctx)) return rc;
-  return polish_edit(ctx, ctx->stream, nullptr, nullptr, false);
+  if (int rc = polish_edit(ctx, ctx->stream, nullptr, nullptr, false)) return rc;
+  return prep_launch(ctx, ctx->cfg.prep_mode, ctx->cfg.prep_k, ctx->cfg.to_upper);
 }
 
 int gp_polish_run(gp_ctx* ctx)
@@ -794,9 +815,48 @@ int gp_polish_run(gp_ctx* ctx)
   if (int rc = polish_launch(ctx)) return rc;
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   ctx->polish_timed = true;
-  ctx->stats.polish_launches = ctx->n_contigs ? 2 : 0; // scatter + edit kernels
+  ctx->stats.polish_launches = ctx->n_contigs ? 2 + ((ctx->cfg.prep_mode || ctx->cfg.to_upper) ? 1 : 0) : 0; // scatter + edit (+ mask) kernels
   ctx->polish_done = true;
   return GP_OK;
+}
+
+int gp_prep(gp_ctx* ctx, uint32_t n_records, const char* seqs, const uint64_t* offsets, int32_t mode, uint32_t k,
+            int32_t to_upper, char* out_seqs, uint64_t out_cap, uint64_t* out_offsets)
+{
+  if (!ctx || !offsets || !out_offsets || (!seqs && n_records && offsets[n_records])) return GP_ERR_ARG;
+  if (mode < 0 || mode > 2 || (mode && (k == 0 || k > 64))) GP_FAIL(ctx, GP_ERR_ARG, "gp_prep: mode 0..2, k 1..64");
+  cudaSetDevice(ctx->cfg.device);
+  const uint32_t n = n_records;
+  ctx->n_contigs = n;
+  ctx->h_len.resize(n);
+  ctx->h_in_off.assign(offsets, offsets + n + 1);
+  ctx->h_batch.assign(n, 0u);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t len = offsets[i + 1] - offsets[i];
+    if (len >= (1ull << 31)) GP_FAIL(ctx, GP_ERR_ARG, "record longer than 2^31 bases");
+    ctx->h_len[i] = uint32_t(len);
+  }
+  const uint64_t total = offsets[n];
+  GP_CUDA(ctx, ctx->d_input.ensure(std::max<uint64_t>(total, 16)));
+  GP_CUDA(ctx, ctx->d_in_off.ensure((size_t(n) + 1) * 8));
+  GP_CUDA(ctx, ctx->d_cur_len.ensure(std::max<size_t>(n, 1) * 4));
+  GP_CUDA(ctx, ctx->d_which.ensure(std::max<size_t>(n, 1)));
+  GP_CUDA(ctx, ctx->d_dropped.ensure(std::max<size_t>(n, 1)));
+  GP_CUDA(ctx, ctx->d_pnext.ensure(4));
+  GP_CUDA(ctx, ctx->d_pcounters.ensure(64));
+  GP_CUDA(ctx, ctx->d_error.ensure(4));
+  cudaStream_t s = ctx->stream;
+  if (total) GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_input.p, seqs, total, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, offsets, (size_t(n) + 1) * 8, cudaMemcpyHostToDevice, s));
+  ctx->grow = 0;
+  if (int rc = polish_layout(ctx)) return rc;
+  if (int rc = polish_prepare(ctx)) return rc; // records into buffer 0
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_which.p, 0, std::max<size_t>(n, 1), s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_dropped.p, 0, std::max<size_t>(n, 1), s));
+  if (int rc = prep_launch(ctx, mode, k, to_upper)) return rc;
+  ctx->polish_staged = false; // the staged contigs (if any) were replaced
+  ctx->polish_done = true;
+  return gp_polish_fetch(ctx, out_seqs, out_cap, out_offsets, nullptr);
 }
 
 int gp_pipeline_run(gp_ctx* ctx)
@@ -847,6 +907,7 @@ int gp_pipeline_run(gp_ctx* ctx)
   uint32_t launches = 0;
   if (int rc = build_launch_levels(ctx, s, ctx->d_batch_order.as<uint32_t>(), ctx->d_batch_done.as<uint32_t>(), 2, &launches)) return rc;
   if (int rc = polish_edit(ctx, s, ctx->d_order_pipe.as<uint32_t>(), ctx->d_batch_done.as<uint32_t>(), true)) return rc;
+  if (int rc = prep_launch(ctx, c.prep_mode, c.prep_k, c.to_upper)) return rc;
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
   ctx->pipelined = true;
   ctx->build_timed = true;
@@ -854,7 +915,7 @@ int gp_pipeline_run(gp_ctx* ctx)
   ctx->stats.build_launches = launches;
   ctx->stats.build_kernel = 2;
   ctx->stats.build_slots = ctx->level_slots;
-  ctx->stats.polish_launches = 2;
+  ctx->stats.polish_launches = 2 + ((c.prep_mode || c.to_upper) ? 1 : 0);
   ctx->filters_ready = true;
   ctx->polish_done = true;
   return GP_OK;

@@ -84,6 +84,18 @@ struct EditParams {
   int32_t mode, mask;
 };
 
+struct PrepParams {             // goldpolish-mask / goldpolish-to-upper on the resident contigs (gp_prep.cu)
+  uint32_t n_contigs;
+  char* buf[2];
+  const uint64_t* cap_off;
+  uint32_t* cur_len;            // in: length, out: length after masking / stripping
+  uint8_t* which;               // in/out: buffer index holding the record
+  const uint8_t* dropped;
+  uint32_t k;                   // -k
+  int32_t mode;                 // 0: to-upper only, 1: soft-mask (-s), 2: hard-mask (-n)
+  int32_t to_upper;
+};
+
 void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint64_t* base_off, uint64_t* pk,
                        uint32_t* nm, uint32_t n_reads, cudaStream_t s);
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
@@ -92,6 +104,7 @@ int levels_max_slots();
 void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uint16_t* anchor, uint32_t n_entries,
                         uint32_t nk, uint64_t anchor_stride, cudaStream_t s);
 void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t iters, uint32_t warps, cudaStream_t s);
+cudaError_t launch_prep(const PrepParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool alongside_build = false);
 
 } // namespace gp

@@ -70,6 +70,11 @@ typedef struct {
   float missing_threshold;         /* -x */
   float edit_threshold;            /* -y */
   int32_t keep_counters;           /* 1: also materialise the counting-filter bytes (gp_build_fetch_cbf; parity tests) */
+  /* optional post-pass on the polished records while they are still on the device (default off):
+   * goldpolish-mask (scripts/goldpolish-mask:44-72) and goldpolish-to-upper (scripts/goldpolish-to-upper:15-21) */
+  int32_t prep_mode;               /* 0 off, 1 = goldpolish-mask -s (soft), 2 = goldpolish-mask -n (hard) */
+  uint32_t prep_k;                 /* its -k (scripts/goldpolish-make:66 passes the first k value); 1..64 */
+  int32_t to_upper;                /* 1: upper-case the records (after masking, if any) */
 } gp_config;
 
 /* one read handed to fill_bfs: index into the uploaded read store + the target's kmer_threshold */
@@ -147,6 +152,11 @@ int gp_polish_stage(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uin
                     const uint32_t* contig_batch);
 int gp_polish_run(gp_ctx* ctx);
 int gp_polish_fetch(gp_ctx* ctx, char* out_seqs, uint64_t out_cap, uint64_t* out_offsets, uint8_t* out_dropped);
+
+/* goldpolish-mask / goldpolish-to-upper alone (no filters needed): records in, records out.  mode and k as
+ * gp_config.prep_mode / prep_k (mode 0 = to-upper only); out_offsets has n_records + 1 entries. */
+int gp_prep(gp_ctx* ctx, uint32_t n_records, const char* seqs, const uint64_t* offsets, int32_t mode, uint32_t k,
+            int32_t to_upper, char* out_seqs, uint64_t out_cap, uint64_t* out_offsets);
 
 /* gp_build_run + gp_polish_run of the staged work as ONE overlapped pass (needs gp_build_stage and
  * gp_polish_stage first; results are fetched with gp_build_fetch / gp_polish_fetch as usual and are
