@@ -51,7 +51,7 @@ EXPORTS = ["gp_default_config", "gp_ctx_create", "gp_ctx_destroy", "gp_last_erro
            "gp_ctx_synchronize", "gp_get_stats", "gp_reads_upload", "gp_build_filters", "gp_build_stage",
            "gp_build_run", "gp_build_fetch", "gp_build_fetch_cbf", "gp_filters_load", "gp_polish",
            "gp_polish_stage", "gp_polish_run", "gp_polish_fetch", "gp_kmer_threshold", "gp_mappings_cap",
-           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep"]
+           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep", "gp_build_output_host"]
 
 
 def load_library():
@@ -95,6 +95,7 @@ def load_library():
     l.gp_roof_microbench.argtypes = [vp, u32, u32, u64, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     l.gp_build_round_times.argtypes = [vp, C.POINTER(u64)]
     l.gp_pipeline_run.argtypes = [vp]
+    l.gp_build_output_host.argtypes = [vp, vp]
     l.gp_prep.argtypes = [vp, u32, vp, vp, C.c_int32, u32, C.c_int32, vp, u64, vp]
     _lib = l
     return l
@@ -202,6 +203,12 @@ class Context:
 
     def build_run(self):
         self._ck(self._l.gp_build_run(self._h))
+
+    def build_output(self, pinned):
+        """Name a page-locked host buffer (e.g. a torch pinned tensor) that the build kernel fills with the filter
+        payloads as they become final; build_fetch(out=<same buffer>) then only synchronises.  None: off."""
+        self._bf_pinned = pinned
+        self._ck(self._l.gp_build_output_host(self._h, _ptr(pinned) if pinned is not None else None))
 
     def build_fetch(self, out=None, want=True):
         if want and out is None:

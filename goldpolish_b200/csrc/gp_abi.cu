@@ -38,6 +38,10 @@ struct gp_ctx {
   gp_config cfg;
   int sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  uint8_t* bf_host_user = nullptr;                    // gp_build_output_host: pinned destination of the filter payloads
+  uint32_t* bf_host_dev = nullptr;                    // ... as the device sees it
+  bool bf_streamed = false;                           // the last build wrote the payloads there itself
+  std::vector<uint32_t> h_empty_streams;              // (batch * nk + ki) of streams without a k-mer
   bool edit_ev_valid = false;                         // edit_ev[] were recorded by the last polish
   bool pipelined = false;                             // last run was gp_pipeline_run's overlapped pass (device timers)
   cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // pack, build, polish (start, stop)
@@ -373,6 +377,12 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
         entry_rel[e] = uint16_t(e - batch_entry_off[b]);
       }
     }
+    ctx->h_empty_streams.clear();
+    for (uint32_t ki = 0; ki < c.nk; ki++) {
+      const uint32_t* pk = pre.data() + size_t(ki) * (n_entries + 1);
+      for (uint32_t b = 0; b < n_batches; b++)
+        if (pk[batch_entry_off[b + 1]] == pk[batch_entry_off[b]]) ctx->h_empty_streams.push_back(b * c.nk + ki);
+    }
     ctx->anchor_stride = 1;
     for (uint32_t ki = 0; ki < c.nk; ki++)
       ctx->anchor_stride = std::max<uint64_t>(ctx->anchor_stride, uint64_t(pre[size_t(ki) * (n_entries + 1) + n_entries]) + 1);
@@ -513,11 +523,13 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
     p.batch_order = batch_order;
     p.batch_done = batch_done;
+    p.bf_host = ctx->bf_host_dev;
     GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s, ctas_per_sm));
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
     launches += 1;
   }
   *launches_out = launches;
+  ctx->bf_streamed = ctx->bf_host_dev != nullptr;
   return GP_OK;
 }
 
@@ -541,6 +553,7 @@ int gp_build_run(gp_ctx* ctx)
     // level-synchronous: all SMs on one stream at a time, timestamps resident in L2
     if (int rc = build_launch_levels(ctx, s, nullptr, nullptr, 0, &launches)) return rc;
   }
+  if (algo == 1) ctx->bf_streamed = false;
   for (size_t wv = 0; algo == 1 && wv < ctx->wave_first.size(); wv++) {
     gp::BuildParams p;
     p.pk = ctx->d_pk.as<uint64_t>();
@@ -585,11 +598,35 @@ int gp_build_round_times(gp_ctx* ctx, uint64_t out[16])
   return GP_OK;
 }
 
+int gp_build_output_host(gp_ctx* ctx, uint8_t* bf_out_pinned)
+{
+  if (!ctx) return GP_ERR_ARG;
+  cudaSetDevice(ctx->cfg.device);
+  ctx->bf_host_user = nullptr;
+  ctx->bf_host_dev = nullptr;
+  ctx->bf_streamed = false;
+  if (!bf_out_pinned) return GP_OK;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, bf_out_pinned) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+    cudaGetLastError();
+    GP_FAIL(ctx, GP_ERR_ARG, "gp_build_output_host needs page-locked host memory (cudaHostAlloc / cudaHostRegister)");
+  }
+  ctx->bf_host_user = bf_out_pinned;
+  ctx->bf_host_dev = static_cast<uint32_t*>(at.devicePointer);
+  return GP_OK;
+}
+
 int gp_build_fetch(gp_ctx* ctx, uint8_t* bf_out)
 {
   if (!ctx) return GP_ERR_ARG;
   if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
   cudaSetDevice(ctx->cfg.device);
+  if (bf_out && bf_out == ctx->bf_host_user && ctx->bf_streamed) {
+    // the build kernel streamed every final filter into this buffer already; streams without k-mers are zeros
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t sidx : ctx->h_empty_streams) std::memset(bf_out + uint64_t(sidx) * gp::kBfBytes, 0, gp::kBfBytes);
+    return GP_OK;
+  }
   if (bf_out && ctx->n_batches)
     GP_CUDA(ctx, cudaMemcpyAsync(bf_out, ctx->d_bf_pool.p, uint64_t(ctx->n_batches) * ctx->cfg.nk * gp::kBfBytes,
                                  cudaMemcpyDeviceToHost, ctx->stream));

@@ -244,11 +244,26 @@ __device__ __forceinline__ uint32_t stream_batch(const LevelParams& p, uint32_t 
   return p.batch_order ? p.batch_order[p.first_batch + lb] : p.first_batch + lb;
 }
 
+// A stream's filter is final (its last barrier has drained on this CTA): stream it to the caller's pinned
+// host buffer if there is one -- every CTA copies its slice straight over PCIe, under the following rounds, so
+// that no bulk D2H is left at the end -- and tell the edit kernel (gp_pipeline_run).
+__device__ __forceinline__ void filter_final(const LevelParams& p, uint32_t batch, uint32_t ki, uint32_t gtid, uint32_t gthreads)
+{
+  if (p.bf_host) {
+    const uint64_t o = (uint64_t(batch) * p.nk + ki) * kBfWords;
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.bf_pool + o);
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(p.bf_host + o);
+    for (uint32_t i = gtid; i < kBfWords / 4u; i += gthreads) dst[i] = __ldcg(src + i);
+  }
+  if (p.batch_done && gtid == 0) atomicAdd(p.batch_done + batch, 1u);
+}
+
 enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_L1 = 2, PH_WRITE = 3, PH_READ = 4 };
 
 struct SlotState {      // uniform over the grid; written by thread 0 of each CTA between rounds
   uint32_t sid;         // wave-local stream, >= n_streams when the slot has run dry
   uint32_t phase, L, lread, epoch, tag, tag_next, n_steps;
+  uint32_t done_b1, done_ki; // batch + 1 and k index of the slot's previous stream while its last barrier drains (0: none)
   unsigned long long target; // barrier count that must be reached before the slot's next round
 };
 
@@ -261,7 +276,6 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   __shared__ uint64_t tr[8 * 256];
   __shared__ SlotState slots[kMaxSlots];
   __shared__ uint32_t next_sid;
-  __shared__ uint32_t pend[kMaxSlots]; // CTA 0: batch + 1 of a finished stream whose last barrier is still draining
   __shared__ uint32_t warp_cnt[kMaxSlots][kLevelWarps]; // survivors in each warp's private list
   if (p.batch_done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the edit kernel may join us now
   if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[20] = globaltimer_ns();
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
     next_sid = 0;
     for (uint32_t s = 0; s < p.n_slots; s++) {
       slots[s].epoch = 0; slots[s].target = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
-      pend[s] = 0;
+      slots[s].done_b1 = 0; slots[s].done_ki = 0;
       begin_stream(slots[s]);
     }
   }
@@ -320,17 +334,12 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         const unsigned long long target = S.target;
         while (ld_relaxed_u64(bar) < target) { }
         __threadfence();
-        if (blockIdx.x == 0) {
-          t_b = globaltimer_ns();
-          if (pend[sl]) { // the slot's previous stream is complete on every CTA: its filter is final
-            if (p.batch_done) atomicAdd(p.batch_done + (pend[sl] - 1u), 1u);
-            pend[sl] = 0;
-          }
-        }
+        if (blockIdx.x == 0) t_b = globaltimer_ns();
       }
       __syncthreads(); // the slot's previous round is complete everywhere
 
       const uint32_t sid = S.sid, phase = S.phase, tag = S.tag, L = S.L, n_steps = S.n_steps, lread = S.lread;
+      if (S.done_b1) filter_final(p, S.done_b1 - 1u, S.done_ki, gtid, gthreads); // the slot's previous stream is complete everywhere
       const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk, batch = stream_batch(p, lb);
       // two timestamp arrays per slot: T_L lives in array (L + 1) & 1 (the second one is used by the fused rounds only)
       uint32_t* __restrict__ V0 = p.V + uint64_t(sl) * 2u * kCbfCounters;
@@ -452,6 +461,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
           p.counters[2 + phase * 3 + 2] += 1;
         }
         S.target += gridDim.x;
+        S.done_b1 = 0;
         // next round of this slot (same decision in every CTA)
         switch (phase) {
         case PH_CLEAR:
@@ -461,11 +471,11 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
           if (S.lread >= 1u && p.fused) { // T_1 carries S.tag; the round that reads it writes T_2 under the next tag
             S.phase = PH_READ; S.L = 1; S.epoch++; S.tag_next = (63u - S.epoch) << kTimeBits;
           } else if (S.lread >= 1u) S.phase = PH_L1;
-          else { pend[sl] = batch + 1u; begin_stream(S); }
+          else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
           break;
         case PH_L1:
           if (S.lread >= 2u) { S.phase = PH_WRITE; S.L = 2; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
-          else { pend[sl] = batch + 1u; begin_stream(S); }
+          else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
           break;
         case PH_WRITE:
           S.phase = PH_READ;
@@ -473,20 +483,23 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         default: // PH_READ
           if (L < S.lread && p.fused) { S.L = L + 1u; S.tag = S.tag_next; S.epoch++; S.tag_next = (63u - S.epoch) << kTimeBits; }
           else if (L < S.lread) { S.phase = PH_WRITE; S.L = L + 1u; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
-          else { pend[sl] = batch + 1u; begin_stream(S); }
+          else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
           break;
         }
       }
     }
     if (!any) break;
   }
-  if (p.batch_done && blockIdx.x == 0 && threadIdx.x == 0) { // last streams of the slots
-    for (uint32_t sl = 0; sl < p.n_slots; sl++) {
-      if (!pend[sl]) continue;
-      while (ld_relaxed_u64(p.bars + sl) < slots[sl].target) { }
+  for (uint32_t sl = 0; sl < p.n_slots; sl++) { // last streams of the slots (states are final and uniform here)
+    __syncthreads();
+    const SlotState& S = slots[sl];
+    if (!S.done_b1) continue;
+    if (threadIdx.x == 0) {
+      while (ld_relaxed_u64(p.bars + sl) < S.target) { }
       __threadfence();
-      atomicAdd(p.batch_done + (pend[sl] - 1u), 1u);
     }
+    __syncthreads();
+    filter_final(p, S.done_b1 - 1u, S.done_ki, gtid, gthreads);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);

@@ -44,6 +44,7 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   unsigned long long* bars;       // per slot: barrier arrival counter (zeroed before a launch)
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
   uint32_t* bf_pool;
+  uint32_t* bf_host;              // optional: device-visible pinned host copy of bf_pool, filled as filters become final
   unsigned long long* counters;
   uint32_t surv_cap;
   uint32_t n_slots;               // streams in flight (1..levels_max_slots())

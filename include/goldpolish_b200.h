@@ -131,6 +131,12 @@ int gp_build_filters(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entr
  * fetch = device->host copy); gp_build_filters == stage + run + fetch */
 int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_off, const gp_read_entry* entries);
 int gp_build_run(gp_ctx* ctx);
+/* Optional: name a PAGE-LOCKED host buffer (n_batches * nk * GP_BF_BYTES of the builds to come) as the destination
+ * of the filter payloads.  The level-synchronous build kernel then writes every filter there itself the moment it
+ * is final (each CTA stores its slice over PCIe under the following rounds), and gp_build_fetch(ctx, same pointer)
+ * only synchronises -- no bulk D2H after the build.  NULL switches it off.  What the reference does per batch with
+ * bfs[i]->save() (goldpolish_targeted_bfs.cpp:138-140), without the end-of-build wait. */
+int gp_build_output_host(gp_ctx* ctx, uint8_t* bf_out_pinned);
 int gp_build_fetch(gp_ctx* ctx, uint8_t* bf_out);
 /* debug / parity: counting-filter bytes of (batch, k index) after the last build */
 int gp_build_fetch_cbf(gp_ctx* ctx, uint32_t batch, uint32_t k_index, uint8_t* cbf_out);

@@ -123,6 +123,39 @@ def test_pipeline_matches_separate_calls(gp, bsize):
             assert st["build_kernel"] == 2 and st["edits"] > 0
 
 
+@pytest.mark.parametrize("pipeline", [False, True])
+def test_filters_streamed_to_pinned_host_memory(gp, pipeline):
+    """gp_build_output_host: the build kernel writes every final filter into page-locked host memory itself;
+    the bytes equal a plain gp_build_fetch, also for a batch without reads (all-zero filters) and over a dirty
+    destination buffer."""
+    import torch
+    d = dataset(genome_len=120000)
+    pl = plan(d, bsize=1)
+    off = pl.batch_entry_off.copy()
+    keep = np.ones(len(pl.entries), dtype=bool)
+    keep[int(off[2]):int(off[3])] = False          # batch 2 loses its reads
+    entries = pl.entries[keep]
+    off[3:] -= off[3] - off[2]
+    with gp.Context() as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        want = ctx.build_filters(off, entries)
+        assert not want[2].any()
+        pinned = torch.full(want.shape, 0xAB, dtype=torch.uint8).pin_memory()
+        ctx.build_output(pinned)
+        ctx.build_stage(off, entries)
+        if pipeline:
+            ctx.polish_stage(d.contig_seq, d.contig_off, pl.contig_batch)
+            ctx.pipeline_run()
+        else:
+            ctx.build_run()
+        ctx.build_fetch(out=pinned)
+        assert np.array_equal(pinned.numpy(), want)
+        ctx.build_output(None)
+        assert np.array_equal(ctx.build_fetch(), want)
+        with pytest.raises(gp.GpError):
+            ctx.build_output(np.zeros(want.shape, dtype=np.uint8))   # pageable memory is refused
+
+
 def test_polish_identity_filters(gp, small):
     """All-ones filter: every k-mer present, nothing is edited.  All-zero filter: every position that
     passes the look-ahead is soft-masked and nothing else changes (size-independent properties)."""
