@@ -423,6 +423,9 @@ def ours(args, rank, world, local_rank):
                     ops_roof = r["hbm"] / 8.0
                 roof["random_access_roof_kmer_ops_per_s"] = ops_roof
                 roof["frac_of_random_access_roof"] = roof["kmer_ops_per_s"] / ops_roof if ops_roof else None
+                # against the HBM random-access roof the north star names (8 touches per op at the HBM sector rate):
+                # above 1 because the level-synchronous kernel keeps the touched state in L2
+                roof["frac_of_hbm_random_access_roof"] = roof["kmer_ops_per_s"] * 8.0 / r["hbm"] if r["hbm"] else None
             except Exception as e:  # measurement aid only
                 roof["random_access_roof_error"] = str(e)
         cpu = None

@@ -523,6 +523,7 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
     p.batch_order = batch_order;
     p.batch_done = batch_done;
+    p.n_batches_total = ctx->n_batches;
     p.bf_host = ctx->bf_host_dev;
     GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s, ctas_per_sm));
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
@@ -788,6 +789,7 @@ static int polish_edit(gp_ctx* ctx, cudaStream_t es, const uint32_t* order, cons
   p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
   p.order = order ? order : ctx->d_order.as<uint32_t>();
   p.batch_done = batch_done;
+  p.n_batches = ctx->n_batches;
   p.next_contig = ctx->d_pnext.as<uint32_t>();
   p.counters = ctx->d_pcounters.as<unsigned long long>();
   p.error = ctx->d_error.as<int>();
@@ -928,12 +930,12 @@ int gp_pipeline_run(gp_ctx* ctx)
   }
   cudaStream_t s = ctx->stream;
   GP_CUDA(ctx, ctx->d_batch_order.ensure(size_t(nb) * 4));
-  GP_CUDA(ctx, ctx->d_batch_done.ensure(size_t(nb) * 4));
+  GP_CUDA(ctx, ctx->d_batch_done.ensure((size_t(nb) + 1) * 4));
   GP_CUDA(ctx, ctx->d_order_pipe.ensure(size_t(n) * 4));
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
   GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_order.p, ctx->h_batch_order.data(), size_t(nb) * 4, cudaMemcpyHostToDevice, s));
   GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_order_pipe.p, ctx->h_order_pipe.data(), size_t(n) * 4, cudaMemcpyHostToDevice, s));
-  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_batch_done.p, 0, size_t(nb) * 4, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_batch_done.p, 0, (size_t(nb) + 1) * 4, s));
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, gp::kBuildCounters * 8, s));
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(nb) * c.nk * gp::kBfBytes, s));
   if (int rc = polish_prepare(ctx)) return rc;

@@ -155,18 +155,26 @@ __device__ __forceinline__ void unpack_index(uint32_t w, uint32_t& ci, uint32_t&
   ci = w & 0xFFFFFFu;
   bi = (w & 0x1FFFFFu) | ((w >> 24) << 21);
 }
-// append the lanes with q set at position cnt of the warp's list
-__device__ __forceinline__ void surv_append(const SurvList& l, uint32_t& cnt, bool q, const uint32_t (&ci)[4],
-                                            const uint32_t (&bi)[4], uint32_t meta, uint32_t lane)
+// append the lanes with q set at position cnt of the warp's list (pw = the four packed indices)
+__device__ __forceinline__ void surv_append(const SurvList& l, uint32_t& cnt, bool q, const uint32_t (&pw)[4], uint32_t meta,
+                                            uint32_t lane)
 {
   const uint32_t m = __ballot_sync(0xffffffffu, q);
   if (q) {
     const uint32_t i = cnt + __popc(m & ((1u << lane) - 1u));
 #pragma unroll
-    for (int j = 0; j < 4; j++) l.w[j][i] = pack_index(ci[j], bi[j]);
+    for (int j = 0; j < 4; j++) l.w[j][i] = pw[j];
     l.w[4][i] = meta;
   }
   cnt += __popc(m);
+}
+__device__ __forceinline__ void surv_append(const SurvList& l, uint32_t& cnt, bool q, const uint32_t (&ci)[4],
+                                            const uint32_t (&bi)[4], uint32_t meta, uint32_t lane)
+{
+  uint32_t pw[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) pw[j] = pack_index(ci[j], bi[j]);
+  surv_append(l, cnt, q, pw, meta, lane);
 }
 // fire-and-forget atomics (REDG): spelled in PTX because ptxas keeps the returning form (ATOMG
 // with a dead destination) for atomicMin/atomicOr in this kernel
@@ -255,7 +263,10 @@ __device__ __forceinline__ void filter_final(const LevelParams& p, uint32_t batc
     uint4* __restrict__ dst = reinterpret_cast<uint4*>(p.bf_host + o);
     for (uint32_t i = gtid; i < kBfWords / 4u; i += gthreads) dst[i] = __ldcg(src + i);
   }
-  if (p.batch_done && gtid == 0) atomicAdd(p.batch_done + batch, 1u);
+  if (p.batch_done && gtid == 0) {
+    atomicAdd(p.batch_done + batch, 1u);
+    atomicAdd(p.batch_done + p.n_batches_total, 1u); // progress beacon for the edit kernel's watchdog
+  }
 }
 
 enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_L1 = 2, PH_WRITE = 3, PH_READ = 4 };
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
       S.n_steps = pre[p.batch_entry_off[batch + 1]] - pre[p.batch_entry_off[batch]];
       if (S.n_steps == 0) { // nothing to insert: the (zeroed) filter is final
-        if (p.batch_done && blockIdx.x == 0) atomicAdd(p.batch_done + batch, 1u);
+        if (p.batch_done && blockIdx.x == 0) { atomicAdd(p.batch_done + batch, 1u); atomicAdd(p.batch_done + p.n_batches_total, 1u); }
         continue;
       }
       const uint32_t lmax = p.batch_max_thr[batch] - 2u + ki; // largest thr of the stream
@@ -424,27 +435,83 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         }
       } else {
         // ---- read: who sees all four counters at >= L before its own time?  compact in place ----
+        // two entries per lane and iteration: their list words, then their timestamps, are all in flight together
         const uint32_t cnt = warp_cnt[sl][wib];
         uint32_t kept = 0;
-        for (uint32_t r = 0; r < cnt; r += 32) {
-          const uint32_t i = r + c.lane;
-          bool q = false;
-          uint32_t meta = 0;
-          uint32_t ci[4] = { 0, 0, 0, 0 }, bi[4] = { 0, 0, 0, 0 };
-          if (i < cnt) {
-            meta = __ldcg(lst.w[4] + i);
+        for (uint32_t r = 0; r < cnt; r += 64) {
+          uint32_t pw[2][4], meta[2];
+          bool live[2], q[2];
 #pragma unroll
-            for (int j = 0; j < 4; j++) unpack_index(__ldcg(lst.w[j] + i), ci[j], bi[j]);
-            const uint32_t t = meta & kTimeMask, thr = meta >> kTimeBits;
-            q = ((cbf || L > 1u) ? level_test(V, cbf, tag, t, L, ci) : level_test_early(V, tag, t, ci)) && thr > L;
-            if (q && thr == L + 1u) bf_insert(bf, bi);
-            if (q && p.fused && L < lread) { // fused rounds: the survivor races for T_{L+1} right away, in the other array
+          for (int e = 0; e < 2; e++) {
+            const uint32_t i = r + 32u * e + c.lane;
+            live[e] = i < cnt;
+            meta[e] = 0;
 #pragma unroll
-              for (int j = 0; j < 4; j++) red_min(Vn + ci[j], tag_next | t);
+            for (int j = 0; j < 4; j++) pw[e][j] = 0;
+            if (live[e]) {
+              meta[e] = __ldcg(lst.w[4] + i);
+#pragma unroll
+              for (int j = 0; j < 4; j++) pw[e][j] = __ldcg(lst.w[j] + i);
             }
           }
-          // every lane has its entry in registers before the ballot inside returns; kept <= r
-          surv_append(lst, kept, q, ci, bi, meta, c.lane);
+          if (cbf || L > 1u) {
+            uint32_t v[2][4];
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+              for (int j = 0; j < 4; j++) v[e][j] = live[e] ? __ldcg(V + (pw[e][j] & 0xFFFFFFu)) : 0u;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const uint32_t t = meta[e] & kTimeMask;
+              bool reached = live[e];
+              uint32_t mx = 0;
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                reached &= (v[e][j] & ~kTimeMask) == tag;
+                mx = max(mx, v[e][j] & kTimeMask);
+                if (cbf && live[e] && v[e][j] == (tag | t)) cbf[pw[e][j] & 0xFFFFFFu] = (uint8_t)L; // moved counter j to level L
+              }
+              q[e] = reached && t > mx;
+            }
+          } else { // level 1: most entries fail on their first counter (they are its first toucher)
+            uint32_t v0[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) v0[e] = live[e] ? __ldcg(V + (pw[e][0] & 0xFFFFFFu)) : 0u;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const uint32_t t = meta[e] & kTimeMask;
+              q[e] = live[e] && (v0[e] & ~kTimeMask) == tag && (v0[e] & kTimeMask) < t;
+            }
+            uint32_t v[2][3];
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+              for (int j = 0; j < 3; j++) v[e][j] = q[e] ? __ldcg(V + (pw[e][j + 1] & 0xFFFFFFu)) : 0u;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const uint32_t t = meta[e] & kTimeMask;
+#pragma unroll
+              for (int j = 0; j < 3; j++) q[e] = q[e] && (v[e][j] & ~kTimeMask) == tag && (v[e][j] & kTimeMask) < t;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const uint32_t t = meta[e] & kTimeMask, thr = meta[e] >> kTimeBits;
+            q[e] = q[e] && thr > L;
+            if (q[e] && thr == L + 1u) {
+              uint32_t ci, bi[4];
+#pragma unroll
+              for (int j = 0; j < 4; j++) unpack_index(pw[e][j], ci, bi[j]);
+              bf_insert(bf, bi);
+            }
+            if (q[e] && p.fused && L < lread) { // fused rounds: the survivor races for T_{L+1} right away, in the other array
+#pragma unroll
+              for (int j = 0; j < 4; j++) red_min(Vn + (pw[e][j] & 0xFFFFFFu), tag_next | t);
+            }
+          }
+          // every lane has both entries in registers before the ballots inside return; kept <= r
+          surv_append(lst, kept, q[0], pw[0], meta[0], c.lane);
+          surv_append(lst, kept, q[1], pw[1], meta[1], c.lane);
         }
         __syncwarp();
         if (c.lane == 0) warp_cnt[sl][wib] = kept;

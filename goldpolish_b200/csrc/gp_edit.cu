@@ -1052,12 +1052,16 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
       uint32_t ok = 1;
       if (lane == 0) {
         const volatile uint32_t* flag = p.batch_done + p.contig_batch[ci];
+        const volatile uint32_t* progress = p.batch_done + p.n_batches; // filters finished so far, all batches
         unsigned long long t0 = 0, t1 = 0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        uint32_t seen = *progress;
         while (*flag < p.nk) {
           __nanosleep(256);
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          if (t1 - t0 > 4000000000ull) { ok = 0; break; } // 4 s without the filters: the build is not running beside us
+          const uint32_t now = *progress;
+          if (now != seen) { seen = now; t0 = t1; }
+          else if (t1 - t0 > 4000000000ull) { ok = 0; break; } // 4 s without ANY new filter: the build is not running beside us
         }
         __threadfence();
       }

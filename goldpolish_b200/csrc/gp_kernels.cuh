@@ -36,7 +36,8 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   const uint32_t* step_pre;       // [nk][n_entries + 1]: steps before entry e, for every k index
   const uint32_t* batch_max_thr;  // per batch: largest kmer_threshold among its entries
   const uint32_t* batch_order;    // optional: build order -> batch (NULL = identity)
-  uint32_t* batch_done;           // optional: per batch, streams whose filter is final (gp_pipeline_run)
+  uint32_t* batch_done;           // optional: per batch, streams whose filter is final; [n_batches_total] counts all (gp_pipeline_run)
+  uint32_t n_batches_total;
   const uint16_t* anchor;         // [nk][anchor_stride]: global step of k index -> entry, relative to its batch
   uint64_t anchor_stride;
   uint32_t* V;                    // per slot: 2 x kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
@@ -72,7 +73,8 @@ struct EditParams {
   const uint64_t* node_off;     // n_contigs + 1
   const uint32_t* contig_batch;
   const uint32_t* bf_pool;      // (batch * nk + ki) * kBfWords
-  const uint32_t* batch_done;   // optional: per batch, finished filter streams; a contig waits for nk of them
+  const uint32_t* batch_done;   // optional: per batch, finished filter streams; a contig waits for nk of them ([n_batches] = total)
+  uint32_t n_batches;
   const uint32_t* order;        // contig ids, longest first
   uint32_t* next_contig;
   unsigned long long* counters; // [0] triggers [1] edits [2] masked [3] rollbacks [4] first / [5] last globaltimer ns
