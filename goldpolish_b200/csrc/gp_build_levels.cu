@@ -340,6 +340,32 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       any = true;
       unsigned long long* bar = p.bars + sl;
       unsigned long long t_a = 0, t_b = 0;
+      // the warp's survivor list (room for every occurrence of its runs) is its own: the first entries of a list
+      // round are fetched BEFORE the barrier wait, they do not depend on the other CTAs
+      const uint32_t wib = threadIdx.x >> 5;
+      SurvList lst;
+      {
+        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + uint64_t(c.gwarp) * (kRuns * run_len(S.n_steps, c.nwarps) * 32u);
+#pragma unroll
+        for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
+      }
+      const uint32_t list_cnt = S.phase == PH_READ ? warp_cnt[sl][wib] : 0u;
+      uint32_t nx_pw[2][4], nx_meta[2]; // entries of the next iteration of the list round
+      auto fetch_entries = [&](uint32_t r) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const uint32_t i = r + 32u * e + c.lane;
+          nx_meta[e] = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) nx_pw[e][j] = 0;
+          if (i < list_cnt) {
+            nx_meta[e] = __ldcg(lst.w[4] + i);
+#pragma unroll
+            for (int j = 0; j < 4; j++) nx_pw[e][j] = __ldcg(lst.w[j] + i);
+          }
+        }
+      };
+      fetch_entries(0);
       if (threadIdx.x == 0) {
         if (blockIdx.x == 0) t_a = globaltimer_ns();
         const unsigned long long target = S.target;
@@ -359,15 +385,6 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       const uint32_t tag_next = S.tag_next;
       uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
       uint8_t* __restrict__ cbf = p.cbf_pool ? p.cbf_pool + uint64_t(sid) * kCbfCounters : nullptr;
-      const uint32_t wib = threadIdx.x >> 5;
-      // the warp's survivor list has room for every occurrence of its runs
-      SurvList lst;
-      {
-        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + uint64_t(c.gwarp) * (kRuns * run_len(n_steps, c.nwarps) * 32u);
-#pragma unroll
-        for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
-      }
-
       if (phase == PH_CLEAR) {
         for (uint64_t i = gtid; i < kCbfCounters * (p.fused ? 2u : 1u); i += gthreads) V0[i] = 0xFFFFFFFFu;
       } else if (phase == PH_L0 || phase == PH_L1) {
@@ -436,24 +453,20 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       } else {
         // ---- read: who sees all four counters at >= L before its own time?  compact in place ----
         // two entries per lane and iteration: their list words, then their timestamps, are all in flight together
-        const uint32_t cnt = warp_cnt[sl][wib];
+        const uint32_t cnt = list_cnt;
         uint32_t kept = 0;
         for (uint32_t r = 0; r < cnt; r += 64) {
           uint32_t pw[2][4], meta[2];
           bool live[2], q[2];
 #pragma unroll
           for (int e = 0; e < 2; e++) {
-            const uint32_t i = r + 32u * e + c.lane;
-            live[e] = i < cnt;
-            meta[e] = 0;
+            live[e] = r + 32u * e + c.lane < cnt;
+            meta[e] = nx_meta[e];
 #pragma unroll
-            for (int j = 0; j < 4; j++) pw[e][j] = 0;
-            if (live[e]) {
-              meta[e] = __ldcg(lst.w[4] + i);
-#pragma unroll
-              for (int j = 0; j < 4; j++) pw[e][j] = __ldcg(lst.w[j] + i);
-            }
+            for (int j = 0; j < 4; j++) pw[e][j] = nx_pw[e][j];
           }
+          // the entries of the next iteration are requested now: this iteration's appends stay below r + 64
+          if (r + 64u < cnt) fetch_entries(r + 64u);
           if (cbf || L > 1u) {
             uint32_t v[2][4];
 #pragma unroll
