@@ -43,6 +43,7 @@ struct gp_ctx {
   bool bf_streamed = false;                           // the last build wrote the payloads there itself
   std::vector<uint32_t> h_empty_streams;              // (batch * nk + ki) of streams without a k-mer
   bool edit_ev_valid = false;                         // edit_ev[] were recorded by the last polish
+  int overlap_state = 0;                              // 0 untested, 1 the two kernels co-run on this device, -1 they do not
   bool pipelined = false;                             // last run was gp_pipeline_run's overlapped pass (device timers)
   cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // pack, build, polish (start, stop)
   std::vector<cudaEvent_t> wave_ev;  // build kernel only: (start, stop) per wave
@@ -906,8 +907,15 @@ int gp_pipeline_run(gp_ctx* ctx)
   cudaSetDevice(ctx->cfg.device);
   const gp_config& c = ctx->cfg;
   const uint32_t n = ctx->n_contigs, nb = ctx->n_batches;
+  if (ctx->overlap_state == 0 && ctx->pipelined) {
+    // first overlapped pass of this context is behind us: did the edit kernel ever see filters arrive while it ran?
+    int err = 0;
+    GP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->d_error.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->overlap_state = err == 2 ? -1 : 1; // 2 = its watchdog fired: this device does not co-schedule the kernels
+  }
   const bool overlap = ctx->build_algo_resolved == 2 && ctx->wave_first.size() == 1 && n && nb && !c.keep_counters &&
-                       !std::getenv("GP_NO_OVERLAP");
+                       ctx->overlap_state >= 0 && !std::getenv("GP_NO_OVERLAP");
   if (!overlap) { // nothing to overlap with (or the in-order kernel, which fills the SMs): one after the other
     if (int rc = gp_build_run(ctx)) return rc;
     return gp_polish_run(ctx);

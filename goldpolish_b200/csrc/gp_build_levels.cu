@@ -603,11 +603,9 @@ int levels_max_slots() { return kMaxSlots; }
 cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s, int ctas_per_sm)
 {
   if (p.n_streams == 0) return cudaSuccess;
-  static bool carve = false;
-  if (!carve) { // 132 KB of shared memory (3 CTAs x 33 KB), the rest L1; the edit kernel asks for the same
-    cudaFuncSetAttribute((const void*)build_filters_levels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
-    carve = true;
-  }
+  // 132 KB of shared memory (3 CTAs x 33 KB), the rest L1; the edit kernel asks for the same so that the two can
+  // share an SM.  Function attributes are per device: set on every launch (a cheap host-side call).
+  cudaFuncSetAttribute((const void*)build_filters_levels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
   LevelParams lp = p;
   void* args[] = { &lp };
   // cooperative launch: the barriers need every CTA resident

@@ -1133,11 +1133,8 @@ constexpr int kAlongsideWarps = 3;
 cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool alongside_build)
 {
   if (p.n_contigs == 0) return cudaSuccess;
-  static bool attr = false;
-  if (!attr) { // same shared-memory carve-out as the build kernel (132 KB), so that the two can share an SM
-    cudaFuncSetAttribute((const void*)edit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
-    attr = true;
-  }
+  // same shared-memory carve-out as the build kernel (132 KB), so that the two can share an SM (per device)
+  cudaFuncSetAttribute((const void*)edit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
   if (alongside_build) {
     uint32_t grid = uint32_t(sm_count);
     const uint32_t need = (p.n_contigs + kAlongsideWarps - 1) / kAlongsideWarps;

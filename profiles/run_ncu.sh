@@ -6,11 +6,12 @@ set -u
 TAG=${1:-r1}; shift || true
 ARGS="--steps 2 --warmup 3 --genome-len 1000000 --no-cpu-baseline --no-roof $*"
 mkdir -p gpurun_out
+python bench.py $ARGS --separate > gpurun_out/plain_separate_$TAG.json 2> gpurun_out/plain_separate_$TAG.log
 python bench.py $ARGS > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.log &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_$TAG.csv python bench.py $ARGS > gpurun_out/ncu1_$TAG.log 2>&1
 python bench.py $ARGS > /dev/null 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:build_filters -s 3 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:build_filters_levels -s 4 -c 1 \
     -o gpurun_out/prof_build_$TAG -f python bench.py $ARGS > gpurun_out/ncu2_$TAG.log 2>&1
 python bench.py $ARGS > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:edit_kernel -s 3 -c 1 \
