@@ -42,15 +42,30 @@ struct LevelCtx {
 };
 
 // A step is 32 consecutive k-mer starts of one read; steps of a stream are numbered in the
-// reference's order, which makes (step * 32 + lane) the occurrence time.  A warp's share of a
-// stream is kRuns runs of `len` consecutive steps, run r of warp w starting at step
-// (r * nwarps + w) * len: every warp samples the whole time axis, so that the survivors -- which
-// crowd towards late times -- spread evenly over the warps.  anchor[] maps a step to its read
-// entry; lane r fetches the head of run r, so the dependent loads of all runs overlap.
+// reference's order, which makes (step * 32 + lane) the occurrence time.  Every warp gets the same number of
+// steps (+1 for the first `rem` columns), cut into kRuns runs that are spread over the whole time axis: the
+// stream is laid out as kRuns "rows" of nwarps runs each -- row r has runs of q or q + 1 steps -- plus a last
+// row of single leftover steps, and a warp takes one run per row, in snake order (its column counted backwards
+// in odd rows).  Survivors crowd towards late times; contiguous shares left the early warps idle in every list
+// round, and rows of equal-length runs (3.7 rows filled of 4) gave a quarter of the warps a run less.
+// anchor[] maps a step to its read entry; lane r fetches the head of run r, so that the dependent loads of all
+// runs overlap.
 constexpr uint32_t kRuns = 4;
-__device__ __forceinline__ uint32_t run_len(uint32_t n_steps, uint32_t nwarps)
+// steps a warp's survivor list must have room for
+__device__ __forceinline__ uint32_t warp_steps(uint32_t n_steps, uint32_t nwarps) { return n_steps / nwarps + 1u; }
+// run of row r (0..kRuns) of this warp: first step and length (0: none)
+__device__ __forceinline__ void run_of_row(uint32_t r, uint32_t n_steps, const LevelCtx& c, uint32_t& s0, uint32_t& len)
 {
-  return (n_steps + nwarps * kRuns - 1u) / (nwarps * kRuns);
+  const uint32_t per = n_steps / c.nwarps, rem = n_steps - per * c.nwarps;
+  const uint32_t q = per / kRuns, x = per - q * kRuns; // rows 0..x-1 have q + 1 steps per run, rows x..kRuns-1 have q
+  const uint32_t col = (r & 1u) ? c.nwarps - 1u - c.gwarp : c.gwarp;
+  if (r < kRuns) {
+    len = q + (r < x ? 1u : 0u);
+    s0 = (r * q + min(r, x)) * c.nwarps + col * len;
+  } else { // the leftover steps, one each
+    len = col < rem ? 1u : 0u;
+    s0 = per * c.nwarps + col;
+  }
 }
 
 // Calls f(step, entry thr, valid, ci, bi) for every step of this warp's runs.
@@ -62,11 +77,11 @@ __device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c
   const uint64_t e0 = p.batch_entry_off[batch], e1 = p.batch_entry_off[batch + 1];
   const uint32_t base = __ldg(pre + e0);
   const uint16_t* anchor = p.anchor + uint64_t(ki) * p.anchor_stride + base;
-  const uint32_t len = run_len(n_steps, c.nwarps);
   uint32_t h_e = 0, h_first = 0, h_last = 0, h_thr = 0, h_len = 0, h_wlo = 0, h_whi = 0;
   {
-    const uint32_t s0 = (c.lane * c.nwarps + c.gwarp) * len;
-    if (c.lane < kRuns && s0 < n_steps) {
+    uint32_t s0 = 0, len = 0;
+    if (c.lane <= kRuns) run_of_row(c.lane, n_steps, c, s0, len);
+    if (len) {
       h_e = __ldg(anchor + s0);
       const uint64_t e = e0 + h_e;
       h_first = __ldg(pre + e) - base; h_last = __ldg(pre + e + 1) - base;
@@ -78,10 +93,11 @@ __device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c
     }
   }
 #pragma unroll 1
-  for (uint32_t r = 0; r < kRuns; r++) {
-    const uint32_t s0 = (r * c.nwarps + c.gwarp) * len;
-    if (s0 >= n_steps) break;
-    const uint32_t s_end = min(n_steps, s0 + len);
+  for (uint32_t r = 0; r <= kRuns; r++) {
+    uint32_t s0, len;
+    run_of_row(r, n_steps, c, s0, len);
+    if (len == 0) continue;
+    const uint32_t s_end = s0 + len;
     const uint64_t e_head = e0 + __shfl_sync(0xffffffffu, h_e, r);
     uint32_t first = __shfl_sync(0xffffffffu, h_first, r), last = __shfl_sync(0xffffffffu, h_last, r);
     uint32_t kthr = __shfl_sync(0xffffffffu, h_thr, r), len_r = __shfl_sync(0xffffffffu, h_len, r);
@@ -345,7 +361,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       const uint32_t wib = threadIdx.x >> 5;
       SurvList lst;
       {
-        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + uint64_t(c.gwarp) * (kRuns * run_len(S.n_steps, c.nwarps) * 32u);
+        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + uint64_t(c.gwarp) * (warp_steps(S.n_steps, c.nwarps) * 32u);
 #pragma unroll
         for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
       }
@@ -367,11 +383,11 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       };
       fetch_entries(0);
       if (threadIdx.x == 0) {
-        if (blockIdx.x == 0) t_a = globaltimer_ns();
+        if (blockIdx.x == p.report_cta) t_a = globaltimer_ns();
         const unsigned long long target = S.target;
         while (ld_relaxed_u64(bar) < target) { }
         __threadfence();
-        if (blockIdx.x == 0) t_b = globaltimer_ns();
+        if (blockIdx.x == p.report_cta) t_b = globaltimer_ns();
       }
       __syncthreads(); // the slot's previous round is complete everywhere
 
@@ -534,7 +550,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1ull);
-        if (blockIdx.x == 0) { // where the time of CTA 0 goes, per kind of round: barrier wait, work, rounds
+        if (blockIdx.x == p.report_cta) { // where the time of one CTA goes, per kind of round: barrier wait, work, rounds
           const unsigned long long t_c = globaltimer_ns();
           p.counters[2 + phase * 3 + 0] += t_b - t_a;
           p.counters[2 + phase * 3 + 1] += t_c - t_b;
