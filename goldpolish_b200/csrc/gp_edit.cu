@@ -70,6 +70,24 @@ struct WS {
   uint32_t n_trig, n_edit, n_mask, n_roll;
 };
 
+// seeds through the per-round shared tables instead of the switch statements of gp_common.cuh (branchy on a
+// latency-bound warp) and instead of rotating by a runtime k (two modulo operations per srol)
+__device__ __forceinline__ uint64_t sF(const WS& w, uint32_t c) { return w.seedt[w.code[c & 255u]]; }       // seedTab[c]
+__device__ __forceinline__ uint64_t sFk(const WS& w, uint32_t c) { return w.seedt[8 + w.code[c & 255u]]; }  // ... rotated by k
+__device__ __forceinline__ uint64_t sR(const WS& w, uint32_t c) { return w.seedt[16 + (c & 7u)]; }          // seedTab[c & cpOff]
+__device__ __forceinline__ uint64_t sRk(const WS& w, uint32_t c) { return w.seedt[24 + (c & 7u)]; }         // ... rotated by k
+// rolling update (nthash.hpp:122-131, 143-152) and last-base replacement (:134-140, 154-169)
+__device__ __forceinline__ void ws_roll(const WS& w, HashState& h, uint32_t out, uint32_t in)
+{
+  h.fh = srol1(h.fh) ^ sF(w, in) ^ sFk(w, out);
+  h.rh = sror1(h.rh ^ sRk(w, in) ^ sR(w, out));
+}
+__device__ __forceinline__ void ws_changelast(const WS& w, HashState& h, uint32_t out, uint32_t in)
+{
+  h.fh ^= sF(w, out) ^ sF(w, in);
+  h.rh = sror1(srol1(h.rh) ^ sRk(w, out) ^ sRk(w, in));
+}
+
 __device__ __forceinline__ bool is_accepted(uint32_t c)
 { // isAcceptedBase(toupper(c)), ntedit.cpp:363-367
   c &= ~0x20u; // toupper for letters; non-letters never match below either way
@@ -215,8 +233,8 @@ __device__ __forceinline__ void compute_block(const WS& w, uint32_t Bp, uint64_t
   const uint32_t a0 = Bp + lane, a1 = Bp + lane + 32;
   const uint32_t c0 = a0 < w.ve ? v_at(w, a0) : 0u;
   const uint32_t c1 = (a1 < w.ve && lane < 31) ? v_at(w, a1) : 0u;
-  uint64_t u0 = srol(seed_of_char(c0), 62 - lane), u1 = lane < 31 ? srol(seed_of_char(c1), 30 - lane) : 0ull;
-  uint64_t x0 = srol(cseed_of_char(c0), lane), x1 = srol(cseed_of_char(c1), lane + 32);
+  uint64_t u0 = srol(sF(w, c0), 62 - lane), u1 = lane < 31 ? srol(sF(w, c1), 30 - lane) : 0ull;
+  uint64_t x0 = srol(sR(w, c0), lane), x1 = srol(sR(w, c1), lane + 32);
   u0 = xor_scan_incl(u0, lane); u1 = xor_scan_incl(u1, lane);
   x0 = xor_scan_incl(x0, lane); x1 = xor_scan_incl(x1, lane);
   u1 ^= __shfl_sync(kFull, u0, 31);
@@ -534,7 +552,7 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
     }
     __syncwarp();
     HashState base = w.hs;
-    hs_changelast(base, k, draft_char, index_char); // :1290
+    ws_changelast(w, base, draft_char, index_char); // :1290
     const uint64_t dF = w.seedt[w.code[draft_char]], dRk = w.seedt[24 + (draft_char & 7u)];
     // a candidate can no longer qualify once it has missed more samples than the threshold allows
     const uint32_t nsamp = (k - 2) / w.jump + 1;
@@ -622,12 +640,12 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
     HashState t = w.hs;
     uint32_t present = 0;
     if (nd - 1 < an) { // the character that follows the deleted run must exist
-      hs_changelast(t, k, draft_char, ahead_at(w, nd - 1)); // :1190-1197
+      ws_changelast(w, t, draft_char, ahead_at(w, nd - 1)); // :1190-1197
       if (bf_contains(w, t)) present++;                     // :1201-1203
       for (uint32_t kk = 1; kk + 2 <= k; kk++) {            // :1204-1220
         const uint32_t ai = nd - 1 + kk;
         if (ai >= an) break; // roll() fails: end of contig
-        hs_roll(t, k, ring_at(w, kk - 1), ahead_at(w, ai));
+        ws_roll(w, t, ring_at(w, kk - 1), ahead_at(w, ai));
         if (kk % w.jump == 0 && bf_contains(w, t)) present++;
       }
     }
@@ -876,7 +894,7 @@ __device__ __forceinline__ void edit_round(WS& w)
         bool gate_l = false;
         if (attempt_l && bsel < nbl) {
           if (w.mode == 2) gate_l = true;
-          else { hs_changelast(gh, k, dch, (pk >> (8 * bsel)) & 255u); gate_l = bf_contains(w, gh); }
+          else { ws_changelast(w, gh, dch, (pk >> (8 * bsel)) & 255u); gate_l = bf_contains(w, gh); }
         }
         const uint32_t gate_bits = __ballot_sync(kFull, gate_l);
         uint32_t done = 0;
@@ -942,7 +960,7 @@ __device__ __forceinline__ void edit_round(WS& w)
           // gate: is the k-mer ending in the candidate base present? (:1565-1570)
           HashState g = w.hs;
           const uint32_t my_base = (packed >> (8 * (lane & 3u))) & 255u;
-          hs_changelast(g, k, draft_char, my_base);
+          ws_changelast(w, g, draft_char, my_base);
           const bool gate = lane < nb && (w.mode == 2 || bf_contains(w, g));
           const uint32_t gates = __ballot_sync(kFull, gate);
           if (gates) {
@@ -958,8 +976,8 @@ __device__ __forceinline__ void edit_round(WS& w)
               // strand (:1585-1606); window j+k no longer contains the base
               uint64_t cf = base_f, cr = base_r;
               if (lane + 1 < k) {
-                cf ^= srol(seed_of_char(draft_char) ^ seed_of_char(sub_base), 1 + lane);
-                cr ^= srol(cseed_of_char(draft_char) ^ cseed_of_char(sub_base), k - 2 - lane);
+                cf ^= srol(sF(w, draft_char) ^ sF(w, sub_base), 1 + lane);
+                cr ^= srol(sR(w, draft_char) ^ sR(w, sub_base), k - 2 - lane);
               }
               const bool hit = lane < k && (lane % w.jump == 0) && bf_contains(w, cf, cr);
               const uint32_t present = __popc(__ballot_sync(kFull, hit));
