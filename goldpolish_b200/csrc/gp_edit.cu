@@ -593,7 +593,7 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
           tq[q].fh = srol1(tq[q].fh) ^ inf ^ of;
           tq[q].rh = sror1(tq[q].rh ^ inr ^ orv);
         }
-        if (kk % w.jump == 0) {
+        if ((w.samp >> kk) & 1ull) { // kk % jump == 0, without a runtime modulo
 #pragma unroll
           for (int q = 0; q < G; q++) {
             if (!act[q]) continue;
@@ -646,7 +646,7 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
         const uint32_t ai = nd - 1 + kk;
         if (ai >= an) break; // roll() fails: end of contig
         ws_roll(w, t, ring_at(w, kk - 1), ahead_at(w, ai));
-        if (kk % w.jump == 0 && bf_contains(w, t)) present++;
+        if (((w.samp >> kk) & 1ull) && bf_contains(w, t)) present++;
       }
     }
     if (float(present) >= w.thrD && present > 0) { // :1226-1233 (returns 0 when rejected)
@@ -979,7 +979,7 @@ __device__ __forceinline__ void edit_round(WS& w)
                 cf ^= srol(sF(w, draft_char) ^ sF(w, sub_base), 1 + lane);
                 cr ^= srol(sR(w, draft_char) ^ sR(w, sub_base), k - 2 - lane);
               }
-              const bool hit = lane < k && (lane % w.jump == 0) && bf_contains(w, cf, cr);
+              const bool hit = ((w.samp >> lane) & 1ull) && bf_contains(w, cf, cr); // lane < k && lane % jump == 0
               const uint32_t present = __popc(__ballot_sync(kFull, hit));
               if (float(present) >= w.thrE) { // :1621-1626
                 if (present >= best.support) { best.type = 1; best.sub_base = sub_base; best.support = present; }
