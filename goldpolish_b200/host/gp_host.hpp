@@ -25,9 +25,12 @@
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 namespace gph {
@@ -62,41 +65,121 @@ class SeqIndex {
 public:
   // Build from a FASTA with exactly 2 lines per record or a FASTQ with exactly 4
   // (src/seqindex.cpp:12-66).  The first duplicate id wins (unordered_map::emplace).
-  static SeqIndex build(const std::string& seqs_path)
+  // Same line arithmetic as the reference's getline loop (line i has phase i % 2 or i % 4, whatever it holds;
+  // a '\r' stays part of its line), but over an mmap of the file with `threads` workers:
+  // every worker counts the newlines of its slice, a prefix sum gives the line number at every slice start, and
+  // the worker then parses the records that START in its slice.  threads = 0: GP_INDEX_THREADS or all cores.
+  static SeqIndex build(const std::string& seqs_path, unsigned threads = 0)
   {
     SeqIndex ix;
     ix.seqs_path = seqs_path;
-    std::ifstream f(seqs_path);
-    if (!f.good()) die("cannot open " + seqs_path);
-    const bool fastq = f.peek() == '@';
-    std::string line, id;
-    long i = 0, byte = 0, id_end = 0, seq_start = 0, seq_len = 0;
-    while (bool(std::getline(f, line))) {
-      const long endbyte = byte + long(line.size());
-      const long phase = fastq ? i % 4 : i % 2;
-      if (phase == 0) {
-        id_end = endbyte;
-        const std::string first = line.substr(0, line.find(' ')); // split(line, " ")[0]
-        id = first.empty() ? std::string() : first.substr(1);
-        if (fastq) id = id.substr(0, id.find('\t')); // :33
-      } else if (phase == 1) {
-        seq_start = id_end + 1;
-        seq_len = endbyte - id_end - 1;
-        if (!fastq) ix.add(id, uint64_t(seq_start), uint64_t(seq_len), 0.0);
-      } else if (fastq && phase == 3) {
-        // calc_phred_avg(line, 0, line.size() - 1): the last quality character is left out (:45)
-        double ph = 0.0;
-        const size_t n = line.size() > 0 ? line.size() - 1 : 0;
-        if (n > 0) {
-          size_t sum = 0;
-          for (size_t q = 0; q < n; q++) sum += size_t((unsigned char)line[q]);
-          ph = double(sum) / double(n) - 33.0;
-        }
-        ix.add(id, uint64_t(seq_start), uint64_t(seq_len), ph);
-      }
-      byte = endbyte + 1;
-      i++;
+    const int fd = open(seqs_path.c_str(), O_RDONLY);
+    if (fd < 0) die("cannot open " + seqs_path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) die("cannot stat " + seqs_path);
+    const size_t N = size_t(st.st_size);
+    if (N == 0) { close(fd); return ix; }
+    const char* d = static_cast<const char*>(mmap(nullptr, N, PROT_READ, MAP_PRIVATE, fd, 0));
+    if (d == MAP_FAILED) die("cannot map " + seqs_path);
+    madvise(const_cast<char*>(d), N, MADV_SEQUENTIAL);
+    const bool fastq = d[0] == '@';
+    const size_t lpr = fastq ? 4 : 2;
+    if (threads == 0) {
+      if (const char* e = std::getenv("GP_INDEX_THREADS")) threads = unsigned(std::atoi(e));
+      if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
     }
+    const size_t T = std::max<size_t>(1, std::min<size_t>(threads, N / (1u << 20) + 1));
+    std::vector<size_t> cut(T + 1), nl(T + 1, 0);
+    for (size_t t = 0; t <= T; t++) cut[t] = N / T * t;
+    cut[T] = N;
+    auto parallel = [&](auto&& fn) {
+      std::vector<std::thread> th;
+      for (size_t t = 1; t < T; t++) th.emplace_back(fn, t);
+      fn(size_t(0));
+      for (auto& x : th) x.join();
+    };
+    parallel([&](size_t t) { // newlines per slice
+      size_t c = 0;
+      const char* p = d + cut[t];
+      const char* e = d + cut[t + 1];
+      while (p < e) {
+        p = static_cast<const char*>(memchr(p, '\n', size_t(e - p)));
+        if (!p) break;
+        c++; p++;
+      }
+      nl[t + 1] = c;
+    });
+    for (size_t t = 0; t < T; t++) nl[t + 1] += nl[t]; // newlines before slice t
+    struct Rec { std::string id; uint64_t start, len; double phred; };
+    std::vector<std::vector<Rec>> out(T);
+    parallel([&](size_t t) {
+      // first line that starts inside the slice, and its number
+      size_t pos = cut[t], line = nl[t];
+      if (pos != 0 && d[pos - 1] != '\n') {
+        const char* q = static_cast<const char*>(memchr(d + pos, '\n', N - pos));
+        if (!q) return;            // the slice is the middle of the last line
+        pos = size_t(q - d) + 1;
+        line++;
+      }
+      // skip to the first header line (phase 0)
+      while (pos < N && line % lpr != 0) {
+        const char* q = static_cast<const char*>(memchr(d + pos, '\n', N - pos));
+        if (!q) return;
+        pos = size_t(q - d) + 1;
+        line++;
+      }
+      auto line_end = [&](size_t a) { // one past the last character of the line starting at a
+        const char* q = a < N ? static_cast<const char*>(memchr(d + a, '\n', N - a)) : nullptr;
+        return q ? size_t(q - d) : N;
+      };
+      while (pos < N && pos < cut[t + 1]) { // records that start in this slice
+        Rec r;
+        const size_t he = line_end(pos);
+        {
+          const char* sp = static_cast<const char*>(memchr(d + pos, ' ', he - pos));
+          size_t ie = sp ? size_t(sp - d) : he;                 // split(line, " ")[0]
+          size_t ib = ie > pos ? pos + 1 : pos;                 // without its first character
+          if (fastq) {                                          // :33 cut at the first tab
+            const char* tb = ib < ie ? static_cast<const char*>(memchr(d + ib, '\t', ie - ib)) : nullptr;
+            if (tb) ie = size_t(tb - d);
+          }
+          r.id.assign(d + ib, ie - ib);
+        }
+        if (he >= N) break; // header without a sequence line: getline ends, nothing is recorded
+        const size_t sb = he + 1;
+        if (sb >= N) break;  // (an empty last line does not exist for getline)
+        const size_t se = line_end(sb);
+        r.start = sb; r.len = se - sb; r.phred = 0.0;
+        size_t next = se + 1;
+        if (!fastq) { out[t].push_back(std::move(r)); pos = next; continue; }
+        // '+' line, then the quality line
+        if (se >= N || next >= N) break;
+        const size_t pe = line_end(next);
+        if (pe >= N || pe + 1 >= N) break;
+        const size_t qb = pe + 1, qe = line_end(qb);
+        // calc_phred_avg(line, 0, line.size() - 1): the last quality character is left out (:45); btllib reads a
+        // length of 0 as "the whole string" (a 1-character line is averaged over that character) and refuses a
+        // range beyond the string (an empty line: size() - 1 wraps)
+        if (qe == qb) die("calc_phred_avg: range exceeds string.");
+        const size_t n = qe - qb > 1 ? qe - qb - 1 : 1;
+        {
+          size_t sum = 0;
+          const unsigned char* qp = reinterpret_cast<const unsigned char*>(d + qb);
+          for (size_t i = 0; i < n; i++) sum += qp[i];
+          r.phred = double(sum) / double(n) - 33.0;
+        }
+        out[t].push_back(std::move(r));
+        pos = qe + 1;
+      }
+    });
+    size_t total = 0;
+    for (auto& v : out) total += v.size();
+    ix.recs.reserve(total);
+    ix.order.reserve(total);
+    for (auto& v : out)
+      for (auto& r : v) ix.add(r.id, r.start, r.len, r.phred);
+    munmap(const_cast<char*>(d), N);
+    close(fd);
     return ix;
   }
 

@@ -146,3 +146,54 @@ def test_goldpolish_ntedit_chain_and_guard():
         subprocess.check_call([os.path.join(BIN, "goldpolish-ntedit"), base2, " ".join(bfs), "32 28 24 20", "0.5", "0.5", "1", out2],
                               env=ENV, stdout=subprocess.DEVNULL)
         assert os.readlink(out2) == base2 + ".fa"
+
+
+def _odd_files(w):
+    """FASTA / FASTQ files that stress the line arithmetic of src/seqindex.cpp:12-66."""
+    import random
+    rnd = random.Random(11)
+    files = {}
+    recs = []
+    for i in range(3000):
+        n = rnd.choice([1, 2, 5, 60, 700, 5000])               # (an empty quality line stops the reference: below)
+        name = f"r{i}" if i % 97 else "dup"                      # duplicate ids: the first one wins
+        tail = ["", " c=1", "\tx", " a\tb"][i % 4]               # comments after a blank, tabs inside the first token
+        recs.append((name + tail, "".join(rnd.choice("ACGTNacgt") for _ in range(n)),
+                     "".join(chr(rnd.randint(33, 73)) for _ in range(n))))
+    files["a.fa"] = "".join(f">{h}\n{s}\n" for h, s, _ in recs)
+    files["b.fq"] = "".join(f"@{h}\n{s}\n+\n{q}\n" for h, s, q in recs)
+    files["c.fq"] = files["b.fq"][:-1]                           # no newline at the end of the last quality line
+    files["d.fa"] = files["a.fa"].replace("\n", "\r\n")          # a '\r' stays part of its line
+    files["e.fq"] = files["b.fq"] + "@cut\nACGT\n+\n"            # truncated last record: not indexed
+    files["f.fa"] = files["a.fa"] + ">last"                      # header without a sequence line
+    files["g.fq"] = ""                                           # empty file
+    files["h.fa"] = files["a.fa"] + ">empty\n\n>x\nAC\n"        # an empty sequence line is a record of length 0
+    for name, text in files.items():
+        with open(os.path.join(w, name), "w", newline="") as f:
+            f.write(text)
+    return sorted(files)
+
+
+def test_index_tool_threads_and_odd_inputs():
+    """The mmap + threads index builder: any thread count gives the same file, and that file equals the
+    reference's own goldpolish-index (oracle/_ref, build container only) on inputs that stress the line
+    arithmetic."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "goldpolish-index")
+    with _tmp() as w:
+        for name in _odd_files(w):
+            path = os.path.join(w, name)
+            outs = []
+            for threads in ("1", "3", "16"):
+                out = path + f".idx{threads}"
+                subprocess.check_call([os.path.join(BIN, "goldpolish-index"), path, out], env=dict(ENV, GP_INDEX_THREADS=threads))
+                outs.append(open(out).read())
+            assert outs[0] == outs[1] == outs[2], name
+            if os.path.exists(ref) and os.path.getsize(path) > 0:
+                subprocess.check_call([ref, path, path + ".ref"], env=ENV, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                assert sorted(outs[0].splitlines()) == sorted(open(path + ".ref").read().splitlines()), name
+        # an empty quality line: btllib::calc_phred_avg refuses the range, the tool exits 1 (as the reference does)
+        bad = os.path.join(w, "bad.fq")
+        open(bad, "w").write("@a\nACGT\n+\nIIII\n@b\n\n+\n\n")
+        assert subprocess.run([os.path.join(BIN, "goldpolish-index"), bad, bad + ".idx"], env=ENV, capture_output=True).returncode == 1
+        if os.path.exists(ref):
+            assert subprocess.run([ref, bad, bad + ".ref"], env=ENV, capture_output=True).returncode == 1
