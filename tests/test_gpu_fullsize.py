@@ -2,6 +2,7 @@
 properties, since the CPU oracle needs minutes at this size.  (Bit-exactness itself is pinned at
 oracle-sized inputs in test_gpu_parity.py / test_gpu_golden.py.)"""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -107,3 +108,31 @@ def test_three_device_paths_agree(full, monkeypatch):
     assert np.array_equal(a, c)
     assert np.array_equal(off, off2) and np.array_equal(dropped, dropped2)
     assert np.array_equal(out, out2[:int(off2[-1])])
+
+
+@pytest.mark.skipif(not os.environ.get("GP_BIG_TESTS"), reason="BASELINE.json configs[2] size: set GP_BIG_TESTS=1 (about 2 minutes)")
+def test_config3_size_paths_agree():
+    """configs[2]: 100 Mbp draft, 40x reads, bsize 8 (28 G k-mer ops, heavily loaded counting filters, where an
+    order-free update would differ -- SURVEY Appendix C): the in-order kernel, the level-synchronous kernel and
+    the overlapped pipeline give the same filters and the same polished records."""
+    import goldpolish_b200 as gp
+    d = dataset(genome_len=100_000_000, coverage=40.0)
+    pl = plan(d, bsize=8)
+    digests = {}
+    with gp.Context() as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        for algo in ("s", "l"):
+            os.environ["GP_BUILD_KERNEL"] = algo
+            bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+            digests[algo] = hashlib.sha256(bfs.tobytes()).hexdigest()
+        os.environ.pop("GP_BUILD_KERNEL")
+        out, off, dropped = ctx.polish(d.contig_seq, d.contig_off, pl.contig_batch)
+        digests["polish"] = hashlib.sha256(out[:int(off[-1])].tobytes()).hexdigest()
+        ctx.build_stage(pl.batch_entry_off, pl.entries)
+        ctx.polish_stage(d.contig_seq, d.contig_off, pl.contig_batch)
+        ctx.pipeline_run()
+        digests["pipe"] = hashlib.sha256(ctx.build_fetch().tobytes()).hexdigest()
+        out2, off2, dropped2 = ctx.polish_fetch()
+        digests["pipe_polish"] = hashlib.sha256(out2[:int(off2[-1])].tobytes()).hexdigest()
+    assert digests["s"] == digests["l"] == digests["pipe"]
+    assert digests["polish"] == digests["pipe_polish"] and np.array_equal(dropped, dropped2)
