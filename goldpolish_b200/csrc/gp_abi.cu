@@ -43,6 +43,8 @@ struct gp_ctx {
   bool bf_streamed = false;                           // the last build wrote the payloads there itself
   std::vector<uint32_t> h_empty_streams;              // (batch * nk + ki) of streams without a k-mer
   bool edit_ev_valid = false;                         // edit_ev[] were recorded by the last polish
+  int l2_persist_max = 0, l2_window_max = 0;          // persisting-L2 capacity and largest access-policy window (bytes)
+  bool l2_window_set = false;
   int overlap_state = 0;                              // 0 untested, 1 the two kernels co-run on this device, -1 they do not
   bool pipelined = false;                             // last run was gp_pipeline_run's overlapped pass (device timers)
   cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // pack, build, polish (start, stop)
@@ -188,6 +190,9 @@ int gp_ctx_create(const gp_config* cfg, gp_ctx** out)
   ctx->cfg = c;
   std::memset(&ctx->stats, 0, sizeof(ctx->stats));
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, c.device);
+  cudaDeviceGetAttribute(&ctx->l2_persist_max, cudaDevAttrMaxPersistingL2CacheSize, c.device);
+  cudaDeviceGetAttribute(&ctx->l2_window_max, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
+
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -212,6 +217,7 @@ void gp_ctx_destroy(gp_ctx* ctx)
                      &ctx->d_contig_batch, &ctx->d_order, &ctx->d_pnext, &ctx->d_pcounters, &ctx->d_error, &ctx->d_out,
                      &ctx->d_out_off, &ctx->d_batch_order, &ctx->d_batch_done, &ctx->d_order_pipe };
   for (auto* b : bufs) b->release();
+  if (ctx->l2_window_set) { cudaCtxResetPersistingL2Cache(); cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->edit_ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->wave_ev) if (ev) cudaEventDestroy(ev);
@@ -527,6 +533,32 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     p.batch_done = batch_done;
     p.n_batches_total = ctx->n_batches;
     p.bf_host = ctx->bf_host_dev;
+    // the timestamp arrays are the kernel's random-access working set: keep them in the persisting part of L2
+    // (79 of 126 MiB on B200), so that the survivor lists, the sequence and the filters streaming through do not
+    // evict them (+6 % k-mer ops/s).  Only when the window can cover them (one stream in flight).
+    {
+      const size_t vbytes = gp::kCbfCounters * 4 * 2 * ctx->level_slots;
+      const char* e = std::getenv("GP_L2_PERSIST");
+      const bool want = !(e && e[0] == '0') && ctx->l2_persist_max > 0 && vbytes <= size_t(ctx->l2_window_max);
+      cudaStreamAttrValue av;
+      std::memset(&av, 0, sizeof av);
+      if (want) {
+        av.accessPolicyWindow.base_ptr = ctx->d_V.p;
+        av.accessPolicyWindow.num_bytes = vbytes;
+        av.accessPolicyWindow.hitRatio = std::min(1.0f, float(ctx->l2_persist_max) / float(vbytes));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      } // else: an empty window switches the policy off
+      if (want != ctx->l2_window_set) {
+        // the set-aside is carved out of the normal L2: claim it only while the window uses it
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want ? size_t(ctx->l2_persist_max) : 0) != cudaSuccess) cudaGetLastError();
+        if (!want) cudaCtxResetPersistingL2Cache();
+      }
+      if (want || ctx->l2_window_set) {
+        GP_CUDA(ctx, cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
+        ctx->l2_window_set = want;
+      }
+    }
     GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s, ctas_per_sm));
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
     launches += 1;

@@ -50,7 +50,7 @@ struct LevelCtx {
 // round, and rows of equal-length runs (3.7 rows filled of 4) gave a quarter of the warps a run less.
 // anchor[] maps a step to its read entry; lane r fetches the head of run r, so that the dependent loads of all
 // runs overlap.
-constexpr uint32_t kRuns = 4;
+constexpr uint32_t kRuns = 8;
 // steps a warp's survivor list must have room for
 __device__ __forceinline__ uint32_t warp_steps(uint32_t n_steps, uint32_t nwarps) { return n_steps / nwarps + 1u; }
 // run of row r (0..kRuns) of this warp: first step and length (0: none)
