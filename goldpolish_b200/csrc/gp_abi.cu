@@ -44,7 +44,7 @@ struct gp_ctx {
   std::vector<uint32_t> h_empty_streams;              // (batch * nk + ki) of streams without a k-mer
   bool edit_ev_valid = false;                         // edit_ev[] were recorded by the last polish
   int l2_persist_max = 0, l2_window_max = 0;          // persisting-L2 capacity and largest access-policy window (bytes)
-  bool l2_window_set = false;
+  bool l2_window_set = false, l2_roof_window = false;
   int overlap_state = 0;                              // 0 untested, 1 the two kernels co-run on this device, -1 they do not
   bool pipelined = false;                             // last run was gp_pipeline_run's overlapped pass (device timers)
   cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // pack, build, polish (start, stop)
@@ -1093,6 +1093,28 @@ int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t reg
   cudaError_t e = bf.ensure(uint64_t(warps) * gp::kBfBytes);
   if (e != cudaSuccess) { cbf.release(); GP_CUDA(ctx, e); }
   cudaStream_t s = ctx->stream;
+  // same L2 conditions as the kernels the roofs are for: the HBM shape (mode 0..2) runs with the whole L2 as normal
+  // cache; the L2 shapes (mode 3..5, one shared 40 MiB array) get the persisting window the level kernel uses
+  int mode = 0;
+  if (const char* m = std::getenv("GP_ROOF_MODE")) mode = std::atoi(m);
+  {
+    cudaStreamSynchronize(s);
+    const bool want = mode >= 3 && ctx->l2_persist_max > 0 && !(std::getenv("GP_L2_PERSIST") && std::getenv("GP_L2_PERSIST")[0] == '0');
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof av);
+    if (want) {
+      av.accessPolicyWindow.base_ptr = cbf.p;
+      av.accessPolicyWindow.num_bytes = gp::kCbfCounters * 4;
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want ? size_t(ctx->l2_persist_max) : 0) != cudaSuccess) cudaGetLastError();
+    cudaCtxResetPersistingL2Cache();
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+    ctx->l2_window_set = false; // the next build claims its own window again
+    ctx->l2_roof_window = want;
+  }
   cudaMemsetAsync(cbf.p, 0, uint64_t(warps) * region_bytes, s);
   cudaMemsetAsync(bf.p, 0, uint64_t(warps) * gp::kBfBytes, s);
   cudaEvent_t a, b;
@@ -1105,12 +1127,19 @@ int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t reg
   float t = 0;
   cudaEventElapsedTime(&t, a, b);
   cudaEventDestroy(a); cudaEventDestroy(b);
+  if (ctx->l2_roof_window) { // leave no window / set-aside behind
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof av);
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    ctx->l2_roof_window = false;
+  }
   cbf.release(); bf.release();
   GP_CUDA(ctx, e);
   if (ms) *ms = t;
   // modes 3..5 touch 4 sectors per iteration (one round), the build-kernel mix 8
-  int touches = 8;
-  if (const char* m = std::getenv("GP_ROOF_MODE")) touches = std::atoi(m) >= 3 ? 4 : 8;
+  const int touches = mode >= 3 ? 4 : 8;
   *sectors_per_s = double(warps) * iters * 32.0 * touches / (double(t) * 1e-3);
   return GP_OK;
 }
