@@ -88,6 +88,8 @@ class SimData:
     map_read: np.ndarray
     map_contig: np.ndarray
     map_mx: np.ndarray
+    map_tstart: np.ndarray          # overlap of the read with the contig, contig coordinates (truth space)
+    map_tend: np.ndarray
     truth: np.ndarray
     fastq: bool
     params: dict = field(default_factory=dict)
@@ -139,6 +141,8 @@ def simulate(write_dir: str | None = None, **kw) -> SimData:
             map_read=_arr(s.map_read, nm, np.uint32),
             map_contig=_arr(s.map_contig, nm, np.uint32),
             map_mx=_arr(s.map_mx, nm, np.uint32),
+            map_tstart=_arr(s.map_tstart, nm, np.uint32),
+            map_tend=_arr(s.map_tend, nm, np.uint32),
             truth=_arr(s.truth, s.truth_len, np.uint8),
             fastq=bool(s.fastq),
             params={k: getattr(p, k) for k, _ in _Params._fields_},
