@@ -537,7 +537,7 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     // (79 of 126 MiB on B200), so that the survivor lists, the sequence and the filters streaming through do not
     // evict them (+6 % k-mer ops/s).  Only when the window can cover them (one stream in flight).
     {
-      const size_t vbytes = gp::kCbfCounters * 4 * 2 * ctx->level_slots;
+      const size_t vbytes = gp::kCbfCounters * 4 * (ctx->level_fused ? 2 : 1) * ctx->level_slots; // (arrays are packed slot after slot)
       const char* e = std::getenv("GP_L2_PERSIST");
       const bool want = !(e && e[0] == '0') && ctx->l2_persist_max > 0 && vbytes <= size_t(ctx->l2_window_max);
       cudaStreamAttrValue av;

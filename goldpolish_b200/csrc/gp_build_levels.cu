@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       if (S.done_b1) filter_final(p, S.done_b1 - 1u, S.done_ki, gtid, gthreads); // the slot's previous stream is complete everywhere
       const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk, batch = stream_batch(p, lb);
       // two timestamp arrays per slot: T_L lives in array (L + 1) & 1 (the second one is used by the fused rounds only)
-      uint32_t* __restrict__ V0 = p.V + uint64_t(sl) * 2u * kCbfCounters;
+      uint32_t* __restrict__ V0 = p.V + uint64_t(sl) * (p.fused ? 2u : 1u) * kCbfCounters;
       uint32_t* __restrict__ V = V0 + ((p.fused && phase == PH_READ) ? ((L + 1u) & 1u) * kCbfCounters : 0u);
       uint32_t* __restrict__ Vn = V0 + (L & 1u) * kCbfCounters; // T_{L+1} (fused rounds)
       const uint32_t tag_next = S.tag_next;
