@@ -381,6 +381,7 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
       if (batch_entry_off[b + 1] - batch_entry_off[b] > 0xFFFFull) ok = false; // step -> entry anchors are 16 bits
       for (uint64_t e = batch_entry_off[b]; e < batch_entry_off[b + 1]; e++) {
         maxthr[b] = std::max(maxthr[b], entries[e].kmer_threshold);
+        if (entries[e].kmer_threshold > 48) ok = false; // a stream's levels must fit the 6-bit epoch tags (the reference caps T at 13)
         entry_rel[e] = uint16_t(e - batch_entry_off[b]);
       }
     }
