@@ -156,6 +156,24 @@ def test_filters_streamed_to_pinned_host_memory(gp, pipeline):
             ctx.build_output(np.zeros(want.shape, dtype=np.uint8))   # pageable memory is refused
 
 
+def test_large_thresholds_fall_back_to_the_in_order_kernel(gp, small):
+    """kmer_threshold values beyond what the level kernel's epoch tags can hold (the reference never produces
+    them: T <= 13) are built by the in-order kernel, still bit-exact."""
+    from oracle import oracle_lib as ol
+    d, ctx = small
+    pl = plan(d, bsize=2)
+    entries = pl.entries.copy()
+    entries["kmer_threshold"][: len(entries) // 2] = 60
+    bfs = ctx.build_filters(pl.batch_entry_off, entries)
+    assert ctx.stats()["build_kernel"] == 1
+    for b in (0, len(pl.batch_entry_off) - 2):
+        fs = ol.FilterSet(KS)
+        for e in range(int(pl.batch_entry_off[b]), int(pl.batch_entry_off[b + 1])):
+            fs.add_read(d.read(int(entries[e]["read_id"])), int(entries[e]["kmer_threshold"]))
+        for ki in range(4):
+            assert np.array_equal(bfs[b, ki], fs.bfs[ki])
+
+
 def test_polish_identity_filters(gp, small):
     """All-ones filter: every k-mer present, nothing is edited.  All-zero filter: every position that
     passes the look-ahead is soft-masked and nothing else changes (size-independent properties)."""
