@@ -1073,13 +1073,17 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
         const volatile uint32_t* progress = p.batch_done + p.n_batches; // filters finished so far, all batches
         unsigned long long t0 = 0, t1 = 0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        uint32_t seen = *progress;
+        uint32_t seen = *progress, naps = 0;
+        unsigned ns = 128;
         while (*flag < p.nk) {
-          __nanosleep(256);
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          const uint32_t now = *progress;
-          if (now != seen) { seen = now; t0 = t1; }
-          else if (t1 - t0 > 4000000000ull) { ok = 0; break; } // 4 s without ANY new filter: the build is not running beside us
+          __nanosleep(ns);
+          if (ns < 2048) ns <<= 1; // back off: hundreds of waiting warps must not hammer the two words they all read
+          if ((++naps & 15u) == 0u) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            const uint32_t now = *progress;
+            if (now != seen) { seen = now; t0 = t1; }
+            else if (t1 - t0 > 4000000000ull) { ok = 0; break; } // 4 s without ANY new filter: the build is not running beside us
+          }
         }
         __threadfence();
       }
