@@ -410,8 +410,8 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * 2 * ctx->level_slots));
     // per slot: warp-private survivor lists, 5 words per entry (a warp's region is its share of
     // the steps, rounded up, x 32); then the barrier counters
-    ctx->surv_cap = uint32_t(size_t(ctx->alive_words) * 32 + size_t(8192) * 4 * 32);
-    GP_CUDA(ctx, ctx->d_alive.ensure(size_t(ctx->surv_cap) * 5 * ctx->level_slots * 4 + 64));
+    ctx->surv_cap = uint32_t(size_t(ctx->alive_words) * 32 + size_t(8192) * 9 * 32); // + (runs + 1) slack slots per warp
+    GP_CUDA(ctx, ctx->d_alive.ensure(size_t(ctx->surv_cap) * 5 * ctx->level_slots * 4 + 64 + 8192));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_step_pre.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_max_thr.p, maxthr.data(), maxthr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (ok) {
@@ -527,7 +527,12 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
     if (c.keep_counters) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * 2 * ctx->level_slots, s));
-    GP_CUDA(ctx, cudaMemsetAsync(p.bars, 0, 64, s));
+    GP_CUDA(ctx, cudaMemsetAsync(p.bars, 0, 64 + 8192, s));
+    p.speed = reinterpret_cast<uint32_t*>(p.bars + 8);
+    {
+      const char* e = std::getenv("GP_LEVEL_WEIGHTED");
+      p.weighted = (ctx->level_slots == 1 && !(e && e[0] == '0')) ? 1u : 0u;
+    }
     while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
     p.batch_order = batch_order;

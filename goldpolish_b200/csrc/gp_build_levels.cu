@@ -39,33 +39,35 @@ struct LevelCtx {
   const uint64_t* tf;
   const uint64_t* tr;
   uint32_t lane, gwarp, nwarps;
+  // this warp's share of every stream: the fraction [cum[0], cum[1]) of 2^32 (all warps together tile [0, 2^32]);
+  // kept in shared memory, read where needed
+  const uint64_t* cum;
 };
 
 // A step is 32 consecutive k-mer starts of one read; steps of a stream are numbered in the
-// reference's order, which makes (step * 32 + lane) the occurrence time.  Every warp gets the same number of
-// steps (+1 for the first `rem` columns), cut into kRuns runs that are spread over the whole time axis: the
-// stream is laid out as kRuns "rows" of nwarps runs each -- row r has runs of q or q + 1 steps -- plus a last
-// row of single leftover steps, and a warp takes one run per row, in snake order (its column counted backwards
-// in odd rows).  Survivors crowd towards late times; contiguous shares left the early warps idle in every list
-// round, and rows of equal-length runs (3.7 rows filled of 4) gave a quarter of the warps a run less.
-// anchor[] maps a step to its read entry; lane r fetches the head of run r, so that the dependent loads of all
-// runs overlap.
+// reference's order, which makes (step * 32 + lane) the occurrence time.  A warp's share of a stream is a
+// fraction [cum[0], cum[1]) of it -- equal fractions to begin with, then proportional to the speed measured for
+// the warp's SM (the same work takes 88..106 us depending on where the SM sits) -- cut into kRuns runs that are
+// spread over the whole time axis: the stream is kRuns "rows" (time slabs) and the warp takes its fraction of
+// every row, the row boundaries dithered by r / kRuns so that the roundings of the rows do not add up (at
+// 5 steps per warp every row gives a warp 0 or 1 step).  Survivors crowd towards late times; contiguous shares
+// left the early warps idle in every list round.  anchor[] maps a step to its read entry; lane r fetches the
+// head of run r, so that the dependent loads of all runs overlap.
 constexpr uint32_t kRuns = 8;
-// steps a warp's survivor list must have room for
-__device__ __forceinline__ uint32_t warp_steps(uint32_t n_steps, uint32_t nwarps) { return n_steps / nwarps + 1u; }
-// run of row r (0..kRuns) of this warp: first step and length (0: none)
+// steps before the warp's share (its survivor list starts there, + one slack slot per row and warp)
+__device__ __forceinline__ uint64_t warp_list_base(uint32_t n_steps, const LevelCtx& c)
+{
+  return ((uint64_t(n_steps) * c.cum[0]) >> 32) + uint64_t(c.gwarp) * (kRuns + 1u);
+}
+// run of row r (0..kRuns-1) of this warp: first step and length (0: none)
 __device__ __forceinline__ void run_of_row(uint32_t r, uint32_t n_steps, const LevelCtx& c, uint32_t& s0, uint32_t& len)
 {
-  const uint32_t per = n_steps / c.nwarps, rem = n_steps - per * c.nwarps;
-  const uint32_t q = per / kRuns, x = per - q * kRuns; // rows 0..x-1 have q + 1 steps per run, rows x..kRuns-1 have q
-  const uint32_t col = (r & 1u) ? c.nwarps - 1u - c.gwarp : c.gwarp;
-  if (r < kRuns) {
-    len = q + (r < x ? 1u : 0u);
-    s0 = (r * q + min(r, x)) * c.nwarps + col * len;
-  } else { // the leftover steps, one each
-    len = col < rem ? 1u : 0u;
-    s0 = per * c.nwarps + col;
-  }
+  const uint32_t r0 = uint32_t(uint64_t(n_steps) * r / kRuns), r1 = uint32_t(uint64_t(n_steps) * (r + 1u) / kRuns);
+  const uint64_t rowlen = r1 - r0, phase = (uint64_t(r) << 32) / kRuns;
+  // boundaries floor(rowlen * cum + phase): 0 for cum = 0, rowlen for cum = 2^32, the same on both sides of a warp border
+  const uint32_t a = uint32_t((rowlen * c.cum[0] + phase) >> 32), b = uint32_t((rowlen * c.cum[1] + phase) >> 32);
+  s0 = r0 + a;
+  len = r < kRuns ? b - a : 0u;
 }
 
 // Calls f(step, entry thr, valid, ci, bi) for every step of this warp's runs.
@@ -80,7 +82,7 @@ __device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c
   uint32_t h_e = 0, h_first = 0, h_last = 0, h_thr = 0, h_len = 0, h_wlo = 0, h_whi = 0;
   {
     uint32_t s0 = 0, len = 0;
-    if (c.lane <= kRuns) run_of_row(c.lane, n_steps, c, s0, len);
+    if (c.lane < kRuns) run_of_row(c.lane, n_steps, c, s0, len);
     if (len) {
       h_e = __ldg(anchor + s0);
       const uint64_t e = e0 + h_e;
@@ -93,7 +95,7 @@ __device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c
     }
   }
 #pragma unroll 1
-  for (uint32_t r = 0; r <= kRuns; r++) {
+  for (uint32_t r = 0; r < kRuns; r++) {
     uint32_t s0, len;
     run_of_row(r, n_steps, c, s0, len);
     if (len == 0) continue;
@@ -285,11 +287,25 @@ __device__ __forceinline__ void filter_final(const LevelParams& p, uint32_t batc
   }
 }
 
+// sum over the CTA, the same value in every thread (scratch: one slot per warp)
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v, unsigned long long* scratch)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31u) == 0u) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long t = 0;
+  for (uint32_t w = 0; w < (blockDim.x >> 5); w++) t += scratch[w];
+  return t;
+}
+
 enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_L1 = 2, PH_WRITE = 3, PH_READ = 4 };
 
 struct SlotState {      // uniform over the grid; written by thread 0 of each CTA between rounds
   uint32_t sid;         // wave-local stream, >= n_streams when the slot has run dry
   uint32_t phase, L, lread, epoch, tag, tag_next, n_steps;
+  uint32_t ord, publish, recal; // streams begun in this slot; this stream's round 0 publishes / re-reads the SM speeds
   uint32_t done_b1, done_ki; // batch + 1 and k index of the slot's previous stream while its last barrier drains (0: none)
   unsigned long long target; // barrier count that must be reached before the slot's next round
 };
@@ -304,6 +320,9 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   __shared__ SlotState slots[kMaxSlots];
   __shared__ uint32_t next_sid;
   __shared__ uint32_t warp_cnt[kMaxSlots][kLevelWarps]; // survivors in each warp's private list
+  __shared__ uint64_t cum_sh[kLevelWarps + 1];          // share boundaries of this CTA's warps (fractions of 2^32)
+  __shared__ unsigned long long cal_ns, cal_steps;      // round-0 work of this CTA since its last speed publication
+  __shared__ unsigned long long red_sh[3][kLevelWarps];
   if (p.batch_done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the edit kernel may join us now
   if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[20] = globaltimer_ns();
   fill_hash_tables(tf, tr);
@@ -312,8 +331,11 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   c.lane = threadIdx.x & 31u;
   c.gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   c.nwarps = (gridDim.x * blockDim.x) >> 5;
+  c.cum = cum_sh + (threadIdx.x >> 5);                   // equal shares (below) until speeds have been measured
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   unsigned long long ops = 0;
+  if (threadIdx.x == 0) { cal_ns = 0; cal_steps = 0; }
+  if (threadIdx.x <= uint32_t(kLevelWarps)) cum_sh[threadIdx.x] = (uint64_t(blockIdx.x * kLevelWarps + threadIdx.x) << 32) / c.nwarps;
 
   // stream -> (n_steps, lread); called by thread 0 only
   auto begin_stream = [&](SlotState& S) {
@@ -331,6 +353,9 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
       // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
       S.lread = p.cbf_pool ? lmax : lmax - 1u;
+      S.ord++;
+      S.publish = p.weighted && (S.ord & 63u) == 4u; // after 4 streams, then every 64: publish the CTA's speed ...
+      S.recal = p.weighted && (S.ord & 63u) == 5u;   // ... and the next stream starts with re-weighted shares
       if (S.epoch + lmax + 1 > kMaxEpoch) { S.phase = PH_CLEAR; return; } // the tags of this stream would wrap
       S.phase = PH_L0;
       S.epoch++;
@@ -342,7 +367,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
     next_sid = 0;
     for (uint32_t s = 0; s < p.n_slots; s++) {
       slots[s].epoch = 0; slots[s].target = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
-      slots[s].done_b1 = 0; slots[s].done_ki = 0;
+      slots[s].done_b1 = 0; slots[s].done_ki = 0; slots[s].ord = 0; slots[s].publish = 0; slots[s].recal = 0;
       begin_stream(slots[s]);
     }
   }
@@ -361,7 +386,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       const uint32_t wib = threadIdx.x >> 5;
       SurvList lst;
       {
-        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + uint64_t(c.gwarp) * (warp_steps(S.n_steps, c.nwarps) * 32u);
+        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + warp_list_base(S.n_steps, c) * 32u;
 #pragma unroll
         for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
       }
@@ -383,15 +408,37 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       };
       fetch_entries(0);
       if (threadIdx.x == 0) {
-        if (blockIdx.x == p.report_cta) t_a = globaltimer_ns();
+        t_a = globaltimer_ns();
         const unsigned long long target = S.target;
         while (ld_relaxed_u64(bar) < target) { }
         __threadfence();
-        if (blockIdx.x == p.report_cta) t_b = globaltimer_ns();
+        t_b = globaltimer_ns();
       }
       __syncthreads(); // the slot's previous round is complete everywhere
 
       const uint32_t sid = S.sid, phase = S.phase, tag = S.tag, L = S.L, n_steps = S.n_steps, lread = S.lread;
+      if (phase == PH_L0 && S.recal) {
+        // every CTA published the rate of its round-0 passes (steps per time) a few rounds ago: shares become
+        // proportional to them.  Integer sums, so that every CTA derives the very same boundaries.
+        unsigned long long tot = 0;
+        for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot += __ldcg(p.speed + i);
+        tot = block_sum(tot, red_sh[0]);
+        const unsigned long long mean = max(1ull, tot / gridDim.x), lo = max(1ull, mean * 7ull / 10ull), hi = mean * 14ull / 10ull + 1ull;
+        unsigned long long all = 0, before = 0, mine = 0;
+        for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+          const unsigned long long v = min(max((unsigned long long)__ldcg(p.speed + i), lo), hi);
+          all += v;
+          if (i < blockIdx.x) before += v;
+          if (i == blockIdx.x) mine = v;
+        }
+        all = block_sum(all, red_sh[0]); before = block_sum(before, red_sh[1]); mine = block_sum(mine, red_sh[2]);
+        if (threadIdx.x <= uint32_t(kLevelWarps))
+          cum_sh[threadIdx.x] = ((before * kLevelWarps + mine * threadIdx.x) << 32) / (all * kLevelWarps);
+        __syncthreads();
+        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + warp_list_base(n_steps, c) * 32u;
+#pragma unroll
+        for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
+      }
       if (S.done_b1) filter_final(p, S.done_b1 - 1u, S.done_ki, gtid, gthreads); // the slot's previous stream is complete everywhere
       const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk, batch = stream_batch(p, lb);
       // two timestamp arrays per slot: T_L lives in array (L + 1) & 1 (the second one is used by the fused rounds only)
@@ -548,10 +595,18 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
 
       __syncthreads(); // every thread of the CTA has issued its part of the round
       if (threadIdx.x == 0) {
+        const unsigned long long t_c = globaltimer_ns();
+        if (phase == PH_L0 && p.weighted) { // this CTA's round-0 rate, for the weighted shares
+          cal_ns += t_c - t_b;
+          cal_steps += ((uint64_t(n_steps) * cum_sh[kLevelWarps]) >> 32) - ((uint64_t(n_steps) * cum_sh[0]) >> 32);
+          if (S.publish) {
+            p.speed[blockIdx.x] = uint32_t(min(max(cal_steps * 4000000ull / max(cal_ns, 1ull), 1ull), 262143ull));
+            cal_ns = 0; cal_steps = 0;
+          }
+        }
         __threadfence();
         atomicAdd(bar, 1ull);
         if (blockIdx.x == p.report_cta) { // where the time of one CTA goes, per kind of round: barrier wait, work, rounds
-          const unsigned long long t_c = globaltimer_ns();
           p.counters[2 + phase * 3 + 0] += t_b - t_a;
           p.counters[2 + phase * 3 + 1] += t_c - t_b;
           p.counters[2 + phase * 3 + 2] += 1;

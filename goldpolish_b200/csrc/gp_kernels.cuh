@@ -43,6 +43,8 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   uint32_t* V;                    // per slot: 2 x kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
   uint32_t* surv;                 // per slot: 5 arrays of surv_cap words ({4 packed indices, time|thr}), warp-private regions
   unsigned long long* bars;       // per slot: barrier arrival counter (zeroed before a launch)
+  uint32_t* speed;                // per CTA: published round-0 rate (weighted shares)
+  uint32_t weighted;              // 1: shares follow the measured speed of each CTA's SM (one stream in flight only)
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
   uint32_t* bf_pool;
   uint32_t* bf_host;              // optional: device-visible pinned host copy of bf_pool, filled as filters become final
