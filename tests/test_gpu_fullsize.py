@@ -85,12 +85,15 @@ def test_polish_subset_consistency_and_identity(full):
     assert np.array_equal(o4[:int(f4[-1])], kept)
 
 
-def test_three_device_paths_agree(full, monkeypatch):
+@pytest.mark.parametrize("bsize", [1, 8])
+def test_three_device_paths_agree(full, bsize, monkeypatch):
     """The oracle is too slow at this size, but three independent device paths must agree bit for bit:
     the in-order one-warp-per-stream kernel (counters in HBM, sequential semantics inside a warp), the
     level-synchronous kernel (order-free rounds over timestamps), and the overlapped pipeline (batches
     built longest-contig first, edit kernel beside the build kernel)."""
     gp, d, pl, ctx = full
+    if bsize != 1:  # large streams: heavily loaded counting filters, weighted shares at work
+        pl = plan(d, bsize=bsize)
     monkeypatch.setenv("GP_BUILD_KERNEL", "s")
     a = ctx.build_filters(pl.batch_entry_off, pl.entries)
     assert ctx.stats()["build_kernel"] == 1
