@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   __shared__ uint64_t cum_sh[kLevelWarps + 1];          // share boundaries of this CTA's warps (fractions of 2^32)
   __shared__ unsigned long long cal_ns, cal_steps;      // round-0 work of this CTA since its last speed publication
   __shared__ unsigned long long red_sh[3][kLevelWarps];
+  __shared__ unsigned long long diag[15];               // round-time diagnostics of this CTA (thread 0)
   if (p.batch_done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the edit kernel may join us now
   if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[20] = globaltimer_ns();
   fill_hash_tables(tf, tr);
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   unsigned long long ops = 0;
   if (threadIdx.x == 0) { cal_ns = 0; cal_steps = 0; }
+  if (threadIdx.x < 15) diag[threadIdx.x] = 0;
   if (threadIdx.x <= uint32_t(kLevelWarps)) cum_sh[threadIdx.x] = (uint64_t(blockIdx.x * kLevelWarps + threadIdx.x) << 32) / c.nwarps;
 
   // stream -> (n_steps, lread); called by thread 0 only
@@ -606,11 +608,11 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         }
         __threadfence();
         atomicAdd(bar, 1ull);
-        if (blockIdx.x == p.report_cta) { // where the time of one CTA goes, per kind of round: barrier wait, work, rounds
-          p.counters[2 + phase * 3 + 0] += t_b - t_a;
-          p.counters[2 + phase * 3 + 1] += t_c - t_b;
-          p.counters[2 + phase * 3 + 2] += 1;
-        }
+        // where the time of a CTA goes, per kind of round: barrier wait, work, rounds (kept in shared memory: global
+        // read-modify-writes here would make the reporting CTA late for every barrier)
+        diag[phase * 3 + 0] += t_b - t_a;
+        diag[phase * 3 + 1] += t_c - t_b;
+        diag[phase * 3 + 2] += 1;
         S.target += gridDim.x;
         S.done_b1 = 0;
         // next round of this slot (same decision in every CTA)
@@ -656,6 +658,8 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);
   if (c.lane == 0 && ops) atomicAdd(p.counters + 0, ops);
   if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[21] = globaltimer_ns();
+  if (blockIdx.x == p.report_cta && threadIdx.x == 0)
+    for (int i = 0; i < 15; i++) p.counters[2 + i] += diag[i]; // several waves add up
 }
 
 int levels_max_grid(int sm_count, int ctas_per_sm)
