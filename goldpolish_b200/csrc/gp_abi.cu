@@ -199,6 +199,8 @@ int gp_ctx_create(const gp_config* cfg, gp_ctx** out)
     return GP_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  gp::preload_levels(); // (CUDA loads kernels lazily; the first overlapped pass must not stall on that)
+  gp::preload_edit();
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   for (auto& ev : ctx->edit_ev) cudaEventCreate(&ev);
   *out = ctx;

@@ -675,6 +675,13 @@ int levels_max_grid(int sm_count, int ctas_per_sm)
 
 int levels_max_slots() { return kMaxSlots; }
 
+void preload_levels()
+{
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, (const void*)build_filters_levels_kernel) != cudaSuccess) cudaGetLastError();
+  if (cudaFuncGetAttributes(&a, (const void*)fill_anchor_kernel) != cudaSuccess) cudaGetLastError();
+}
+
 cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s, int ctas_per_sm)
 {
   if (p.n_streams == 0) return cudaSuccess;

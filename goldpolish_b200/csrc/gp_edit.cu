@@ -1152,6 +1152,14 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
 // (per scheduler: 2 build CTAs x 2 warps x 80 registers + one edit warp x 168 registers <= 16384).
 constexpr int kAlongsideWarps = 3;
 
+// load the kernel now (lazy module loading would otherwise do it at the first launch -- and that launch would wait for
+// everything already running, e.g. the build kernel it is meant to run beside)
+void preload_edit()
+{
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, (const void*)edit_kernel) != cudaSuccess) cudaGetLastError();
+}
+
 cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool alongside_build)
 {
   if (p.n_contigs == 0) return cudaSuccess;

@@ -107,6 +107,8 @@ void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint6
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s, int ctas_per_sm = 0);
 int levels_max_slots();
+void preload_levels();
+void preload_edit();
 void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uint16_t* anchor, uint32_t n_entries,
                         uint32_t nk, uint64_t anchor_stride, cudaStream_t s);
 void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t iters, uint32_t warps, cudaStream_t s);
