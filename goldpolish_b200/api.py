@@ -51,7 +51,7 @@ EXPORTS = ["gp_default_config", "gp_ctx_create", "gp_ctx_destroy", "gp_last_erro
            "gp_ctx_synchronize", "gp_get_stats", "gp_reads_upload", "gp_build_filters", "gp_build_stage",
            "gp_build_run", "gp_build_fetch", "gp_build_fetch_cbf", "gp_filters_load", "gp_polish",
            "gp_polish_stage", "gp_polish_run", "gp_polish_fetch", "gp_kmer_threshold", "gp_mappings_cap",
-           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep", "gp_build_output_host"]
+           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep", "gp_build_output_host", "gp_host_alloc", "gp_host_free"]
 
 
 def load_library():
@@ -96,6 +96,10 @@ def load_library():
     l.gp_build_round_times.argtypes = [vp, C.POINTER(u64)]
     l.gp_pipeline_run.argtypes = [vp]
     l.gp_build_output_host.argtypes = [vp, vp]
+    l.gp_host_alloc.argtypes = [u64]
+    l.gp_host_alloc.restype = vp
+    l.gp_host_free.argtypes = [vp]
+    l.gp_host_free.restype = None
     l.gp_prep.argtypes = [vp, u32, vp, vp, C.c_int32, u32, C.c_int32, vp, u64, vp]
     _lib = l
     return l

@@ -641,6 +641,18 @@ int gp_build_round_times(gp_ctx* ctx, uint64_t out[16])
   return GP_OK;
 }
 
+void* gp_host_alloc(uint64_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, size_t(bytes), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void gp_host_free(void* p)
+{
+  if (p) cudaFreeHost(p);
+}
+
 int gp_build_output_host(gp_ctx* ctx, uint8_t* bf_out_pinned)
 {
   if (!ctx) return GP_ERR_ARG;

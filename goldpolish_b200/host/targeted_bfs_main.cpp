@@ -65,15 +65,19 @@ struct Server {
   std::deque<std::shared_ptr<Request>> queue;
   bool stopping = false;
 
-  // GPU worker: builds every request that is pending in one call
+  // GPU worker: builds every request that is pending in one call.  The payloads land in page-locked memory
+  // that the build kernel fills filter by filter as they become final (gp_build_output_host): no bulk copy
+  // after the build, and what bfs[i]->save() writes (:138-140) is ready when the call returns.
   void gpu_loop()
   {
+    uint8_t* pinned = nullptr;
+    size_t pinned_cap = 0;
     for (;;) {
       std::vector<std::shared_ptr<Request>> todo;
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_work.wait(lk, [&] { return stopping || !queue.empty(); });
-        if (queue.empty() && stopping) return;
+        if (queue.empty() && stopping) { gp_build_output_host(ctx, nullptr); gp_host_free(pinned); return; }
         todo.assign(queue.begin(), queue.end());
         queue.clear();
       }
@@ -83,12 +87,24 @@ struct Server {
         ents.insert(ents.end(), r->entries.begin(), r->entries.end());
         off.push_back(ents.size());
       }
-      std::vector<uint8_t> out(todo.size() * ks.size() * GP_BF_BYTES);
-      check_gp(ctx, gp_build_filters(ctx, uint32_t(todo.size()), off.data(), ents.data(), out.data()), "gp_build_filters");
+      const size_t need = todo.size() * ks.size() * GP_BF_BYTES;
+      std::vector<uint8_t> pageable;
+      uint8_t* out = nullptr;
+      if (need > pinned_cap) {
+        gp_build_output_host(ctx, nullptr);
+        gp_host_free(pinned);
+        pinned_cap = need + need / 2;
+        pinned = static_cast<uint8_t*>(gp_host_alloc(pinned_cap));
+        if (!pinned) pinned_cap = 0;
+        else check_gp(ctx, gp_build_output_host(ctx, pinned), "gp_build_output_host");
+      }
+      if (pinned) out = pinned;
+      else { pageable.resize(need); out = pageable.data(); } // no page-locked memory to be had: plain copy
+      check_gp(ctx, gp_build_filters(ctx, uint32_t(todo.size()), off.data(), ents.data(), out), "gp_build_filters");
       {
         std::lock_guard<std::mutex> lk(mu);
         for (size_t i = 0; i < todo.size(); i++) {
-          todo[i]->payload.assign(out.begin() + i * ks.size() * GP_BF_BYTES, out.begin() + (i + 1) * ks.size() * GP_BF_BYTES);
+          todo[i]->payload.assign(out + i * ks.size() * GP_BF_BYTES, out + (i + 1) * ks.size() * GP_BF_BYTES);
           todo[i]->done = true;
         }
       }

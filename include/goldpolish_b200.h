@@ -137,6 +137,10 @@ int gp_build_run(gp_ctx* ctx);
  * only synchronises -- no bulk D2H after the build.  NULL switches it off.  What the reference does per batch with
  * bfs[i]->save() (goldpolish_targeted_bfs.cpp:138-140), without the end-of-build wait. */
 int gp_build_output_host(gp_ctx* ctx, uint8_t* bf_out_pinned);
+/* Page-locked host memory for callers that do not link the CUDA runtime themselves (the C++ drop-in tools):
+ * NULL when it cannot be had.  A context must exist (the device is chosen by then). */
+void* gp_host_alloc(uint64_t bytes);
+void gp_host_free(void* p);
 int gp_build_fetch(gp_ctx* ctx, uint8_t* bf_out);
 /* debug / parity: counting-filter bytes of (batch, k index) after the last build */
 int gp_build_fetch_cbf(gp_ctx* ctx, uint32_t batch, uint32_t k_index, uint8_t* cbf_out);
