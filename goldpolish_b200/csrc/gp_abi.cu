@@ -69,7 +69,7 @@ struct gp_ctx {
   // level-synchronous build
   DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel;
   uint64_t anchor_stride = 0;
-  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_fused = 1;
+  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_fused = 1, level_time_bits = 26;
   bool levels_ok = false; // every stream fits the 26-bit occurrence clock
   int build_algo = 0;     // 0 = auto, 1 = warp per stream, 2 = level-synchronous
   int build_algo_resolved = 1;
@@ -399,6 +399,8 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     ctx->levels_ok = ok;
     ctx->n_entries = uint32_t(n_entries);
     ctx->alive_words = uint32_t(max_steps + 1);
+    ctx->level_time_bits = 16; // occurrence times of the longest stream must fit
+    while (ctx->level_time_bits < 26 && (max_steps * 32) >> ctx->level_time_bits) ctx->level_time_bits++;
     GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
     GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
     // level-synchronous kernel: streams in flight (each with two timestamp arrays and its survivor lists)
@@ -516,6 +518,7 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     p.surv = ctx->d_alive.as<uint32_t>();
     p.bars = reinterpret_cast<unsigned long long*>(ctx->d_alive.as<uint32_t>() + size_t(5) * ctx->surv_cap * ctx->level_slots);
     p.n_slots = ctx->level_slots;
+    p.time_bits = ctx->level_time_bits;
     if (const char* f = std::getenv("GP_LEVEL_REPORT_CTA")) p.report_cta = uint32_t(std::atoi(f));
     p.fused = ctx->level_fused;
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;

@@ -30,9 +30,12 @@
 
 namespace gp {
 
+// list entries: time in the low 26 bits of the meta word, thr above
 constexpr uint32_t kTimeBits = 26;
 constexpr uint32_t kTimeMask = (1u << kTimeBits) - 1u;
-constexpr uint32_t kMaxEpoch = 62; // tags 63 - epoch; tag 63 (epoch 0) is the cleared state
+// timestamp entries: tag << time_bits | time, where time_bits (LevelParams) is just wide enough for the longest
+// stream of the launch: 26 bits leave 62 epochs between two clear rounds, 22 bits (3 M k-mers) a thousand.
+// Tags count down (newer epochs compare smaller); the all-ones tag (epoch 0) is the cleared state.
 constexpr int kLevelWarps = 8;
 
 struct LevelCtx {
@@ -206,8 +209,8 @@ __device__ __forceinline__ void red_or(uint32_t* p, uint32_t v)
 }
 
 // the level test: all four counters carry the current tag and a time before t
-__device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8_t* __restrict__ cbf, uint32_t tag, uint32_t t,
-                                           uint32_t L, const uint32_t (&ci)[4])
+__device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8_t* __restrict__ cbf, uint32_t tag, uint32_t vmask,
+                                           uint32_t t, uint32_t L, const uint32_t (&ci)[4])
 {
   uint32_t v[4];
 #pragma unroll
@@ -216,8 +219,8 @@ __device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8
   uint32_t mx = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    reached &= (v[j] & ~kTimeMask) == tag;
-    mx = max(mx, v[j] & kTimeMask);
+    reached &= (v[j] & ~vmask) == tag;
+    mx = max(mx, v[j] & vmask);
     if (cbf && v[j] == (tag | t)) cbf[ci[j]] = (uint8_t)L; // this occurrence moved counter j to level L
   }
   return reached && t > mx;
@@ -225,16 +228,17 @@ __device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8
 // the same test for occurrences that mostly fail it (level 1 from the sequence: most k-mers of
 // noisy reads are seen once, and such an occurrence is the first toucher of its own counters):
 // look at one counter, fetch the other three only if that one was reached before t
-__device__ __forceinline__ bool level_test_early(const uint32_t* __restrict__ V, uint32_t tag, uint32_t t, const uint32_t (&ci)[4])
+__device__ __forceinline__ bool level_test_early(const uint32_t* __restrict__ V, uint32_t tag, uint32_t vmask, uint32_t t,
+                                                 const uint32_t (&ci)[4])
 {
   const uint32_t v0 = __ldcg(V + ci[0]);
-  if ((v0 & ~kTimeMask) != tag || (v0 & kTimeMask) >= t) return false;
+  if ((v0 & ~vmask) != tag || (v0 & vmask) >= t) return false;
   uint32_t v[3];
 #pragma unroll
   for (int j = 0; j < 3; j++) v[j] = __ldcg(V + ci[j + 1]);
   bool ok = true;
 #pragma unroll
-  for (int j = 0; j < 3; j++) ok &= (v[j] & ~kTimeMask) == tag && (v[j] & kTimeMask) < t;
+  for (int j = 0; j < 3; j++) ok &= (v[j] & ~vmask) == tag && (v[j] & vmask) < t;
   return ok;
 }
 __device__ __forceinline__ void bf_insert(uint32_t* __restrict__ bf, const uint32_t (&bi)[4])
@@ -334,6 +338,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   c.nwarps = (gridDim.x * blockDim.x) >> 5;
   c.cum = cum_sh + (threadIdx.x >> 5);                   // equal shares (below) until speeds have been measured
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t tb = p.time_bits, vmask = (1u << tb) - 1u, maxtag = (1u << (32u - tb)) - 1u;
   unsigned long long ops = 0;
   if (threadIdx.x == 0) { cal_ns = 0; cal_steps = 0; }
   if (threadIdx.x < 15) diag[threadIdx.x] = 0;
@@ -358,10 +363,10 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       S.ord++;
       S.publish = p.weighted && (S.ord & 63u) == 4u; // after 4 streams, then every 64: publish the CTA's speed ...
       S.recal = p.weighted && (S.ord & 63u) == 5u;   // ... and the next stream starts with re-weighted shares
-      if (S.epoch + lmax + 1 > kMaxEpoch) { S.phase = PH_CLEAR; return; } // the tags of this stream would wrap
+      if (S.epoch + lmax + 1 > maxtag - 1u) { S.phase = PH_CLEAR; return; } // the tags of this stream would wrap
       S.phase = PH_L0;
       S.epoch++;
-      S.tag = (63u - S.epoch) << kTimeBits;
+      S.tag = (maxtag - S.epoch) << tb;
       return;
     }
   };
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
                       const uint32_t t = s * 32u + c.lane;
                       bool q = false;
                       if (valid && thr > 0u) {
-                        q = (cbf ? level_test(V, cbf, tag, t, 1u, ci) : level_test_early(V, tag, t, ci)) && thr > 1u;
+                        q = (cbf ? level_test(V, cbf, tag, vmask, t, 1u, ci) : level_test_early(V, tag, vmask, t, ci)) && thr > 1u;
                         if (q && thr == 2u) bf_insert(bf, bi); // count after the update reaches thr
                       }
                       surv_append(lst, cnt, q, ci, bi, t | (thr << kTimeBits), c.lane);
@@ -545,8 +550,8 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
               uint32_t mx = 0;
 #pragma unroll
               for (int j = 0; j < 4; j++) {
-                reached &= (v[e][j] & ~kTimeMask) == tag;
-                mx = max(mx, v[e][j] & kTimeMask);
+                reached &= (v[e][j] & ~vmask) == tag;
+                mx = max(mx, v[e][j] & vmask);
                 if (cbf && live[e] && v[e][j] == (tag | t)) cbf[pw[e][j] & 0xFFFFFFu] = (uint8_t)L; // moved counter j to level L
               }
               q[e] = reached && t > mx;
@@ -558,7 +563,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
 #pragma unroll
             for (int e = 0; e < 2; e++) {
               const uint32_t t = meta[e] & kTimeMask;
-              q[e] = live[e] && (v0[e] & ~kTimeMask) == tag && (v0[e] & kTimeMask) < t;
+              q[e] = live[e] && (v0[e] & ~vmask) == tag && (v0[e] & vmask) < t;
             }
             uint32_t v[2][3];
 #pragma unroll
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
             for (int e = 0; e < 2; e++) {
               const uint32_t t = meta[e] & kTimeMask;
 #pragma unroll
-              for (int j = 0; j < 3; j++) q[e] = q[e] && (v[e][j] & ~kTimeMask) == tag && (v[e][j] & kTimeMask) < t;
+              for (int j = 0; j < 3; j++) q[e] = q[e] && (v[e][j] & ~vmask) == tag && (v[e][j] & vmask) < t;
             }
           }
 #pragma unroll
@@ -618,24 +623,24 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         // next round of this slot (same decision in every CTA)
         switch (phase) {
         case PH_CLEAR:
-          S.epoch = 1; S.tag = (63u - 1u) << kTimeBits; S.phase = PH_L0;
+          S.epoch = 1; S.tag = (maxtag - 1u) << tb; S.phase = PH_L0;
           break;
         case PH_L0:
           if (S.lread >= 1u && p.fused) { // T_1 carries S.tag; the round that reads it writes T_2 under the next tag
-            S.phase = PH_READ; S.L = 1; S.epoch++; S.tag_next = (63u - S.epoch) << kTimeBits;
+            S.phase = PH_READ; S.L = 1; S.epoch++; S.tag_next = (maxtag - S.epoch) << tb;
           } else if (S.lread >= 1u) S.phase = PH_L1;
           else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
           break;
         case PH_L1:
-          if (S.lread >= 2u) { S.phase = PH_WRITE; S.L = 2; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
+          if (S.lread >= 2u) { S.phase = PH_WRITE; S.L = 2; S.epoch++; S.tag = (maxtag - S.epoch) << tb; }
           else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
           break;
         case PH_WRITE:
           S.phase = PH_READ;
           break;
         default: // PH_READ
-          if (L < S.lread && p.fused) { S.L = L + 1u; S.tag = S.tag_next; S.epoch++; S.tag_next = (63u - S.epoch) << kTimeBits; }
-          else if (L < S.lread) { S.phase = PH_WRITE; S.L = L + 1u; S.epoch++; S.tag = (63u - S.epoch) << kTimeBits; }
+          if (L < S.lread && p.fused) { S.L = L + 1u; S.tag = S.tag_next; S.epoch++; S.tag_next = (maxtag - S.epoch) << tb; }
+          else if (L < S.lread) { S.phase = PH_WRITE; S.L = L + 1u; S.epoch++; S.tag = (maxtag - S.epoch) << tb; }
           else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
           break;
         }
