@@ -41,6 +41,10 @@ struct gp_ctx {
   uint8_t* bf_host_user = nullptr;                    // gp_build_output_host: pinned destination of the filter payloads
   uint32_t* bf_host_dev = nullptr;                    // ... as the device sees it
   bool bf_streamed = false;                           // the last build wrote the payloads there itself
+  std::vector<uint32_t> h_pre, h_maxthr;              // steps before every entry per k; largest kmer_threshold per batch
+  std::vector<uint64_t> h_batch_entry_off;
+  std::vector<uint4> h_stream_tab;
+  DevBuf d_stream_tab;
   std::vector<uint32_t> h_empty_streams;              // (batch * nk + ki) of streams without a k-mer
   bool edit_ev_valid = false;                         // edit_ev[] were recorded by the last polish
   int l2_persist_max = 0, l2_window_max = 0;          // persisting-L2 capacity and largest access-policy window (bytes)
@@ -217,7 +221,7 @@ void gp_ctx_destroy(gp_ctx* ctx)
                      &ctx->d_next, &ctx->d_counters, &ctx->d_step_pre, &ctx->d_batch_max_thr, &ctx->d_V, &ctx->d_alive, &ctx->d_anchor, &ctx->d_entry_rel, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
                      &ctx->d_cap_off, &ctx->d_cur_len, &ctx->d_which, &ctx->d_dropped, &ctx->d_nodes, &ctx->d_node_off,
                      &ctx->d_contig_batch, &ctx->d_order, &ctx->d_pnext, &ctx->d_pcounters, &ctx->d_error, &ctx->d_out,
-                     &ctx->d_out_off, &ctx->d_batch_order, &ctx->d_batch_done, &ctx->d_order_pipe };
+                     &ctx->d_out_off, &ctx->d_batch_order, &ctx->d_batch_done, &ctx->d_order_pipe, &ctx->d_stream_tab };
   for (auto* b : bufs) b->release();
   if (ctx->l2_window_set) { cudaCtxResetPersistingL2Cache(); cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -397,6 +401,9 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     for (uint32_t ki = 0; ki < c.nk; ki++)
       ctx->anchor_stride = std::max<uint64_t>(ctx->anchor_stride, uint64_t(pre[size_t(ki) * (n_entries + 1) + n_entries]) + 1);
     ctx->levels_ok = ok;
+    ctx->h_pre = pre;
+    ctx->h_maxthr = maxthr;
+    ctx->h_batch_entry_off.assign(batch_entry_off, batch_entry_off + n_batches + 1);
     ctx->n_entries = uint32_t(n_entries);
     ctx->alive_words = uint32_t(max_steps + 1);
     ctx->level_time_bits = 16; // occurrence times of the longest stream must fit
@@ -495,11 +502,29 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
 
 // level-synchronous build of every wave on stream s; batch_order / batch_done / ctas_per_sm are
 // gp_pipeline_run's (NULL, NULL, 0 otherwise)
-static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batch_order, uint32_t* batch_done,
+static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, uint32_t* batch_done,
                                int ctas_per_sm, uint32_t* launches_out)
 {
   const gp_config& c = ctx->cfg;
   uint32_t launches = 0;
+  // per stream, in launch order: steps, largest thr, batch (the kernel reads it one stream ahead)
+  {
+    const size_t total = size_t(ctx->n_batches) * c.nk;
+    ctx->h_stream_tab.resize(std::max<size_t>(total, 1));
+    const size_t ne1 = size_t(ctx->n_entries) + 1;
+    size_t w = 0;
+    for (size_t wv = 0; wv < ctx->wave_first.size(); wv++)
+      for (uint32_t st = 0; st < ctx->wave_count[wv] * c.nk; st++, w++) {
+        const uint32_t lb = st / c.nk, ki = st - lb * c.nk;
+        const uint32_t b = build_order ? ctx->h_batch_order[ctx->wave_first[wv] + lb] : ctx->wave_first[wv] + lb;
+        const uint32_t* pk = ctx->h_pre.data() + size_t(ki) * ne1;
+        const uint32_t steps = pk[ctx->h_batch_entry_off[b + 1]] - pk[ctx->h_batch_entry_off[b]];
+        ctx->h_stream_tab[w] = make_uint4(steps, ctx->h_maxthr[b] - 2u + ki, b, 0u);
+      }
+    GP_CUDA(ctx, ctx->d_stream_tab.ensure(ctx->h_stream_tab.size() * sizeof(uint4)));
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_stream_tab.p, ctx->h_stream_tab.data(), ctx->h_stream_tab.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  }
+  size_t tab_off = 0;
   for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
     // level-synchronous: all SMs on one stream at a time, timestamps resident in L2
     gp::LevelParams p;
@@ -528,6 +553,8 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     p.n_entries = ctx->n_entries;
     p.n_streams = ctx->wave_count[wv] * c.nk;
     p.first_batch = ctx->wave_first[wv];
+    p.stream_tab = ctx->d_stream_tab.as<uint4>() + tab_off;
+    tab_off += p.n_streams;
     p.nk = c.nk;
     for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
     if (c.keep_counters) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
@@ -540,7 +567,6 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, const uint32_t* batc
     }
     while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
-    p.batch_order = batch_order;
     p.batch_done = batch_done;
     p.n_batches_total = ctx->n_batches;
     p.bf_host = ctx->bf_host_dev;
@@ -597,7 +623,7 @@ int gp_build_run(gp_ctx* ctx)
   const int algo = ctx->build_algo_resolved;
   if (algo == 2) {
     // level-synchronous: all SMs on one stream at a time, timestamps resident in L2
-    if (int rc = build_launch_levels(ctx, s, nullptr, nullptr, 0, &launches)) return rc;
+    if (int rc = build_launch_levels(ctx, s, false, nullptr, 0, &launches)) return rc;
   }
   if (algo == 1) ctx->bf_streamed = false;
   for (size_t wv = 0; algo == 1 && wv < ctx->wave_first.size(); wv++) {
@@ -1008,7 +1034,7 @@ int gp_pipeline_run(gp_ctx* ctx)
   // it becomes resident next to the running build, takes the contigs in build order and waits for each one's
   // filters.  No event may sit between the two launches; their durations come from device timers.
   uint32_t launches = 0;
-  if (int rc = build_launch_levels(ctx, s, ctx->d_batch_order.as<uint32_t>(), ctx->d_batch_done.as<uint32_t>(), 2, &launches)) return rc;
+  if (int rc = build_launch_levels(ctx, s, true, ctx->d_batch_done.as<uint32_t>(), 2, &launches)) return rc;
   if (int rc = polish_edit(ctx, s, ctx->d_order_pipe.as<uint32_t>(), ctx->d_batch_done.as<uint32_t>(), true)) return rc;
   if (int rc = prep_launch(ctx, c.prep_mode, c.prep_k, c.to_upper)) return rc;
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));

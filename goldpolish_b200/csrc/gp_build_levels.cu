@@ -268,12 +268,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
   return t;
 }
 
-// wave-local batch index -> batch (the pipeline builds the batches with the longest contigs first)
-__device__ __forceinline__ uint32_t stream_batch(const LevelParams& p, uint32_t lb)
-{
-  return p.batch_order ? p.batch_order[p.first_batch + lb] : p.first_batch + lb;
-}
-
 // A stream's filter is final (its last barrier has drained on this CTA): stream it to the caller's pinned
 // host buffer if there is one -- every CTA copies its slice straight over PCIe, under the following rounds, so
 // that no bulk D2H is left at the end -- and tell the edit kernel (gp_pipeline_run).
@@ -308,7 +302,7 @@ enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_L1 = 2, PH_WRITE = 3, PH_READ = 4 
 
 struct SlotState {      // uniform over the grid; written by thread 0 of each CTA between rounds
   uint32_t sid;         // wave-local stream, >= n_streams when the slot has run dry
-  uint32_t phase, L, lread, epoch, tag, tag_next, n_steps;
+  uint32_t phase, L, lread, epoch, tag, tag_next, n_steps, batch;
   uint32_t ord, publish, recal; // streams begun in this slot; this stream's round 0 publishes / re-reads the SM speeds
   uint32_t done_b1, done_ki; // batch + 1 and k index of the slot's previous stream while its last barrier drains (0: none)
   unsigned long long target; // barrier count that must be reached before the slot's next round
@@ -345,18 +339,24 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   if (threadIdx.x <= uint32_t(kLevelWarps)) cum_sh[threadIdx.x] = (uint64_t(blockIdx.x * kLevelWarps + threadIdx.x) << 32) / c.nwarps;
 
   // stream -> (n_steps, lread); called by thread 0 only
+  // stream_tab[sid] = {steps, largest thr, batch} in launch order, fetched one stream ahead (thread 0's registers)
+  uint4 nx_info = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0 && p.n_streams) nx_info = __ldg(p.stream_tab);
   auto begin_stream = [&](SlotState& S) {
     for (;;) {
       S.sid = next_sid++;
       if (S.sid >= p.n_streams) return;
-      const uint32_t lb = S.sid / p.nk, ki = S.sid - lb * p.nk, batch = stream_batch(p, lb);
-      const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
-      S.n_steps = pre[p.batch_entry_off[batch + 1]] - pre[p.batch_entry_off[batch]];
+      const uint4 info = nx_info;
+      if (S.sid + 1u < p.n_streams) nx_info = __ldg(p.stream_tab + S.sid + 1u);
+      const uint32_t ki = S.sid % p.nk, batch = info.z;
+      S.n_steps = info.x;
+      S.batch = batch;
       if (S.n_steps == 0) { // nothing to insert: the (zeroed) filter is final
         if (p.batch_done && blockIdx.x == 0) { atomicAdd(p.batch_done + batch, 1u); atomicAdd(p.batch_done + p.n_batches_total, 1u); }
         continue;
       }
-      const uint32_t lmax = p.batch_max_thr[batch] - 2u + ki; // largest thr of the stream
+      const uint32_t lmax = info.y; // largest thr of the stream (kmer_threshold - 2 + k index, utils.cpp:108,121)
+      (void)ki;
       // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
       // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
       S.lread = p.cbf_pool ? lmax : lmax - 1u;
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
       }
       if (S.done_b1) filter_final(p, S.done_b1 - 1u, S.done_ki, gtid, gthreads); // the slot's previous stream is complete everywhere
-      const uint32_t lb = sid / p.nk, ki = sid - lb * p.nk, batch = stream_batch(p, lb);
+      const uint32_t ki = sid % p.nk, batch = S.batch;
       // two timestamp arrays per slot: T_L lives in array (L + 1) & 1 (the second one is used by the fused rounds only)
       uint32_t* __restrict__ V0 = p.V + uint64_t(sl) * (p.fused ? 2u : 1u) * kCbfCounters;
       uint32_t* __restrict__ V = V0 + ((p.fused && phase == PH_READ) ? ((L + 1u) & 1u) * kCbfCounters : 0u);

@@ -35,7 +35,7 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   const gp_read_entry* entries;
   const uint32_t* step_pre;       // [nk][n_entries + 1]: steps before entry e, for every k index
   const uint32_t* batch_max_thr;  // per batch: largest kmer_threshold among its entries
-  const uint32_t* batch_order;    // optional: build order -> batch (NULL = identity)
+  const uint4* stream_tab;        // per stream of the launch, in launch order: {steps, largest thr, batch, -}
   uint32_t* batch_done;           // optional: per batch, streams whose filter is final; [n_batches_total] counts all (gp_pipeline_run)
   uint32_t n_batches_total;
   const uint16_t* anchor;         // [nk][anchor_stride]: global step of k index -> entry, relative to its batch
