@@ -46,6 +46,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_FD = None
+
+
+def own_stdout():
+    """Keep stdout for the ONE JSON line: anything a library prints there (NCCL announces its version on stdout)
+    goes to stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def make_dataset(rank: int, genome_len: int):
     import sim
     return sim.simulate(genome_len=genome_len, coverage=WORKLOAD["coverage"], seed=20250607 + 1000003 * rank)
@@ -254,7 +275,7 @@ def reference_arm(args, rank, world):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     finally:
         shutil.rmtree(work, ignore_errors=True)
 
@@ -466,7 +487,7 @@ def ours(args, rank, world, local_rank):
             "stats": {k: st2[k] for k in ("kmer_ops", "serial_kmers", "triggers", "edits", "masked", "rollbacks",
                                           "build_ms", "polish_ms", "pack_ms", "build_kernel_ms", "edit_kernel_ms")},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.barrier()
@@ -494,6 +515,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3 and args.impl == "ours":
         log("bench.py: note: timing rules ask for >= 3 warm-up steps")
+    own_stdout()
     if args.impl == "reference":
         reference_arm(args, rank, world)
     else:
