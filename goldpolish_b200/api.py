@@ -287,7 +287,7 @@ class Context:
         """Level-synchronous build kernel, CTA 0: {round kind: (barrier wait ms, work ms, rounds)}."""
         out = (C.c_uint64 * 16)()
         self._ck(self._l.gp_build_round_times(self._h, out))
-        names = ("clear", "level0_write", "level1_read", "list_write", "list_read")
+        names = ("clear", "round0", "list_round")
         r = {n: (out[3 * i] / 1e6, out[3 * i + 1] / 1e6, int(out[3 * i + 2])) for i, n in enumerate(names)}
         r["list_entries"] = int(out[15])
         return r

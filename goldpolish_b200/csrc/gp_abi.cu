@@ -73,7 +73,7 @@ struct gp_ctx {
   // level-synchronous build
   DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel;
   uint64_t anchor_stride = 0;
-  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_fused = 1, level_time_bits = 26;
+  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_time_bits = 26;
   bool levels_ok = false; // every stream fits the 26-bit occurrence clock
   int build_algo = 0;     // 0 = auto, 1 = warp per stream, 2 = level-synchronous
   int build_algo_resolved = 1;
@@ -411,13 +411,11 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
     GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
     // level-synchronous kernel: streams in flight (each with two timestamp arrays and its survivor lists)
-    // and whether "read level L" and "write level L+1" are one round.  Default = one stream, fused rounds:
-    // 80 MiB of timestamps sit in L2; two streams with fused rounds (160 MiB) do not, and measured slower
+    // Default = one stream: its 80 MiB of timestamps sit in (the persisting part of) L2; two streams (160 MiB) do not,
+    // and measured slower
     ctx->level_slots = 1;
-    ctx->level_fused = 1;
     if (const char* f = std::getenv("GP_LEVEL_SLOTS")) ctx->level_slots = uint32_t(std::atoi(f));
     ctx->level_slots = std::max(1u, std::min(ctx->level_slots, uint32_t(gp::levels_max_slots())));
-    if (const char* f = std::getenv("GP_LEVEL_FUSED")) ctx->level_fused = std::atoi(f) ? 1u : 0u;
     GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * 2 * ctx->level_slots));
     // per slot: warp-private survivor lists, 5 words per entry (a warp's region is its share of
     // the steps, rounded up, x 32); then the barrier counters
@@ -545,7 +543,6 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
     p.n_slots = ctx->level_slots;
     p.time_bits = ctx->level_time_bits;
     if (const char* f = std::getenv("GP_LEVEL_REPORT_CTA")) p.report_cta = uint32_t(std::atoi(f));
-    p.fused = ctx->level_fused;
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
     p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
     p.counters = ctx->d_counters.as<unsigned long long>();
@@ -574,7 +571,7 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
     // (79 of 126 MiB on B200), so that the survivor lists, the sequence and the filters streaming through do not
     // evict them (+6 % k-mer ops/s).  Only when the window can cover them (one stream in flight).
     {
-      const size_t vbytes = gp::kCbfCounters * 4 * (ctx->level_fused ? 2 : 1) * ctx->level_slots; // (arrays are packed slot after slot)
+      const size_t vbytes = gp::kCbfCounters * 4 * 2 * ctx->level_slots;
       const char* e = std::getenv("GP_L2_PERSIST");
       const bool want = !(e && e[0] == '0') && ctx->l2_persist_max > 0 && vbytes <= size_t(ctx->l2_window_max);
       cudaStreamAttrValue av;

@@ -17,6 +17,9 @@
 // carry a 6-bit epoch tag (newer epochs compare smaller, so atomicMin overwrites stale entries,
 // and readers treat a stale tag as "never"), so nothing is cleared between levels or streams.
 //
+// "Read level L" and "write level L+1" are ONE round over two alternating timestamp arrays (T_L lives in array
+// (L + 1) & 1), and round 0 already puts every occurrence on its warp's list: 1 + max thr - 1 rounds per stream.
+//
 // Rounds of one stream are separated by grid-wide barriers.  To keep the SMs busy while a barrier
 // drains, the grid works on `n_slots` streams at a time (each with its own timestamp array and
 // survivor lists; 2 x 40 MiB still sits in the 126 MB L2): a CTA runs one round of slot 0,
@@ -208,39 +211,6 @@ __device__ __forceinline__ void red_or(uint32_t* p, uint32_t v)
   asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// the level test: all four counters carry the current tag and a time before t
-__device__ __forceinline__ bool level_test(const uint32_t* __restrict__ V, uint8_t* __restrict__ cbf, uint32_t tag, uint32_t vmask,
-                                           uint32_t t, uint32_t L, const uint32_t (&ci)[4])
-{
-  uint32_t v[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) v[j] = __ldcg(V + ci[j]);
-  bool reached = true;
-  uint32_t mx = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    reached &= (v[j] & ~vmask) == tag;
-    mx = max(mx, v[j] & vmask);
-    if (cbf && v[j] == (tag | t)) cbf[ci[j]] = (uint8_t)L; // this occurrence moved counter j to level L
-  }
-  return reached && t > mx;
-}
-// the same test for occurrences that mostly fail it (level 1 from the sequence: most k-mers of
-// noisy reads are seen once, and such an occurrence is the first toucher of its own counters):
-// look at one counter, fetch the other three only if that one was reached before t
-__device__ __forceinline__ bool level_test_early(const uint32_t* __restrict__ V, uint32_t tag, uint32_t vmask, uint32_t t,
-                                                 const uint32_t (&ci)[4])
-{
-  const uint32_t v0 = __ldcg(V + ci[0]);
-  if ((v0 & ~vmask) != tag || (v0 & vmask) >= t) return false;
-  uint32_t v[3];
-#pragma unroll
-  for (int j = 0; j < 3; j++) v[j] = __ldcg(V + ci[j + 1]);
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < 3; j++) ok &= (v[j] & ~vmask) == tag && (v[j] & vmask) < t;
-  return ok;
-}
 __device__ __forceinline__ void bf_insert(uint32_t* __restrict__ bf, const uint32_t (&bi)[4])
 {
   uint32_t w[4]; // the filter is 512 KiB and mostly hit by repeats of the same k-mers: look first
@@ -298,7 +268,7 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
   return t;
 }
 
-enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_L1 = 2, PH_WRITE = 3, PH_READ = 4 };
+enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_READ = 2 };
 
 struct SlotState {      // uniform over the grid; written by thread 0 of each CTA between rounds
   uint32_t sid;         // wave-local stream, >= n_streams when the slot has run dry
@@ -333,7 +303,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   c.cum = cum_sh + (threadIdx.x >> 5);                   // equal shares (below) until speeds have been measured
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   const uint32_t tb = p.time_bits, vmask = (1u << tb) - 1u, maxtag = (1u << (32u - tb)) - 1u;
-  unsigned long long ops = 0;
+  unsigned long long ops = 0, list_seen = 0;
   if (threadIdx.x == 0) { cal_ns = 0; cal_steps = 0; }
   if (threadIdx.x < 15) diag[threadIdx.x] = 0;
   if (threadIdx.x <= uint32_t(kLevelWarps)) cum_sh[threadIdx.x] = (uint64_t(blockIdx.x * kLevelWarps + threadIdx.x) << 32) / c.nwarps;
@@ -448,80 +418,38 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       }
       if (S.done_b1) filter_final(p, S.done_b1 - 1u, S.done_ki, gtid, gthreads); // the slot's previous stream is complete everywhere
       const uint32_t ki = sid % p.nk, batch = S.batch;
-      // two timestamp arrays per slot: T_L lives in array (L + 1) & 1 (the second one is used by the fused rounds only)
-      uint32_t* __restrict__ V0 = p.V + uint64_t(sl) * (p.fused ? 2u : 1u) * kCbfCounters;
-      uint32_t* __restrict__ V = V0 + ((p.fused && phase == PH_READ) ? ((L + 1u) & 1u) * kCbfCounters : 0u);
-      uint32_t* __restrict__ Vn = V0 + (L & 1u) * kCbfCounters; // T_{L+1} (fused rounds)
+      // two timestamp arrays per slot: T_L lives in array (L + 1) & 1
+      uint32_t* __restrict__ V0 = p.V + uint64_t(sl) * 2u * kCbfCounters;
+      uint32_t* __restrict__ V = V0 + (phase == PH_READ ? ((L + 1u) & 1u) * kCbfCounters : 0u);
+      uint32_t* __restrict__ Vn = V0 + (L & 1u) * kCbfCounters; // where T_{L+1} goes
       const uint32_t tag_next = S.tag_next;
       uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
       uint8_t* __restrict__ cbf = p.cbf_pool ? p.cbf_pool + uint64_t(sid) * kCbfCounters : nullptr;
       if (phase == PH_CLEAR) {
-        for (uint64_t i = gtid; i < kCbfCounters * (p.fused ? 2u : 1u); i += gthreads) V0[i] = 0xFFFFFFFFu;
-      } else if (phase == PH_L0 || phase == PH_L1) {
+        for (uint64_t i = gtid; i < kCbfCounters * 2u; i += gthreads) V0[i] = 0xFFFFFFFFu;
+      } else if (phase == PH_L0) {
+        // ---- round 0: every occurrence writes its time into T_1 (the first toucher of a counter wins) and goes
+        // to the warp's list, so that level 1 is an ordinary list round (no second hashing pass) ----
         const StreamConsts sc = stream_consts(p.k[ki]);
-        if (phase == PH_L0 && p.fused) {
-          // ---- level 0 -> 1, fused form: every occurrence writes its time AND goes to the warp's list, so that
-          // level 1 is an ordinary list round (no second hashing pass) ----
-          uint32_t cnt = 0;
-          for_runs(p, c, batch, ki, sc, n_steps,
-                    [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
-                      const uint32_t t = s * 32u + c.lane;
-                      const bool q = valid && thr > 0u;
-                      if (q) {
+        uint32_t cnt = 0;
+        for_runs(p, c, batch, ki, sc, n_steps,
+                 [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+                   const uint32_t t = s * 32u + c.lane;
+                   const bool q = valid && thr > 0u;
+                   if (q) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) red_min(V + ci[j], tag | t);
-                        if (thr == 1u) bf_insert(bf, bi);
-                      }
-                      if (valid) ops++;
-                      surv_append(lst, cnt, q && thr > 1u, ci, bi, t | (thr << kTimeBits), c.lane);
-                    });
-          if (c.lane == 0) warp_cnt[sl][wib] = cnt;
-        } else if (phase == PH_L0) {
-          // ---- level 0 -> 1: every occurrence writes its time (the first toucher of a counter wins) ----
-          for_runs(p, c, batch, ki, sc, n_steps,
-                    [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
-                      const uint32_t t = s * 32u + c.lane;
-                      if (valid && thr > 0u) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) red_min(V + ci[j], tag | t);
-                        if (thr == 1u) bf_insert(bf, bi);
-                      }
-                      if (valid) ops++;
-                    });
-        } else {
-          // ---- level 1 read, from the sequence: survivors go to the warp's list ----
-          uint32_t cnt = 0;
-          for_runs(p, c, batch, ki, sc, n_steps,
-                    [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
-                      const uint32_t t = s * 32u + c.lane;
-                      bool q = false;
-                      if (valid && thr > 0u) {
-                        q = (cbf ? level_test(V, cbf, tag, vmask, t, 1u, ci) : level_test_early(V, tag, vmask, t, ci)) && thr > 1u;
-                        if (q && thr == 2u) bf_insert(bf, bi); // count after the update reaches thr
-                      }
-                      surv_append(lst, cnt, q, ci, bi, t | (thr << kTimeBits), c.lane);
-                    });
-          if (c.lane == 0) warp_cnt[sl][wib] = cnt;
-        }
-      } else if (phase == PH_WRITE) {
-        // ---- write: survivors of level L-1 race for T_L of their counters ----
-        const uint32_t cnt = warp_cnt[sl][wib];
-        if (c.lane == 0 && cnt) atomicAdd(p.counters + 17, (unsigned long long)cnt);
-        for (uint32_t i = c.lane; i < cnt; i += 32) {
-          const uint32_t t = __ldcg(lst.w[4] + i) & kTimeMask;
-          // survivors are mostly the many occurrences of the same true k-mers: look before the
-          // atomic, an entry that already holds an earlier time of this round cannot be lowered
-          uint32_t x[4], v[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) x[j] = __ldcg(lst.w[j] + i) & 0xFFFFFFu;
-#pragma unroll
-          for (int j = 0; j < 4; j++) v[j] = __ldcg(V + x[j]);
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (v[j] > (tag | t)) red_min(V + x[j], tag | t);
-        }
+                     for (int j = 0; j < 4; j++) red_min(V + ci[j], tag | t);
+                     if (thr == 1u) bf_insert(bf, bi);
+                   }
+                   if (valid) ops++;
+                   surv_append(lst, cnt, q && thr > 1u, ci, bi, t | (thr << kTimeBits), c.lane);
+                 });
+        if (c.lane == 0) warp_cnt[sl][wib] = cnt;
       } else {
-        // ---- read: who sees all four counters at >= L before its own time?  compact in place ----
+        // ---- list round: who sees all four counters at >= L before its own time?  Survivors with thr = L + 1 enter
+        // the filter and, unless it is the stream's last round, race for T_{L+1} right away in the other array; the
+        // list is compacted in place ----
+        if (c.lane == 0) list_seen += list_cnt; // (diagnostic, flushed once at the end)
         // two entries per lane and iteration: their list words, then their timestamps, are all in flight together
         const uint32_t cnt = list_cnt;
         uint32_t kept = 0;
@@ -587,7 +515,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
               for (int j = 0; j < 4; j++) unpack_index(pw[e][j], ci, bi[j]);
               bf_insert(bf, bi);
             }
-            if (q[e] && p.fused && L < lread) { // fused rounds: the survivor races for T_{L+1} right away, in the other array
+            if (q[e] && L < lread) {
 #pragma unroll
               for (int j = 0; j < 4; j++) red_min(Vn + (pw[e][j] & 0xFFFFFFu), tag_next | t);
             }
@@ -625,22 +553,12 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         case PH_CLEAR:
           S.epoch = 1; S.tag = (maxtag - 1u) << tb; S.phase = PH_L0;
           break;
-        case PH_L0:
-          if (S.lread >= 1u && p.fused) { // T_1 carries S.tag; the round that reads it writes T_2 under the next tag
-            S.phase = PH_READ; S.L = 1; S.epoch++; S.tag_next = (maxtag - S.epoch) << tb;
-          } else if (S.lread >= 1u) S.phase = PH_L1;
+        case PH_L0: // T_1 carries S.tag; the round that reads it writes T_2 under the next tag
+          if (S.lread >= 1u) { S.phase = PH_READ; S.L = 1; S.epoch++; S.tag_next = (maxtag - S.epoch) << tb; }
           else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
-          break;
-        case PH_L1:
-          if (S.lread >= 2u) { S.phase = PH_WRITE; S.L = 2; S.epoch++; S.tag = (maxtag - S.epoch) << tb; }
-          else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
-          break;
-        case PH_WRITE:
-          S.phase = PH_READ;
           break;
         default: // PH_READ
-          if (L < S.lread && p.fused) { S.L = L + 1u; S.tag = S.tag_next; S.epoch++; S.tag_next = (maxtag - S.epoch) << tb; }
-          else if (L < S.lread) { S.phase = PH_WRITE; S.L = L + 1u; S.epoch++; S.tag = (maxtag - S.epoch) << tb; }
+          if (L < S.lread) { S.L = L + 1u; S.tag = S.tag_next; S.epoch++; S.tag_next = (maxtag - S.epoch) << tb; }
           else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
           break;
         }
@@ -662,6 +580,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);
   if (c.lane == 0 && ops) atomicAdd(p.counters + 0, ops);
+  if (c.lane == 0 && list_seen) atomicAdd(p.counters + 17, list_seen);
   if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[21] = globaltimer_ns();
   if (blockIdx.x == p.report_cta && threadIdx.x == 0)
     for (int i = 0; i < 15; i++) p.counters[2 + i] += diag[i]; // several waves add up

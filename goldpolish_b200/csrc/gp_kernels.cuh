@@ -53,7 +53,6 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   uint32_t n_slots;               // streams in flight (1..levels_max_slots())
   uint32_t time_bits;             // width of the time field of a timestamp entry (16..26): the longest stream fits
   uint32_t report_cta;            // which CTA fills the round-time diagnostics (GP_LEVEL_REPORT_CTA, default 0)
-  uint32_t fused;                 // 1: two timestamp arrays per slot, "read level L" and "write level L+1" are one round
   uint32_t n_entries;
   uint32_t n_streams;
   uint32_t first_batch;

@@ -192,10 +192,10 @@ int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t reg
                        float* ms);
 
 /* Diagnostic (no reference counterpart): where the time of one CTA of the level-synchronous build
- * kernel went during the last gp_build_run, per kind of round r = 0 clear, 1 level-0 write,
- * 2 level-1 read, 3 list write, 4 list read: out[3r] = ns waiting at the round barrier,
- * out[3r+1] = ns working, out[3r+2] = rounds; out[15] = survivor-list entries visited by all
- * list-write rounds of the launch. */
+ * kernel went during the last gp_build_run, per kind of round r = 0 clear, 1 round 0 (hashing + first
+ * timestamps), 2 list round: out[3r] = ns waiting at the round barrier, out[3r+1] = ns working,
+ * out[3r+2] = rounds; out[15] = survivor-list entries visited by all list rounds of the launch
+ * (out[9..14] unused). */
 int gp_build_round_times(gp_ctx* ctx, uint64_t out[16]);
 
 #ifdef __cplusplus

@@ -25,8 +25,8 @@ for slots in os.environ.get("SLOTS", "1 2").split():
     print(f"slots {slots}: build kernel {st['build_kernel_ms']:.2f} ms, {st['kmer_ops'] / st['build_kernel_ms'] / 1e6:.2f} G ops/s, "
           f"{n_streams} streams, {st['kmer_ops'] / n_streams / 1e3:.0f} k ops/stream")
     le = rt.pop("list_entries")
-    print(f"   list entries visited by write rounds: {le} = {le / st['kmer_ops']:.3f} per k-mer op, "
-          f"{le / max(rt['list_write'][2], 1) / 1e3:.0f} k per round")
+    print(f"   list entries visited by list rounds: {le} = {le / st['kmer_ops']:.3f} per k-mer op, "
+          f"{le / max(rt['list_round'][2], 1) / 1e3:.0f} k per round")
     for k, (w, r, n) in rt.items():
         if n:
             print(f"   {k:13s} rounds {n:6d}  wait {w:8.2f} ms ({1e3 * w / n:6.2f} us/round)  work {r:8.2f} ms ({1e3 * r / n:6.2f} us/round)")

@@ -45,16 +45,12 @@ def test_filters_match_oracle(gp, small, bsize, algo, monkeypatch):
     assert st["build_launches"] > 0
 
 
-@pytest.mark.parametrize("fused", ["0", "1"])
 @pytest.mark.parametrize("slots", ["1", "2", "3"])
 @pytest.mark.parametrize("bsize", [1, 8])
-def test_level_slots_match_oracle(gp, small, bsize, slots, fused, monkeypatch):
-    """The level-synchronous kernel with 1, 2 or 3 streams in flight (split-phase barriers), with separate
-    and with fused read/write rounds; the many small streams of bsize 1 also drive the epoch tags through
-    their wrap (clear round)."""
+def test_level_slots_match_oracle(gp, small, bsize, slots, monkeypatch):
+    """The level-synchronous kernel with 1, 2 or 3 streams in flight (split-phase barriers)."""
     monkeypatch.setenv("GP_BUILD_KERNEL", "l")
     monkeypatch.setenv("GP_LEVEL_SLOTS", slots)
-    monkeypatch.setenv("GP_LEVEL_FUSED", fused)
     d, ctx = small
     pl = plan(d, bsize=bsize)
     bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
