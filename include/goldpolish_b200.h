@@ -171,11 +171,12 @@ int gp_prep(gp_ctx* ctx, uint32_t n_records, const char* seqs, const uint64_t* o
 /* gp_build_run + gp_polish_run of the staged work as ONE overlapped pass (needs gp_build_stage and
  * gp_polish_stage first; results are fetched with gp_build_fetch / gp_polish_fetch as usual and are
  * identical to the two separate calls).  The batches holding the longest contigs are built first, and a
- * persistent edit kernel on a second internal stream starts on each contig as soon as the nk filters of
- * its batch are final, next to the build kernel -- the reference's per-batch order "BF server answers,
- * then goldpolish-ntedit runs" (scripts/goldpolish-polish-batch:62-105), kept per batch instead of per run.
- * Falls back to the two calls in sequence when there is nothing to overlap (in-order build kernel,
- * several waves, keep_counters). */
+ * persistent edit kernel -- launched behind the build kernel in the same stream with programmatic stream
+ * serialization, so that it becomes resident beside it -- starts on each contig as soon as the nk filters of
+ * its batch are final: the reference's per-batch order "BF server answers, then goldpolish-ntedit runs"
+ * (scripts/goldpolish-polish-batch:62-105), kept per batch instead of per run.  Falls back to the two calls in
+ * sequence when there is nothing to overlap (in-order build kernel, several waves, keep_counters) or when the
+ * device turned out not to co-schedule the two kernels (the edit kernel's watchdog, checked after the first pass). */
 int gp_pipeline_run(gp_ctx* ctx);
 
 /* ---- host-side rules shared with the reference ------------------------------------ */
@@ -187,7 +188,10 @@ int gp_guard_rejects(uint64_t input_bytes, uint64_t output_bytes);
 /* Random-access roof microbenchmark with the build kernel's access shape: `warps` warps, each
  * doing `iters` rounds of 32x4 dependent byte loads + conditional byte stores into a private
  * region of region_bytes, plus 32x4 atomicOr into a private 512 KiB region.  Returns sector
- * touches per second (8 per k-mer op) in *sectors_per_s. */
+ * touches per second (8 per k-mer op) in *sectors_per_s.  Environment GP_ROOF_MODE selects other shapes:
+ * 1 loads only, 2 loads + counter stores (HBM, private regions); 3 alternating rounds of 4 atomicMin / 4 loads,
+ * 4 atomicMin only, 5 loads only over ONE shared 40 MiB array in L2 (the level-synchronous kernel's shape;
+ * 4 touches per iteration are counted). */
 int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t region_bytes, double* sectors_per_s,
                        float* ms);
 
