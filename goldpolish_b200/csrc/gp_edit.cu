@@ -1179,7 +1179,10 @@ cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool 
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, edit_kernel, p);
+    if (cudaLaunchKernelEx(&cfg, edit_kernel, p) == cudaSuccess) return cudaSuccess;
+    cudaGetLastError(); // no programmatic launch on this driver: an ordinary launch runs after the build (correct, no overlap)
+    edit_kernel<<<grid, kAlongsideWarps * 32, 0, s>>>(p);
+    return cudaGetLastError();
   }
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edit_kernel, kEditWarps * 32, 0);
