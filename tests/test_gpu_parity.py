@@ -152,6 +152,50 @@ def test_filters_streamed_to_pinned_host_memory(gp, pipeline):
             ctx.build_output(np.zeros(want.shape, dtype=np.uint8))   # pageable memory is refused
 
 
+@pytest.mark.parametrize("algo", ["l", "s"])
+def test_ragged_reads_and_word_boundaries(gp, algo, monkeypatch):
+    """Hand-made reads around every boundary of the packed layout (k-1, k, k+1, 31..33, 63..65 bases, empty),
+    N and lower-case bases at word edges, a batch of reads that are all shorter than k, an empty batch:
+    filters and counters against the oracle for both build kernels."""
+    from oracle import oracle_lib as ol
+    monkeypatch.setenv("GP_BUILD_KERNEL", algo)
+    rnd = np.random.default_rng(17)
+    def rseq(n, alphabet="ACGT"):
+        return "".join(rnd.choice(list(alphabet), size=n)) if n else ""
+    reads = [rseq(n) for n in (0, 1, 19, 20, 21, 23, 24, 25, 27, 28, 29, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 1000)]
+    reads += [rseq(300, "ACGTacgtN") for _ in range(6)]
+    for pos in (0, 19, 31, 32, 33, 63, 64, 65, 299):                       # one N at a time, at word edges
+        s = list(rseq(300)); s[pos] = "N"; reads.append("".join(s))
+    reads += [rseq(5000) for _ in range(4)]
+    reads += reads[-4:]                                                    # repeats: counters climb past the thresholds
+    reads += reads[-4:]
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    buf = np.frombuffer("".join(reads).encode(), dtype=np.uint8).copy()
+    short = [i for i, r in enumerate(reads) if len(r) < 20]
+    batches = [list(range(len(reads))), short, [], list(range(len(reads) - 12, len(reads))) * 2]
+    thr = [4, 5, 4, 6]
+    entries = np.zeros(sum(len(b) for b in batches), dtype=np.dtype([("read_id", np.uint32), ("kmer_threshold", np.uint32)]))
+    boff = np.zeros(len(batches) + 1, dtype=np.uint64)
+    e = 0
+    for b, ids in enumerate(batches):
+        for i in ids:
+            entries[e] = (i, thr[b]); e += 1
+        boff[b + 1] = e
+    with gp.Context(keep_counters=1) as ctx:
+        ctx.upload_reads(buf, off)
+        bfs = ctx.build_filters(boff, entries)
+        for b, ids in enumerate(batches):
+            fs = ol.FilterSet(KS)
+            for i in ids:
+                fs.add_read(reads[i].encode(), thr[b])
+            for ki in range(4):
+                assert np.array_equal(bfs[b, ki], fs.bfs[ki]), f"filter differs: batch {b} k={KS[ki]}"
+                if b == len(batches) - 1:
+                    assert np.array_equal(ctx.fetch_cbf(b, ki), fs.cbfs[ki]), f"counters differ: batch {b} k={KS[ki]}"
+        assert bfs[0].any() and not bfs[1].any() and not bfs[2].any()
+
+
 def test_large_thresholds_fall_back_to_the_in_order_kernel(gp, small):
     """kmer_threshold values beyond what the level kernel's epoch tags can hold (the reference never produces
     them: T <= 13) are built by the in-order kernel, still bit-exact."""
