@@ -18,7 +18,7 @@
 // and readers treat a stale tag as "never"), so nothing is cleared between levels or streams.
 //
 // "Read level L" and "write level L+1" are ONE round over two alternating timestamp arrays (T_L lives in array
-// (L + 1) & 1), and round 0 already puts every occurrence on its warp's list: 1 + max thr - 1 rounds per stream.
+// (L + 1) & 1), and round 0 already puts every occurrence on its warp's list: max thr rounds per stream.
 //
 // Rounds of one stream are separated by grid-wide barriers.  To keep the SMs busy while a barrier
 // drains, the grid works on `n_slots` streams at a time (each with its own timestamp array and
