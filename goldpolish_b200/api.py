@@ -40,7 +40,7 @@ class _Stats(C.Structure):
                 ("build_ms", C.c_float), ("polish_ms", C.c_float), ("pack_ms", C.c_float),
                 ("build_kernel_ms", C.c_float), ("edit_kernel_ms", C.c_float),
                 ("build_launches", C.c_uint32), ("polish_launches", C.c_uint32), ("pack_launches", C.c_uint32),
-                ("build_kernel", C.c_uint32), ("build_slots", C.c_uint32)]
+                ("build_kernel", C.c_uint32), ("build_slots", C.c_uint32), ("polish_reruns", C.c_uint32)]
 
 
 READ_ENTRY_DTYPE = np.dtype([("read_id", np.uint32), ("kmer_threshold", np.uint32)])
@@ -51,7 +51,8 @@ EXPORTS = ["gp_default_config", "gp_ctx_create", "gp_ctx_destroy", "gp_last_erro
            "gp_ctx_synchronize", "gp_get_stats", "gp_reads_upload", "gp_build_filters", "gp_build_stage",
            "gp_build_run", "gp_build_fetch", "gp_build_fetch_cbf", "gp_filters_load", "gp_polish",
            "gp_polish_stage", "gp_polish_run", "gp_polish_fetch", "gp_kmer_threshold", "gp_mappings_cap",
-           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep", "gp_build_output_host", "gp_host_alloc", "gp_host_free"]
+           "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep", "gp_build_output_host", "gp_host_alloc", "gp_host_free",
+           "gp_build_cta_times"]
 
 
 def load_library():
@@ -95,6 +96,7 @@ def load_library():
     l.gp_roof_microbench.argtypes = [vp, u32, u32, u64, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     l.gp_build_round_times.argtypes = [vp, C.POINTER(u64)]
     l.gp_pipeline_run.argtypes = [vp]
+    l.gp_build_cta_times.argtypes = [vp, vp, u32, C.POINTER(u32)]
     l.gp_build_output_host.argtypes = [vp, vp]
     l.gp_host_alloc.argtypes = [u64]
     l.gp_host_alloc.restype = vp
@@ -284,13 +286,21 @@ class Context:
 
     # ---- measurement ----
     def build_round_times(self):
-        """Level-synchronous build kernel, CTA 0: {round kind: (barrier wait ms, work ms, rounds)}."""
-        out = (C.c_uint64 * 16)()
+        """Level-synchronous build kernel, CTA 0: {interval kind: (barrier wait ms, work ms, intervals)}."""
+        out = (C.c_uint64 * 32)()
         self._ck(self._l.gp_build_round_times(self._h, out))
-        names = ("clear", "round0", "list_round")
-        r = {n: (out[3 * i] / 1e6, out[3 * i + 1] / 1e6, int(out[3 * i + 2])) for i, n in enumerate(names)}
-        r["list_entries"] = int(out[15])
+        r = {n: (out[3 * i] / 1e6, out[3 * i + 1] / 1e6, int(out[3 * i + 2])) for i, n in enumerate(self.INTERVAL_KINDS)}
+        r["list_entries"] = int(out[31])
         return r
+
+    INTERVAL_KINDS = ("clear", "round0", "level1", "late", "round0+late", "level1+late")
+
+    def build_cta_times(self) -> np.ndarray:
+        """[n_ctas, 6 kinds, 3] ns / counts of every CTA (needs GP_LEVEL_CTA_TIMES=1 during the build)."""
+        out = np.zeros((1024, 32), dtype=np.uint64)
+        n = C.c_uint32()
+        self._ck(self._l.gp_build_cta_times(self._h, _ptr(out), 1024, C.byref(n)))
+        return out[:n.value, :18].reshape(n.value, 6, 3)
 
     def roof_microbench(self, warps: int, iters: int, region_bytes: int = CBF_BYTES):
         sps, ms = C.c_double(), C.c_float()

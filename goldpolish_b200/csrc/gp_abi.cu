@@ -71,7 +71,8 @@ struct gp_ctx {
   std::vector<uint32_t> wave_first, wave_count, wave_order_off;
   DevBuf d_batch_entry_off, d_entries, d_bf_pool, d_cbf_pool, d_stream_order, d_next, d_counters;
   // level-synchronous build
-  DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel;
+  DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel, d_cta_times;
+  uint32_t level_grid = 0; // CTAs of the last level-synchronous launch
   uint64_t anchor_stride = 0;
   uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_time_bits = 26;
   bool levels_ok = false; // every stream fits the 26-bit occurrence clock
@@ -221,7 +222,7 @@ void gp_ctx_destroy(gp_ctx* ctx)
                      &ctx->d_next, &ctx->d_counters, &ctx->d_step_pre, &ctx->d_batch_max_thr, &ctx->d_V, &ctx->d_alive, &ctx->d_anchor, &ctx->d_entry_rel, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
                      &ctx->d_cap_off, &ctx->d_cur_len, &ctx->d_which, &ctx->d_dropped, &ctx->d_nodes, &ctx->d_node_off,
                      &ctx->d_contig_batch, &ctx->d_order, &ctx->d_pnext, &ctx->d_pcounters, &ctx->d_error, &ctx->d_out,
-                     &ctx->d_out_off, &ctx->d_batch_order, &ctx->d_batch_done, &ctx->d_order_pipe, &ctx->d_stream_tab };
+                     &ctx->d_out_off, &ctx->d_batch_order, &ctx->d_batch_done, &ctx->d_order_pipe, &ctx->d_stream_tab, &ctx->d_cta_times };
   for (auto* b : bufs) b->release();
   if (ctx->l2_window_set) { cudaCtxResetPersistingL2Cache(); cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -387,7 +388,7 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
       if (batch_entry_off[b + 1] - batch_entry_off[b] > 0xFFFFull) ok = false; // step -> entry anchors are 16 bits
       for (uint64_t e = batch_entry_off[b]; e < batch_entry_off[b + 1]; e++) {
         maxthr[b] = std::max(maxthr[b], entries[e].kmer_threshold);
-        if (entries[e].kmer_threshold > 48) ok = false; // a stream's levels must fit the 6-bit epoch tags (the reference caps T at 13)
+        if (entries[e].kmer_threshold > 24) ok = false; // the levels of two streams in flight must fit the 6-bit epoch tags (the reference caps T at 13)
         entry_rel[e] = uint16_t(e - batch_entry_off[b]);
       }
     }
@@ -410,17 +411,16 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     while (ctx->level_time_bits < 26 && (max_steps * 32) >> ctx->level_time_bits) ctx->level_time_bits++;
     GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
     GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
-    // level-synchronous kernel: streams in flight (each with two timestamp arrays and its survivor lists)
-    // Default = one stream: its 80 MiB of timestamps sit in (the persisting part of) L2; two streams (160 MiB) do not,
-    // and measured slower
-    ctx->level_slots = 1;
-    if (const char* f = std::getenv("GP_LEVEL_SLOTS")) ctx->level_slots = uint32_t(std::atoi(f));
-    ctx->level_slots = std::max(1u, std::min(ctx->level_slots, uint32_t(gp::levels_max_slots())));
-    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * 2 * ctx->level_slots));
-    // per slot: warp-private survivor lists, 5 words per entry (a warp's region is its share of
-    // the steps, rounded up, x 32); then the barrier counters
+    // level-synchronous kernel: three timestamp arrays (T_1, and two that alternate for the levels above it) serve two
+    // streams in flight -- the late list rounds of one stream run beside round 0 / the level-1 round of the next
+    // (GP_LEVEL_OVERLAP=0: one stream at a time, same arrays)
+    ctx->level_slots = 2;
+    if (const char* f = std::getenv("GP_LEVEL_OVERLAP")) ctx->level_slots = f[0] == '0' ? 1u : 2u;
+    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * gp::kLevelArrays));
+    // warp-private survivor lists, kLevelSurvWords words per entry (a warp's region is its share of the steps,
+    // rounded up, x 32), one buffer per stream in flight; then the barrier counter
     ctx->surv_cap = uint32_t(size_t(ctx->alive_words) * 32 + size_t(8192) * 9 * 32); // + (runs + 1) slack slots per warp
-    GP_CUDA(ctx, ctx->d_alive.ensure(size_t(ctx->surv_cap) * 5 * ctx->level_slots * 4 + 64 + 8192));
+    GP_CUDA(ctx, ctx->d_alive.ensure(size_t(ctx->surv_cap) * gp::kLevelSurvWords * gp::kLevelListBufs * 4 + 64 + 8192));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_step_pre.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_max_thr.p, maxthr.data(), maxthr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (ok) {
@@ -539,8 +539,10 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
     p.anchor_stride = ctx->anchor_stride;
     p.V = ctx->d_V.as<uint32_t>();
     p.surv = ctx->d_alive.as<uint32_t>();
-    p.bars = reinterpret_cast<unsigned long long*>(ctx->d_alive.as<uint32_t>() + size_t(5) * ctx->surv_cap * ctx->level_slots);
-    p.n_slots = ctx->level_slots;
+    p.bars = reinterpret_cast<unsigned long long*>(ctx->d_alive.as<uint32_t>() + size_t(gp::kLevelSurvWords) * gp::kLevelListBufs * ctx->surv_cap);
+    p.overlap = ctx->level_slots > 1 ? 1u : 0u;
+    p.arrays = 2; // three arrays let every late round be joined, but 120 MiB of timestamps do not stay in L2: measured 1.5x slower
+    if (const char* f = std::getenv("GP_LEVEL_ARRAYS")) p.arrays = f[0] == '2' ? 2u : 3u;
     p.time_bits = ctx->level_time_bits;
     if (const char* f = std::getenv("GP_LEVEL_REPORT_CTA")) p.report_cta = uint32_t(std::atoi(f));
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
@@ -555,12 +557,12 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
     p.nk = c.nk;
     for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
     if (c.keep_counters) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * 2 * ctx->level_slots, s));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * gp::kLevelArrays, s));
     GP_CUDA(ctx, cudaMemsetAsync(p.bars, 0, 64 + 8192, s));
     p.speed = reinterpret_cast<uint32_t*>(p.bars + 8);
     {
       const char* e = std::getenv("GP_LEVEL_WEIGHTED");
-      p.weighted = (ctx->level_slots == 1 && !(e && e[0] == '0')) ? 1u : 0u;
+      p.weighted = !(e && e[0] == '0') ? 1u : 0u;
     }
     while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
@@ -571,15 +573,19 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
     // (79 of 126 MiB on B200), so that the survivor lists, the sequence and the filters streaming through do not
     // evict them (+6 % k-mer ops/s).  Only when the window can cover them (one stream in flight).
     {
-      const size_t vbytes = gp::kCbfCounters * 4 * 2 * ctx->level_slots;
+      const size_t vbytes = gp::kCbfCounters * 4 * p.arrays;
       const char* e = std::getenv("GP_L2_PERSIST");
       const bool want = !(e && e[0] == '0') && ctx->l2_persist_max > 0 && vbytes <= size_t(ctx->l2_window_max);
       cudaStreamAttrValue av;
       std::memset(&av, 0, sizeof av);
       if (want) {
-        av.accessPolicyWindow.base_ptr = ctx->d_V.p;
-        av.accessPolicyWindow.num_bytes = vbytes;
-        av.accessPolicyWindow.hitRatio = std::min(1.0f, float(ctx->l2_persist_max) / float(vbytes));
+        // GP_L2_WINDOW=c: only the T_1 array (the densest one: every occurrence touches it twice), all of it
+        const char* wsel = std::getenv("GP_L2_WINDOW");
+        const bool only_c = wsel && wsel[0] == 'c' && p.arrays == 3u;
+        const size_t wbytes = only_c ? gp::kCbfCounters * 4 : vbytes;
+        av.accessPolicyWindow.base_ptr = only_c ? static_cast<void*>(ctx->d_V.as<uint32_t>() + 2 * gp::kCbfCounters) : ctx->d_V.p;
+        av.accessPolicyWindow.num_bytes = wbytes;
+        av.accessPolicyWindow.hitRatio = std::min(1.0f, float(ctx->l2_persist_max) / float(wbytes));
         av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       } // else: an empty window switches the policy off
@@ -593,6 +599,12 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
         ctx->l2_window_set = want;
       }
     }
+    if (std::getenv("GP_LEVEL_CTA_TIMES")) { // diagnostics of every CTA (gp_build_cta_times)
+      GP_CUDA(ctx, ctx->d_cta_times.ensure(size_t(ctx->sm_count) * 4 * 32 * 8));
+      GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cta_times.p, 0, size_t(ctx->sm_count) * 4 * 32 * 8, s));
+      p.cta_times = ctx->d_cta_times.as<unsigned long long>();
+    }
+    ctx->level_grid = uint32_t(gp::levels_max_grid(ctx->sm_count, ctas_per_sm));
     GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s, ctas_per_sm));
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
     launches += 1;
@@ -657,13 +669,28 @@ int gp_build_run(gp_ctx* ctx)
   return GP_OK;
 }
 
-int gp_build_round_times(gp_ctx* ctx, uint64_t out[16])
+int gp_build_round_times(gp_ctx* ctx, uint64_t out[32])
 {
   if (!ctx || !out) return GP_ERR_ARG;
   if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
   cudaSetDevice(ctx->cfg.device);
   GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  GP_CUDA(ctx, cudaMemcpy(out, ctx->d_counters.as<unsigned long long>() + 2, 16 * 8, cudaMemcpyDeviceToHost));
+  unsigned long long c[gp::kBuildCounters];
+  GP_CUDA(ctx, cudaMemcpy(c, ctx->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
+  std::memset(out, 0, 32 * 8);
+  for (uint32_t i = 0; i < gp::kLevelDiag; i++) out[i] = c[gp::kLevelDiagAt + i];
+  out[31] = c[17];
+  return GP_OK;
+}
+
+int gp_build_cta_times(gp_ctx* ctx, uint64_t* out, uint32_t cap_ctas, uint32_t* n_ctas)
+{
+  if (!ctx || !out || !n_ctas) return GP_ERR_ARG;
+  if (!ctx->filters_ready || !ctx->d_cta_times.p) GP_FAIL(ctx, GP_ERR_STATE, "no per-CTA times were recorded (set GP_LEVEL_CTA_TIMES=1 before the build)");
+  cudaSetDevice(ctx->cfg.device);
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_ctas = std::min(cap_ctas, ctx->level_grid);
+  GP_CUDA(ctx, cudaMemcpy(out, ctx->d_cta_times.p, size_t(*n_ctas) * 32 * 8, cudaMemcpyDeviceToHost));
   return GP_OK;
 }
 
@@ -1065,7 +1092,9 @@ int gp_polish_fetch(gp_ctx* ctx, char* out_seqs, uint64_t out_cap, uint64_t* out
     }
     GP_CUDA(ctx, cudaStreamSynchronize(s));
     if (!err) break;
+    ctx->stats.polish_reruns++;
     if (err == 2) { // pipelined edit kernel gave up waiting for filters (no co-residency): plain re-run, filters are final now
+      ctx->overlap_state = -1; // remembered here: the re-run below clears d_error before gp_pipeline_run could look at it
       if (int rc = polish_launch(ctx)) return rc;
       continue;
     }

@@ -12,20 +12,23 @@
 //     t > max_j T_{thr(t)-1}(x_j(t)).
 // An occurrence that fails the test at level L fails it at every higher level.  So a stream is
 // Lmax = max thr rounds of: "survivors test against T_L" then "survivors atomicMin their time
-// into T_{L+1}" -- order-free inside a round, which lets ALL SMs work on ONE stream, whose single
-// 40 MiB timestamp array then lives in L2 instead of HBM.  One array serves every level: entries
-// carry a 6-bit epoch tag (newer epochs compare smaller, so atomicMin overwrites stale entries,
-// and readers treat a stale tag as "never"), so nothing is cleared between levels or streams.
+// into T_{L+1}" -- order-free inside a round, which lets ALL SMs work on ONE stream, whose
+// timestamp arrays (10 485 760 x 4 B each) then live in L2 instead of HBM.  Entries carry an epoch
+// tag (newer epochs compare smaller, so atomicMin overwrites stale entries, and readers treat a
+// stale tag as "never"), so nothing is cleared between levels or streams.
 //
-// "Read level L" and "write level L+1" are ONE round over two alternating timestamp arrays (T_L lives in array
-// (L + 1) & 1), and round 0 already puts every occurrence on its warp's list: max thr rounds per stream.
-//
-// Rounds of one stream are separated by grid-wide barriers.  To keep the SMs busy while a barrier
-// drains, the grid works on `n_slots` streams at a time (each with its own timestamp array and
-// survivor lists; 2 x 40 MiB still sits in the 126 MB L2): a CTA runs one round of slot 0,
-// ARRIVES at slot 0's barrier, runs one round of slot 1, arrives, and only then WAITS for slot
-// 0's barrier -- by which time the other CTAs have normally arrived (split-phase barrier).  Every
-// CTA takes the same deterministic sequence of (slot, stream, round) decisions from uniform data.
+// Rounds and arrays.  Round 0 hashes every occurrence, races for T_1 and puts the occurrence on its
+// warp's survivor list (12 bytes: the canonical hash h0 -- the other three hashes and all eight
+// indices are re-derived from it -- and time | thr << 26).  List round L reads T_L, and the
+// survivors race for T_{L+1} right away in ANOTHER array.  T_1 has an array of its own (C); the
+// levels above alternate between two more (A/B, parity chosen per stream).  That makes two
+// consecutive streams independent enough to overlap: while stream s runs its LATE list rounds
+// (L >= 2: a few survivors per thread, i.e. one list -> timestamp -> red latency chain per round),
+// stream s+1 runs round 0 -- cut into as many parts as s has late rounds left -- and then its
+// level-1 round beside the LAST round of s (which only reads).  One grid barrier per interval
+// serves both streams; half of the warps of a CTA start with the late round, the other half with
+// the head work, so that the latency chain of one hides under the instruction stream of the other.
+// Every CTA takes the same deterministic sequence of decisions from uniform data.
 #include "gp_hashing.cuh"
 
 #include <algorithm>
@@ -41,15 +44,6 @@ constexpr uint32_t kTimeMask = (1u << kTimeBits) - 1u;
 // Tags count down (newer epochs compare smaller); the all-ones tag (epoch 0) is the cleared state.
 constexpr int kLevelWarps = 8;
 
-struct LevelCtx {
-  const uint64_t* tf;
-  const uint64_t* tr;
-  uint32_t lane, gwarp, nwarps;
-  // this warp's share of every stream: the fraction [cum[0], cum[1]) of 2^32 (all warps together tile [0, 2^32]);
-  // kept in shared memory, read where needed
-  const uint64_t* cum;
-};
-
 // A step is 32 consecutive k-mer starts of one read; steps of a stream are numbered in the
 // reference's order, which makes (step * 32 + lane) the occurrence time.  A warp's share of a stream is a
 // fraction [cum[0], cum[1]) of it -- equal fractions to begin with, then proportional to the speed measured for
@@ -60,26 +54,48 @@ struct LevelCtx {
 // left the early warps idle in every list round.  anchor[] maps a step to its read entry; lane r fetches the
 // head of run r, so that the dependent loads of all runs overlap.
 constexpr uint32_t kRuns = 8;
+
+struct LevelCtx {
+  const uint64_t* tf;
+  const uint64_t* tr;
+  uint32_t lane, gwarp;
+};
+
 // steps before the warp's share (its survivor list starts there, + one slack slot per row and warp)
-__device__ __forceinline__ uint64_t warp_list_base(uint32_t n_steps, const LevelCtx& c)
+__device__ __forceinline__ uint64_t warp_list_base(uint32_t n_steps, const uint64_t* cum, uint32_t gwarp)
 {
-  return ((uint64_t(n_steps) * c.cum[0]) >> 32) + uint64_t(c.gwarp) * (kRuns + 1u);
+  return ((uint64_t(n_steps) * cum[0]) >> 32) + uint64_t(gwarp) * (kRuns + 1u);
 }
 // run of row r (0..kRuns-1) of this warp: first step and length (0: none)
-__device__ __forceinline__ void run_of_row(uint32_t r, uint32_t n_steps, const LevelCtx& c, uint32_t& s0, uint32_t& len)
+__device__ __forceinline__ void run_of_row(uint32_t r, uint32_t n_steps, const uint64_t* cum, uint32_t& s0, uint32_t& len)
 {
   const uint32_t r0 = uint32_t(uint64_t(n_steps) * r / kRuns), r1 = uint32_t(uint64_t(n_steps) * (r + 1u) / kRuns);
   const uint64_t rowlen = r1 - r0, phase = (uint64_t(r) << 32) / kRuns;
   // boundaries floor(rowlen * cum + phase): 0 for cum = 0, rowlen for cum = 2^32, the same on both sides of a warp border
-  const uint32_t a = uint32_t((rowlen * c.cum[0] + phase) >> 32), b = uint32_t((rowlen * c.cum[1] + phase) >> 32);
+  const uint32_t a = uint32_t((rowlen * cum[0] + phase) >> 32), b = uint32_t((rowlen * cum[1] + phase) >> 32);
   s0 = r0 + a;
   len = r < kRuns ? b - a : 0u;
 }
 
-// Calls f(step, entry thr, valid, ci, bi) for every step of this warp's runs.
+// h0 -> the four hashes' counter indices (mod 10485760), each with bit 21 of its hash on top (bit 24), so that
+// the 22-bit filter index is recoverable from the same word
+__device__ __forceinline__ uint32_t pack_index(uint64_t h) { return cbf_index(h) | ((uint32_t(h >> 21) & 1u) << 24); }
+__device__ __forceinline__ void unpack_index(uint32_t w, uint32_t& ci, uint32_t& bi)
+{
+  ci = w & 0xFFFFFFu;
+  bi = (w & 0x1FFFFFu) | ((w >> 24) << 21);
+}
+__device__ __forceinline__ void derive_rest(uint64_t h0, const StreamConsts& sc, uint32_t (&pw)[4])
+{ // nthash.hpp:297-301
+  uint64_t h1 = h0 * sc.mul1, h2 = h0 * sc.mul2, h3 = h0 * sc.mul3;
+  h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
+  pw[1] = pack_index(h1); pw[2] = pack_index(h2); pw[3] = pack_index(h3);
+}
+
+// Calls f(step, entry thr, valid, h0, pw) for every step of this warp's runs in rows [row0, row1).
 template<typename F>
-__device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c, uint32_t batch, uint32_t ki,
-                                         const StreamConsts& sc, uint32_t n_steps, F&& f)
+__device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c, const uint64_t* cum, uint32_t batch, uint32_t ki,
+                                         const StreamConsts& sc, uint32_t n_steps, uint32_t row0, uint32_t row1, F&& f)
 {
   const uint32_t* pre = p.step_pre + uint64_t(ki) * (p.n_entries + 1);
   const uint64_t e0 = p.batch_entry_off[batch], e1 = p.batch_entry_off[batch + 1];
@@ -88,7 +104,7 @@ __device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c
   uint32_t h_e = 0, h_first = 0, h_last = 0, h_thr = 0, h_len = 0, h_wlo = 0, h_whi = 0;
   {
     uint32_t s0 = 0, len = 0;
-    if (c.lane < kRuns) run_of_row(c.lane, n_steps, c, s0, len);
+    if (c.lane >= row0 && c.lane < row1) run_of_row(c.lane, n_steps, cum, s0, len);
     if (len) {
       h_e = __ldg(anchor + s0);
       const uint64_t e = e0 + h_e;
@@ -101,9 +117,9 @@ __device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c
     }
   }
 #pragma unroll 1
-  for (uint32_t r = 0; r < kRuns; r++) {
+  for (uint32_t r = row0; r < row1; r++) {
     uint32_t s0, len;
-    run_of_row(r, n_steps, c, s0, len);
+    run_of_row(r, n_steps, cum, s0, len);
     if (len == 0) continue;
     const uint32_t s_end = s0 + len;
     const uint64_t e_head = e0 + __shfl_sync(0xffffffffu, h_e, r);
@@ -135,9 +151,11 @@ __device__ __forceinline__ void for_runs(const LevelParams& p, const LevelCtx& c
           w1 = __ldg(p.pk + wbase + rs + 2);
           m1 = __ldg(p.nm + wbase + rs + 2);
         }
-        uint32_t ci[4], bi[4];
-        const bool valid = hash_from_words(c.tf, c.tr, cw0, cw1, cm0, cm1, rs * 32u, npos, c.lane, sc, ci, bi);
-        f(s, thr, valid, ci, bi);
+        uint64_t h0 = 0;
+        const bool valid = hash_h0(c.tf, c.tr, cw0, cw1, cm0, cm1, rs * 32u, npos, c.lane, sc, h0);
+        uint32_t pw[4] = { 0xFFFFF0u, 0xFFFFF1u, 0xFFFFF2u, 0xFFFFF3u };
+        if (valid) { pw[0] = pack_index(h0); derive_rest(h0, sc, pw); }
+        f(s, thr, valid, h0, pw);
       }
     }
   }
@@ -165,40 +183,50 @@ void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uin
   fill_anchor_kernel<<<uint32_t((warps + 7) / 8), 256, 0, s>>>(step_pre, entry_rel, anchor, n_entries, nk, anchor_stride);
 }
 
-// Survivor lists: occurrences that passed level L.  An entry is five words: the four counter
-// indices (24 bits; bit 24 carries bit 21 of the hash, so that the 22-bit filter index is
-// recoverable without re-hashing) and time | thr << 26.  Lists are WARP-PRIVATE: a warp keeps the
-// survivors of its own share of the stream in its own region (share * 32 entries) and compacts
-// them in place level after level -- no list counters, no reservation atomics, no second buffer.
+// Survivor lists: occurrences that passed level L.  An entry is kSurvWords = 3 words: the canonical hash h0
+// (the three other hashes are multiply-xorshifts of it, nthash.hpp:297-301: ~40 instructions against 8 bytes
+// of list traffic per visit) and time | thr << 26.  Lists are WARP-PRIVATE: a warp keeps the survivors of its own
+// share of the stream in its own region (share * 32 entries) and compacts them in place level after level -- no
+// list counters, no reservation atomics.  Two list buffers alternate between consecutive streams (the late
+// rounds of one stream run beside round 0 of the next).
 struct SurvList {
-  uint32_t* w[5];   // w[0..3] packed indices, w[4] meta; already offset to the warp's region
+  uint32_t *lo, *hi, *meta;   // h0 low, h0 high, time | thr << 26; already offset to the warp's region
 };
-__device__ __forceinline__ uint32_t pack_index(uint32_t ci, uint32_t bi) { return ci | ((bi >> 21) << 24); }
-__device__ __forceinline__ void unpack_index(uint32_t w, uint32_t& ci, uint32_t& bi)
+__device__ __forceinline__ SurvList list_of(const LevelParams& p, uint32_t buf, uint32_t n_steps, const uint64_t* cum, uint32_t gwarp)
 {
-  ci = w & 0xFFFFFFu;
-  bi = (w & 0x1FFFFFu) | ((w >> 24) << 21);
+  SurvList l;
+  l.lo = p.surv + uint64_t(buf) * kLevelSurvWords * p.surv_cap + warp_list_base(n_steps, cum, gwarp) * 32u;
+  l.hi = l.lo + p.surv_cap;
+  l.meta = l.hi + p.surv_cap;
+  return l;
 }
-// append the lanes with q set at position cnt of the warp's list (pw = the four packed indices)
-__device__ __forceinline__ void surv_append(const SurvList& l, uint32_t& cnt, bool q, const uint32_t (&pw)[4], uint32_t meta,
-                                            uint32_t lane)
+// append the lanes with q set at position cnt of the warp's list
+__device__ __forceinline__ void surv_append(const SurvList& l, uint32_t& cnt, bool q, uint64_t h0, uint32_t meta, uint32_t lane)
 {
   const uint32_t m = __ballot_sync(0xffffffffu, q);
   if (q) {
     const uint32_t i = cnt + __popc(m & ((1u << lane) - 1u));
-#pragma unroll
-    for (int j = 0; j < 4; j++) l.w[j][i] = pw[j];
-    l.w[4][i] = meta;
+    l.lo[i] = uint32_t(h0);
+    l.hi[i] = uint32_t(h0 >> 32);
+    l.meta[i] = meta;
   }
   cnt += __popc(m);
 }
-__device__ __forceinline__ void surv_append(const SurvList& l, uint32_t& cnt, bool q, const uint32_t (&ci)[4],
-                                            const uint32_t (&bi)[4], uint32_t meta, uint32_t lane)
+// entries r + 32 e + lane (e < E) of a list of cnt entries; zeros beyond its end
+template<int E>
+__device__ __forceinline__ void fetch_entries(const SurvList& l, uint32_t cnt, uint32_t r, uint32_t lane, uint32_t (&lo)[E],
+                                              uint32_t (&hi)[E], uint32_t (&meta)[E])
 {
-  uint32_t pw[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) pw[j] = pack_index(ci[j], bi[j]);
-  surv_append(l, cnt, q, pw, meta, lane);
+  for (int e = 0; e < E; e++) {
+    const uint32_t i = r + 32u * e + lane;
+    lo[e] = 0; hi[e] = 0; meta[e] = 0;
+    if (i < cnt) {
+      lo[e] = __ldcg(l.lo + i);
+      hi[e] = __ldcg(l.hi + i);
+      meta[e] = __ldcg(l.meta + i);
+    }
+  }
 }
 // fire-and-forget atomics (REDG): spelled in PTX because ptxas keeps the returning form (ATOMG
 // with a dead destination) for atomicMin/atomicOr in this kernel
@@ -211,17 +239,140 @@ __device__ __forceinline__ void red_or(uint32_t* p, uint32_t v)
   asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void bf_insert(uint32_t* __restrict__ bf, const uint32_t (&bi)[4])
+__device__ __forceinline__ void bf_load(const uint32_t* __restrict__ bf, const uint32_t (&pw)[4], uint32_t (&w)[4])
+{ // the filter is 512 KiB and mostly hit by repeats of the same k-mers: look first
+#pragma unroll
+  for (int j = 0; j < 4; j++) { uint32_t ci, bi; unpack_index(pw[j], ci, bi); w[j] = __ldcg(bf + (bi >> 5)); }
+}
+__device__ __forceinline__ void bf_set(uint32_t* __restrict__ bf, const uint32_t (&pw)[4], const uint32_t (&w)[4])
 {
-  uint32_t w[4]; // the filter is 512 KiB and mostly hit by repeats of the same k-mers: look first
 #pragma unroll
-  for (int j = 0; j < 4; j++) w[j] = __ldcg(bf + (bi[j] >> 5));
-#pragma unroll
-  for (int j = 0; j < 4; j++)
-    if (!(w[j] & (1u << (bi[j] & 31u)))) red_or(bf + (bi[j] >> 5), 1u << (bi[j] & 31u));
+  for (int j = 0; j < 4; j++) {
+    uint32_t ci, bi;
+    unpack_index(pw[j], ci, bi);
+    if (!(w[j] & (1u << (bi & 31u)))) red_or(bf + (bi >> 5), 1u << (bi & 31u));
+  }
+}
+__device__ __forceinline__ void bf_insert(uint32_t* __restrict__ bf, const uint32_t (&pw)[4])
+{
+  uint32_t w[4];
+  bf_load(bf, pw, w);
+  bf_set(bf, pw, w);
 }
 
-// ---- split-phase grid barrier: one monotone counter per slot ----
+// ---- list rounds ----
+// One list round of one warp: who sees all four counters at >= L before its own time?  Survivors with thr = L + 1
+// enter the filter and, unless it is the stream's last round, race for T_{L+1} right away in the other array; the
+// list is compacted in place.  Two shapes:
+//   list_round_all    every entry loads its four timestamps at once (and, if it would enter the filter in this
+//                     round, the four filter words with them): one memory round trip per 64 entries.  The late
+//                     rounds, and any round that materialises counter bytes.
+//   list_round_first  level 1: most entries fail on their first counter (they are its first toucher); the other
+//                     three are only loaded for those that do not -- fewer touches, two round trips.  (Loading
+//                     all four for four entries per lane was tried for short lists: 19 against 13 us.)
+struct ListJob {
+  SurvList lst;
+  uint32_t cnt;
+  const uint32_t* V;   // T_L
+  uint32_t* Vn;        // where T_{L+1} goes
+  uint32_t* bf;
+  uint8_t* cbf;
+  uint32_t L, lread, tag, tag_next, vmask;
+};
+
+__device__ __forceinline__ uint32_t list_round_all(const ListJob& J, const StreamConsts& sc, uint32_t lane, uint32_t (&nlo)[2],
+                                                   uint32_t (&nhi)[2], uint32_t (&nmeta)[2])
+{
+  uint32_t kept = 0;
+  for (uint32_t r = 0; r < J.cnt; r += 64u) {
+    uint64_t h0[2];
+    uint32_t pw[2][4], meta[2], v[2][4], fw[2][4];
+    bool live[2], q[2], ins[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      live[e] = r + 32u * e + lane < J.cnt;
+      meta[e] = nmeta[e];
+      h0[e] = uint64_t(nlo[e]) | (uint64_t(nhi[e]) << 32);
+      ins[e] = live[e] && (meta[e] >> kTimeBits) == J.L + 1u; // enters the filter if it survives this round
+      pw[e][0] = pack_index(h0[e]);
+      derive_rest(h0[e], sc, pw[e]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[e][j] = live[e] ? __ldcg(J.V + (pw[e][j] & 0xFFFFFFu)) : 0u;
+#pragma unroll
+      for (int j = 0; j < 4; j++) fw[e][j] = 0u;
+      if (ins[e]) bf_load(J.bf, pw[e], fw[e]);
+    }
+    // the entries of the next iteration are requested now: this iteration's appends stay below r + 64
+    if (r + 64u < J.cnt) fetch_entries<2>(J.lst, J.cnt, r + 64u, lane, nlo, nhi, nmeta);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const uint32_t t = meta[e] & kTimeMask, thr = meta[e] >> kTimeBits;
+      bool reached = live[e];
+      uint32_t mx = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        reached &= (v[e][j] & ~J.vmask) == J.tag;
+        mx = max(mx, v[e][j] & J.vmask);
+        if (J.cbf && live[e] && v[e][j] == (J.tag | t)) J.cbf[pw[e][j] & 0xFFFFFFu] = (uint8_t)J.L; // moved counter j to level L
+      }
+      q[e] = reached && t > mx && thr > J.L;
+      if (q[e] && ins[e]) bf_set(J.bf, pw[e], fw[e]);
+      if (q[e] && J.L < J.lread) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) red_min(J.Vn + (pw[e][j] & 0xFFFFFFu), J.tag_next | t);
+      }
+    }
+    // every lane has both entries in registers before the ballots inside return; kept <= r
+    surv_append(J.lst, kept, q[0], h0[0], meta[0], lane);
+    surv_append(J.lst, kept, q[1], h0[1], meta[1], lane);
+  }
+  return kept;
+}
+
+__device__ __forceinline__ uint32_t list_round_first(const ListJob& J, const StreamConsts& sc, uint32_t lane, uint32_t (&nlo)[2],
+                                                     uint32_t (&nhi)[2], uint32_t (&nmeta)[2])
+{
+  uint32_t kept = 0;
+  for (uint32_t r = 0; r < J.cnt; r += 64u) {
+    uint64_t h0[2];
+    uint32_t pw[2][4], meta[2], v0[2], v[2][3];
+    bool live[2], q[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      live[e] = r + 32u * e + lane < J.cnt;
+      meta[e] = nmeta[e];
+      h0[e] = uint64_t(nlo[e]) | (uint64_t(nhi[e]) << 32);
+      pw[e][0] = pack_index(h0[e]);
+      v0[e] = live[e] ? __ldcg(J.V + (pw[e][0] & 0xFFFFFFu)) : 0u;
+    }
+    if (r + 64u < J.cnt) fetch_entries<2>(J.lst, J.cnt, r + 64u, lane, nlo, nhi, nmeta);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const uint32_t t = meta[e] & kTimeMask;
+      q[e] = live[e] && (v0[e] & ~J.vmask) == J.tag && (v0[e] & J.vmask) < t;
+      if (q[e]) derive_rest(h0[e], sc, pw[e]);
+#pragma unroll
+      for (int j = 0; j < 3; j++) v[e][j] = q[e] ? __ldcg(J.V + (pw[e][j + 1] & 0xFFFFFFu)) : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const uint32_t t = meta[e] & kTimeMask, thr = meta[e] >> kTimeBits;
+#pragma unroll
+      for (int j = 0; j < 3; j++) q[e] = q[e] && (v[e][j] & ~J.vmask) == J.tag && (v[e][j] & J.vmask) < t;
+      q[e] = q[e] && thr > J.L;
+      if (q[e] && thr == J.L + 1u) bf_insert(J.bf, pw[e]);
+      if (q[e] && J.L < J.lread) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) red_min(J.Vn + (pw[e][j] & 0xFFFFFFu), J.tag_next | t);
+      }
+    }
+    surv_append(J.lst, kept, q[0], h0[0], meta[0], lane);
+    surv_append(J.lst, kept, q[1], h0[1], meta[1], lane);
+  }
+  return kept;
+}
+
+// ---- grid barrier: one monotone counter ----
 // polling uses a relaxed load (an acquire load costs an L1 invalidate -- CCTL.IVALL -- per poll);
 // one fence after the loop orders the data reads of the next round behind it
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
@@ -268,30 +419,47 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
   return t;
 }
 
-enum : uint32_t { PH_CLEAR = 0, PH_L0 = 1, PH_READ = 2 };
+// what the head stream does in an interval
+enum : uint32_t { MK_NONE = 0, MK_CLEAR = 1, MK_R0 = 2, MK_R1 = 3 };
 
-struct SlotState {      // uniform over the grid; written by thread 0 of each CTA between rounds
-  uint32_t sid;         // wave-local stream, >= n_streams when the slot has run dry
-  uint32_t phase, L, lread, epoch, tag, tag_next, n_steps, batch;
-  uint32_t ord, publish, recal; // streams begun in this slot; this stream's round 0 publishes / re-reads the SM speeds
-  uint32_t done_b1, done_ki; // batch + 1 and k index of the slot's previous stream while its last barrier drains (0: none)
-  unsigned long long target; // barrier count that must be reached before the slot's next round
+struct StreamSt {       // one stream in flight (uniform over the grid: every CTA derives the same values)
+  uint32_t valid;
+  uint32_t sid, batch, ki, n_steps, lread;
+  uint32_t buf;         // which list buffer it uses
+  uint32_t cum;         // which share table it uses
+  uint32_t pb;          // T_L (L >= 2) lives in array (L + pb) & 1; T_1 in array 2, or (two arrays) in (1 + pb) & 1
+  uint32_t L;           // its next list round
+  uint32_t tag;         // tag carried by T_L (what round L reads)
+  uint32_t tag_next;    // tag given to T_{L+1} in round L
 };
 
-constexpr int kMaxSlots = 3;
+struct Sched {          // the planner's own state
+  StreamSt cur;         // head stream: round 0 (in parts), then its level-1 round
+  StreamSt tail;        // previous stream: late list rounds (L >= 2)
+  uint32_t next_sid, epoch, ord;
+  uint32_t need_clear, parts, part, r0_done, publish, recal; // of cur
+  uint4 nx_info;        // stream_tab entry of stream next_sid, fetched one stream ahead
+};
+
+struct Plan {           // what one interval does; written by the planner thread one interval ahead
+  uint32_t finished, main_kind, tail_on;
+  uint32_t row0, row1, part, last_part, publish, recal; // main_kind == MK_R0
+  StreamSt cur, tail;   // snapshots valid for this interval
+  uint32_t done_n, done_b[2], done_ki[2]; // streams whose last round ran in the interval before
+};
 
 // 3 CTAs of 8 warps per SM (80 registers); a 64-register build with 4 CTAs spills and measured 8 % slower
 __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kernel(LevelParams p)
 {
   __shared__ uint64_t tf[8 * 256];
   __shared__ uint64_t tr[8 * 256];
-  __shared__ SlotState slots[kMaxSlots];
-  __shared__ uint32_t next_sid;
-  __shared__ uint32_t warp_cnt[kMaxSlots][kLevelWarps]; // survivors in each warp's private list
-  __shared__ uint64_t cum_sh[kLevelWarps + 1];          // share boundaries of this CTA's warps (fractions of 2^32)
-  __shared__ unsigned long long cal_ns, cal_steps;      // round-0 work of this CTA since its last speed publication
+  __shared__ Sched sch;
+  __shared__ Plan plans[2];
+  __shared__ uint32_t warp_cnt[2][kLevelWarps];         // survivors in each warp's private list, per list buffer
+  __shared__ uint64_t cum_sh[2][kLevelWarps + 1];       // two tables of share boundaries of this CTA's warps (fractions of 2^32)
+  __shared__ unsigned long long cal_ns, cal_steps;      // round-0 work of this CTA's first warp since its last speed publication
   __shared__ unsigned long long red_sh[3][kLevelWarps];
-  __shared__ unsigned long long diag[15];               // round-time diagnostics of this CTA (thread 0)
+  __shared__ unsigned long long diag[kLevelDiag];       // interval-time diagnostics of this CTA (thread 0)
   if (p.batch_done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the edit kernel may join us now
   if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[20] = globaltimer_ns();
   fill_hash_tables(tf, tr);
@@ -299,283 +467,255 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   c.tf = tf; c.tr = tr;
   c.lane = threadIdx.x & 31u;
   c.gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  c.nwarps = (gridDim.x * blockDim.x) >> 5;
-  c.cum = cum_sh + (threadIdx.x >> 5);                   // equal shares (below) until speeds have been measured
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t wib = threadIdx.x >> 5;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   const uint32_t tb = p.time_bits, vmask = (1u << tb) - 1u, maxtag = (1u << (32u - tb)) - 1u;
+  const bool planner = threadIdx.x == 32u; // a thread that neither polls nor arrives: planning stays off the barrier's critical path
   unsigned long long ops = 0, list_seen = 0;
   if (threadIdx.x == 0) { cal_ns = 0; cal_steps = 0; }
-  if (threadIdx.x < 15) diag[threadIdx.x] = 0;
-  if (threadIdx.x <= uint32_t(kLevelWarps)) cum_sh[threadIdx.x] = (uint64_t(blockIdx.x * kLevelWarps + threadIdx.x) << 32) / c.nwarps;
+  if (threadIdx.x < kLevelDiag) diag[threadIdx.x] = 0;
+  if (threadIdx.x <= uint32_t(kLevelWarps)) // equal shares until speeds have been measured
+    cum_sh[0][threadIdx.x] = cum_sh[1][threadIdx.x] = (uint64_t(blockIdx.x * kLevelWarps + threadIdx.x) << 32) / nwarps;
 
-  // stream -> (n_steps, lread); called by thread 0 only
-  // stream_tab[sid] = {steps, largest thr, batch} in launch order, fetched one stream ahead (thread 0's registers)
-  uint4 nx_info = make_uint4(0u, 0u, 0u, 0u);
-  if (threadIdx.x == 0 && p.n_streams) nx_info = __ldg(p.stream_tab);
-  auto begin_stream = [&](SlotState& S) {
+  // ---- scheduling (planner thread only; every CTA computes the same sequence from uniform data) ----
+  auto new_tag = [&]() { sch.epoch++; return (maxtag - sch.epoch) << tb; };
+  auto begin_stream = [&]() {   // next stream with work becomes the head; sch.cur.valid = 0 when there is none
+    StreamSt& S = sch.cur;
+    const uint32_t prev_cum = S.cum;
+    S.valid = 0;
     for (;;) {
-      S.sid = next_sid++;
-      if (S.sid >= p.n_streams) return;
-      const uint4 info = nx_info;
-      if (S.sid + 1u < p.n_streams) nx_info = __ldg(p.stream_tab + S.sid + 1u);
-      const uint32_t ki = S.sid % p.nk, batch = info.z;
-      S.n_steps = info.x;
-      S.batch = batch;
-      if (S.n_steps == 0) { // nothing to insert: the (zeroed) filter is final
+      const uint32_t sid = sch.next_sid;
+      if (sid >= p.n_streams) return;
+      sch.next_sid = sid + 1u;
+      const uint4 info = sch.nx_info;
+      if (sid + 1u < p.n_streams) sch.nx_info = __ldg(p.stream_tab + sid + 1u);
+      const uint32_t ki = sid % p.nk, batch = info.z;
+      if (info.x == 0) { // nothing to insert: the (zeroed) filter is final
         if (p.batch_done && blockIdx.x == 0) { atomicAdd(p.batch_done + batch, 1u); atomicAdd(p.batch_done + p.n_batches_total, 1u); }
         continue;
       }
       const uint32_t lmax = info.y; // largest thr of the stream (kmer_threshold - 2 + k index, utils.cpp:108,121)
-      (void)ki;
+      S.valid = 1; S.sid = sid; S.batch = batch; S.ki = ki; S.n_steps = info.x;
       // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
       // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
       S.lread = p.cbf_pool ? lmax : lmax - 1u;
-      S.ord++;
-      S.publish = p.weighted && (S.ord & 63u) == 4u; // after 4 streams, then every 64: publish the CTA's speed ...
-      S.recal = p.weighted && (S.ord & 63u) == 5u;   // ... and the next stream starts with re-weighted shares
-      if (S.epoch + lmax + 1 > maxtag - 1u) { S.phase = PH_CLEAR; return; } // the tags of this stream would wrap
-      S.phase = PH_L0;
-      S.epoch++;
-      S.tag = (maxtag - S.epoch) << tb;
-      return;
+      S.buf = sch.ord & 1u;
+      sch.ord++;
+      sch.publish = p.weighted && (sch.ord & 63u) == 4u; // after 4 streams, then every 64: publish the CTA's speed ...
+      sch.recal = p.weighted && (sch.ord & 63u) == 5u;   // ... and the next stream starts with re-weighted shares,
+      S.cum = sch.recal ? prev_cum ^ 1u : prev_cum;       // in the table that the stream before it does not use
+      sch.part = 0; sch.r0_done = 0;
+      // the tags of this stream and of the late rounds still to come of the one before it must not wrap
+      const uint32_t pending = sch.tail.valid ? sch.tail.lread + 2u - sch.tail.L : 0u;
+      sch.need_clear = sch.epoch + lmax + 2u + pending > maxtag - 1u;
+      // three arrays: its T_2 must not land in the array that the last round of the stream before it reads;
+      // two arrays (T_1 alternates with the others): its T_1 must not
+      const uint32_t z = (sch.tail.lread + sch.tail.pb) & 1u;
+      S.pb = sch.tail.valid ? (p.arrays == 3u ? z ^ 1u : z) : 0u;
+      // three arrays: round 0 in as many parts as the tail has late rounds left before its last one
+      sch.parts = 1;
+      if (p.overlap && p.arrays == 3u && sch.tail.valid && !sch.need_clear) {
+        const uint32_t left = sch.tail.lread + 1u - sch.tail.L; // rounds L .. lread
+        sch.parts = left > 2u ? min(left - 1u, kRuns) : 1u;
+      }
+      return; // (the tag of its T_1 is drawn when its round 0 starts: tags must reach every array in order)
     }
   };
-  if (threadIdx.x == 0) {
-    next_sid = 0;
-    for (uint32_t s = 0; s < p.n_slots; s++) {
-      slots[s].epoch = 0; slots[s].target = 0; // V arrives cleared (all 0xFFFFFFFF = tag 63)
-      slots[s].done_b1 = 0; slots[s].done_ki = 0; slots[s].ord = 0; slots[s].publish = 0; slots[s].recal = 0;
-      begin_stream(slots[s]);
+  // what the interval after `prev` does (prev == nullptr: the first one)
+  auto make_plan = [&](const Plan* prev, Plan& P) {
+    P.done_n = 0;
+    auto push_done = [&](const StreamSt& S) { P.done_b[P.done_n] = S.batch; P.done_ki[P.done_n] = S.ki; P.done_n++; };
+    if (prev) { // ---- advance both streams past the interval `prev` ----
+      if (prev->tail_on) {
+        if (sch.tail.L >= sch.tail.lread) { push_done(sch.tail); sch.tail.valid = 0; }
+        else { sch.tail.L++; sch.tail.tag = sch.tail.tag_next; }
+      }
+      switch (prev->main_kind) {
+      case MK_CLEAR:
+        sch.epoch = 0; sch.need_clear = 0;
+        break;
+      case MK_R0:
+        if (++sch.part == sch.parts) {
+          sch.r0_done = 1;
+          if (sch.cur.lread == 0u) { push_done(sch.cur); sch.cur.valid = 0; } // (thr <= 1 everywhere: no list round)
+        }
+        break;
+      case MK_R1: // T_2 was written under tag_next; the stream goes on as the tail (the old tail has just finished)
+        if (sch.cur.lread <= 1u) push_done(sch.cur);
+        else { sch.tail = sch.cur; sch.tail.L = 2; sch.tail.tag = sch.cur.tag_next; }
+        sch.cur.valid = 0;
+        break;
+      default: break;
+      }
     }
+    if (!sch.cur.valid) begin_stream();
+    P.tail_on = sch.tail.valid;
+    P.main_kind = MK_NONE;
+    if (sch.cur.valid) {
+      if (sch.need_clear) {
+        if (!sch.tail.valid) P.main_kind = MK_CLEAR; // (waits for the tail: both streams' arrays are cleared)
+      } else if (!sch.r0_done) {
+        // two arrays: round 0 may only join the tail's LAST round (which reads one array and writes none)
+        if (!sch.tail.valid || (p.overlap && (p.arrays == 3u || sch.tail.L == sch.tail.lread))) {
+          P.main_kind = MK_R0;
+          if (sch.part == 0u) sch.cur.tag = new_tag();
+          P.part = sch.part;
+          P.last_part = sch.part + 1u == sch.parts;
+          P.row0 = kRuns * sch.part / sch.parts;
+          P.row1 = kRuns * (sch.part + 1u) / sch.parts;
+          P.publish = sch.publish; P.recal = sch.recal;
+        }
+      } else { // level-1 round: three arrays only, beside the LAST round of the tail (it writes T_2 into the array that round does not read)
+        if (!sch.tail.valid || (p.overlap && p.arrays == 3u && sch.tail.L == sch.tail.lread)) {
+          P.main_kind = MK_R1;
+          sch.cur.L = 1;
+          sch.cur.tag_next = new_tag();
+        }
+      }
+    }
+    if (P.tail_on) sch.tail.tag_next = new_tag();
+    P.cur = sch.cur; P.tail = sch.tail;
+    P.finished = P.main_kind == MK_NONE && !P.tail_on;
+  };
+  if (planner) {
+    sch.next_sid = 0; sch.epoch = 0; sch.ord = 0; // V arrives cleared (all 0xFFFFFFFF = epoch 0)
+    sch.cur.valid = 0; sch.cur.cum = 0; sch.tail.valid = 0;
+    sch.need_clear = 0; sch.parts = 1; sch.part = 0; sch.r0_done = 0; sch.publish = 0; sch.recal = 0;
+    sch.nx_info = p.n_streams ? __ldg(p.stream_tab) : make_uint4(0u, 0u, 0u, 0u);
+    make_plan(nullptr, plans[0]);
   }
+  __syncthreads();
 
-  for (;;) {
-    bool any = false;
-    for (uint32_t sl = 0; sl < p.n_slots; sl++) {
-      __syncthreads(); // slot states are stable from here to the next __syncthreads
-      SlotState& S = slots[sl];
-      if (S.sid >= p.n_streams) continue;
-      any = true;
-      unsigned long long* bar = p.bars + sl;
-      unsigned long long t_a = 0, t_b = 0;
-      // the warp's survivor list (room for every occurrence of its runs) is its own: the first entries of a list
-      // round are fetched BEFORE the barrier wait, they do not depend on the other CTAs
-      const uint32_t wib = threadIdx.x >> 5;
-      SurvList lst;
-      {
-        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + warp_list_base(S.n_steps, c) * 32u;
-#pragma unroll
-        for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
+  // T_1 of a stream: the third array, or (two arrays) the one its T_2 does not use
+  auto t1_array = [&](const StreamSt& S) { return p.V + (p.arrays == 3u ? 2u : ((1u + S.pb) & 1u)) * kCbfCounters; };
+  unsigned long long target = 0; // barrier count that must be reached before the coming interval (thread 0)
+  for (uint32_t it = 0;; it++) {
+    // Between the __syncthreads that ended the previous interval's work and the one below, plans[it & 1] is stable (it
+    // was written during the previous interval), thread 0 arrives at and polls the grid barrier, and everybody else
+    // fetches the first entries of its first list round -- its own list, independent of the other CTAs.
+    const Plan& P = plans[it & 1u];
+    const uint32_t main_kind = P.main_kind, tail_on = P.tail_on;
+    // this warp runs the tail's list round first if it is an even warp, the head's work first otherwise: the
+    // latency chain of a late round (few entries per thread) hides under the other half's instruction stream
+    const bool tail_first = tail_on && ((wib & 1u) == 0u || main_kind == MK_NONE);
+    uint32_t nx_lo[2], nx_hi[2], nx_meta[2];
+    uint32_t pre_for = 0; // 1: tail list prefetched, 2: head list prefetched
+    if (!P.finished && (tail_first || main_kind == MK_R1)) {
+      const StreamSt* S = tail_first ? &P.tail : &P.cur;
+      const SurvList l = list_of(p, S->buf, S->n_steps, cum_sh[S->cum] + wib, c.gwarp);
+      fetch_entries<2>(l, warp_cnt[S->buf][wib], 0, c.lane, nx_lo, nx_hi, nx_meta);
+      pre_for = tail_first ? 1u : 2u;
+    }
+    unsigned long long t_a = 0, t_b = 0;
+    if (threadIdx.x == 0) {
+      t_a = globaltimer_ns();
+      while (ld_relaxed_u64(p.bars) < target) { }
+      __threadfence();
+      t_b = globaltimer_ns();
+      target += gridDim.x;
+    }
+    __syncthreads(); // the previous interval is complete everywhere
+    for (uint32_t i = 0; i < P.done_n; i++) filter_final(p, P.done_b[i], P.done_ki[i], gtid, gthreads);
+    if (P.finished) break;
+    if (planner) make_plan(&P, plans[(it + 1u) & 1u]);
+    if (main_kind == MK_R0 && P.part == 0u && P.recal) {
+      // every CTA published the rate of its round-0 passes (steps per time) a few streams ago: the shares of the stream
+      // that begins are proportional to them.  Integer sums, so that every CTA derives the very same boundaries.
+      unsigned long long tot = 0;
+      for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot += __ldcg(p.speed + i);
+      tot = block_sum(tot, red_sh[0]);
+      const unsigned long long mean = max(1ull, tot / gridDim.x), lo = max(1ull, mean * 7ull / 10ull), hi = mean * 14ull / 10ull + 1ull;
+      unsigned long long all = 0, before = 0, mine = 0;
+      for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+        const unsigned long long v = min(max((unsigned long long)__ldcg(p.speed + i), lo), hi);
+        all += v;
+        if (i < blockIdx.x) before += v;
+        if (i == blockIdx.x) mine = v;
       }
-      const uint32_t list_cnt = S.phase == PH_READ ? warp_cnt[sl][wib] : 0u;
-      uint32_t nx_pw[2][4], nx_meta[2]; // entries of the next iteration of the list round
-      auto fetch_entries = [&](uint32_t r) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const uint32_t i = r + 32u * e + c.lane;
-          nx_meta[e] = 0;
-#pragma unroll
-          for (int j = 0; j < 4; j++) nx_pw[e][j] = 0;
-          if (i < list_cnt) {
-            nx_meta[e] = __ldcg(lst.w[4] + i);
-#pragma unroll
-            for (int j = 0; j < 4; j++) nx_pw[e][j] = __ldcg(lst.w[j] + i);
-          }
-        }
-      };
-      fetch_entries(0);
-      if (threadIdx.x == 0) {
-        t_a = globaltimer_ns();
-        const unsigned long long target = S.target;
-        while (ld_relaxed_u64(bar) < target) { }
-        __threadfence();
-        t_b = globaltimer_ns();
-      }
-      __syncthreads(); // the slot's previous round is complete everywhere
+      all = block_sum(all, red_sh[0]); before = block_sum(before, red_sh[1]); mine = block_sum(mine, red_sh[2]);
+      if (threadIdx.x <= uint32_t(kLevelWarps))
+        cum_sh[P.cur.cum][threadIdx.x] = ((before * kLevelWarps + mine * threadIdx.x) << 32) / (all * kLevelWarps);
+      __syncthreads();
+    }
 
-      const uint32_t sid = S.sid, phase = S.phase, tag = S.tag, L = S.L, n_steps = S.n_steps, lread = S.lread;
-      if (phase == PH_L0 && S.recal) {
-        // every CTA published the rate of its round-0 passes (steps per time) a few rounds ago: shares become
-        // proportional to them.  Integer sums, so that every CTA derives the very same boundaries.
-        unsigned long long tot = 0;
-        for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot += __ldcg(p.speed + i);
-        tot = block_sum(tot, red_sh[0]);
-        const unsigned long long mean = max(1ull, tot / gridDim.x), lo = max(1ull, mean * 7ull / 10ull), hi = mean * 14ull / 10ull + 1ull;
-        unsigned long long all = 0, before = 0, mine = 0;
-        for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-          const unsigned long long v = min(max((unsigned long long)__ldcg(p.speed + i), lo), hi);
-          all += v;
-          if (i < blockIdx.x) before += v;
-          if (i == blockIdx.x) mine = v;
-        }
-        all = block_sum(all, red_sh[0]); before = block_sum(before, red_sh[1]); mine = block_sum(mine, red_sh[2]);
-        if (threadIdx.x <= uint32_t(kLevelWarps))
-          cum_sh[threadIdx.x] = ((before * kLevelWarps + mine * threadIdx.x) << 32) / (all * kLevelWarps);
-        __syncthreads();
-        uint32_t* base = p.surv + uint64_t(sl) * 5u * p.surv_cap + warp_list_base(n_steps, c) * 32u;
-#pragma unroll
-        for (int j = 0; j < 5; j++) lst.w[j] = base + size_t(j) * p.surv_cap;
+    for (uint32_t ph = 0; ph < 2u; ph++) {
+      const bool tail_now = tail_on ? (tail_first ? ph == 0u : ph == 1u) : false;
+      const bool main_now = tail_on ? !tail_now : ph == 0u;
+      if (!tail_now && !(main_now && main_kind != MK_NONE)) continue;
+      if (main_now && main_kind == MK_CLEAR) {
+        for (uint64_t i = gtid; i < kCbfCounters * p.arrays; i += gthreads) p.V[i] = 0xFFFFFFFFu;
+        continue;
       }
-      if (S.done_b1) filter_final(p, S.done_b1 - 1u, S.done_ki, gtid, gthreads); // the slot's previous stream is complete everywhere
-      const uint32_t ki = sid % p.nk, batch = S.batch;
-      // two timestamp arrays per slot: T_L lives in array (L + 1) & 1
-      uint32_t* __restrict__ V0 = p.V + uint64_t(sl) * 2u * kCbfCounters;
-      uint32_t* __restrict__ V = V0 + (phase == PH_READ ? ((L + 1u) & 1u) * kCbfCounters : 0u);
-      uint32_t* __restrict__ Vn = V0 + (L & 1u) * kCbfCounters; // where T_{L+1} goes
-      const uint32_t tag_next = S.tag_next;
-      uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
-      uint8_t* __restrict__ cbf = p.cbf_pool ? p.cbf_pool + uint64_t(sid) * kCbfCounters : nullptr;
-      if (phase == PH_CLEAR) {
-        for (uint64_t i = gtid; i < kCbfCounters * 2u; i += gthreads) V0[i] = 0xFFFFFFFFu;
-      } else if (phase == PH_L0) {
-        // ---- round 0: every occurrence writes its time into T_1 (the first toucher of a counter wins) and goes
-        // to the warp's list, so that level 1 is an ordinary list round (no second hashing pass) ----
+      if (main_now && main_kind == MK_R0) {
+        // ---- round 0 (rows [row0, row1) of it): every occurrence writes its time into T_1 (the first toucher of a
+        // counter wins) and goes to the warp's list, so that level 1 is an ordinary list round ----
+        const uint32_t ki = P.cur.ki, batch = P.cur.batch, cb = P.cur.buf, n_steps = P.cur.n_steps;
+        const uint64_t* cum = cum_sh[P.cur.cum] + wib;
         const StreamConsts sc = stream_consts(p.k[ki]);
-        uint32_t cnt = 0;
-        for_runs(p, c, batch, ki, sc, n_steps,
-                 [&](uint32_t s, uint32_t thr, bool valid, const uint32_t (&ci)[4], const uint32_t (&bi)[4]) {
+        uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
+        const SurvList lst = list_of(p, cb, n_steps, cum, c.gwarp);
+        uint32_t cnt = P.part ? warp_cnt[cb][wib] : 0u;
+        const uint32_t tag = P.cur.tag;
+        uint32_t* __restrict__ VC = t1_array(P.cur);
+        unsigned long long w_t0 = 0;
+        uint32_t w_steps = 0;
+        if (threadIdx.x == 0) w_t0 = globaltimer_ns();
+        for_runs(p, c, cum, batch, ki, sc, n_steps, P.row0, P.row1,
+                 [&](uint32_t s, uint32_t thr, bool valid, uint64_t h0, const uint32_t (&pw)[4]) {
                    const uint32_t t = s * 32u + c.lane;
                    const bool q = valid && thr > 0u;
                    if (q) {
 #pragma unroll
-                     for (int j = 0; j < 4; j++) red_min(V + ci[j], tag | t);
-                     if (thr == 1u) bf_insert(bf, bi);
+                     for (int j = 0; j < 4; j++) red_min(VC + (pw[j] & 0xFFFFFFu), tag | t);
+                     if (thr == 1u) bf_insert(bf, pw);
                    }
                    if (valid) ops++;
-                   surv_append(lst, cnt, q && thr > 1u, ci, bi, t | (thr << kTimeBits), c.lane);
+                   w_steps++;
+                   surv_append(lst, cnt, q && thr > 1u, h0, t | (thr << kTimeBits), c.lane);
                  });
-        if (c.lane == 0) warp_cnt[sl][wib] = cnt;
-      } else {
-        // ---- list round: who sees all four counters at >= L before its own time?  Survivors with thr = L + 1 enter
-        // the filter and, unless it is the stream's last round, race for T_{L+1} right away in the other array; the
-        // list is compacted in place ----
-        if (c.lane == 0) list_seen += list_cnt; // (diagnostic, flushed once at the end)
-        // two entries per lane and iteration: their list words, then their timestamps, are all in flight together
-        const uint32_t cnt = list_cnt;
-        uint32_t kept = 0;
-        for (uint32_t r = 0; r < cnt; r += 64) {
-          uint32_t pw[2][4], meta[2];
-          bool live[2], q[2];
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            live[e] = r + 32u * e + c.lane < cnt;
-            meta[e] = nx_meta[e];
-#pragma unroll
-            for (int j = 0; j < 4; j++) pw[e][j] = nx_pw[e][j];
-          }
-          // the entries of the next iteration are requested now: this iteration's appends stay below r + 64
-          if (r + 64u < cnt) fetch_entries(r + 64u);
-          if (cbf || L > 1u) {
-            uint32_t v[2][4];
-#pragma unroll
-            for (int e = 0; e < 2; e++)
-#pragma unroll
-              for (int j = 0; j < 4; j++) v[e][j] = live[e] ? __ldcg(V + (pw[e][j] & 0xFFFFFFu)) : 0u;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const uint32_t t = meta[e] & kTimeMask;
-              bool reached = live[e];
-              uint32_t mx = 0;
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                reached &= (v[e][j] & ~vmask) == tag;
-                mx = max(mx, v[e][j] & vmask);
-                if (cbf && live[e] && v[e][j] == (tag | t)) cbf[pw[e][j] & 0xFFFFFFu] = (uint8_t)L; // moved counter j to level L
-              }
-              q[e] = reached && t > mx;
-            }
-          } else { // level 1: most entries fail on their first counter (they are its first toucher)
-            uint32_t v0[2];
-#pragma unroll
-            for (int e = 0; e < 2; e++) v0[e] = live[e] ? __ldcg(V + (pw[e][0] & 0xFFFFFFu)) : 0u;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const uint32_t t = meta[e] & kTimeMask;
-              q[e] = live[e] && (v0[e] & ~vmask) == tag && (v0[e] & vmask) < t;
-            }
-            uint32_t v[2][3];
-#pragma unroll
-            for (int e = 0; e < 2; e++)
-#pragma unroll
-              for (int j = 0; j < 3; j++) v[e][j] = q[e] ? __ldcg(V + (pw[e][j + 1] & 0xFFFFFFu)) : 0u;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const uint32_t t = meta[e] & kTimeMask;
-#pragma unroll
-              for (int j = 0; j < 3; j++) q[e] = q[e] && (v[e][j] & ~vmask) == tag && (v[e][j] & vmask) < t;
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const uint32_t t = meta[e] & kTimeMask, thr = meta[e] >> kTimeBits;
-            q[e] = q[e] && thr > L;
-            if (q[e] && thr == L + 1u) {
-              uint32_t ci, bi[4];
-#pragma unroll
-              for (int j = 0; j < 4; j++) unpack_index(pw[e][j], ci, bi[j]);
-              bf_insert(bf, bi);
-            }
-            if (q[e] && L < lread) {
-#pragma unroll
-              for (int j = 0; j < 4; j++) red_min(Vn + (pw[e][j] & 0xFFFFFFu), tag_next | t);
-            }
-          }
-          // every lane has both entries in registers before the ballots inside return; kept <= r
-          surv_append(lst, kept, q[0], pw[0], meta[0], c.lane);
-          surv_append(lst, kept, q[1], pw[1], meta[1], c.lane);
-        }
-        __syncwarp();
-        if (c.lane == 0) warp_cnt[sl][wib] = kept;
+        if (c.lane == 0) warp_cnt[cb][wib] = cnt;
+        if (threadIdx.x == 0 && p.weighted) { cal_ns += globaltimer_ns() - w_t0; cal_steps += w_steps; }
+        continue;
       }
+      // ---- list round of the tail (level >= 2) or of the head (level 1) ----
+      const StreamSt* S = tail_now ? &P.tail : &P.cur;
+      const uint32_t sbuf = S->buf;
+      const StreamConsts sc = stream_consts(p.k[S->ki]);
+      ListJob J;
+      J.L = S->L; J.lread = S->lread; J.tag = S->tag; J.tag_next = S->tag_next; J.vmask = vmask;
+      J.lst = list_of(p, sbuf, S->n_steps, cum_sh[S->cum] + wib, c.gwarp);
+      J.V = J.L == 1u ? t1_array(*S) : p.V + ((J.L + S->pb) & 1u) * kCbfCounters;
+      J.Vn = p.V + ((J.L + 1u + S->pb) & 1u) * kCbfCounters;
+      J.bf = p.bf_pool + (uint64_t(S->batch) * p.nk + S->ki) * kBfWords;
+      J.cbf = p.cbf_pool ? p.cbf_pool + uint64_t(S->sid) * kCbfCounters : nullptr;
+      J.cnt = warp_cnt[sbuf][wib];
+      if (c.lane == 0) list_seen += J.cnt; // (diagnostic, flushed once at the end)
+      if (pre_for != (tail_now ? 1u : 2u)) fetch_entries<2>(J.lst, J.cnt, 0, c.lane, nx_lo, nx_hi, nx_meta);
+      pre_for = 0;
+      const uint32_t kept = (J.cbf || J.L > 1u) ? list_round_all(J, sc, c.lane, nx_lo, nx_hi, nx_meta)
+                                                 : list_round_first(J, sc, c.lane, nx_lo, nx_hi, nx_meta);
+      __syncwarp();
+      if (c.lane == 0) warp_cnt[sbuf][wib] = kept;
+    }
 
-      __syncthreads(); // every thread of the CTA has issued its part of the round
-      if (threadIdx.x == 0) {
-        const unsigned long long t_c = globaltimer_ns();
-        if (phase == PH_L0 && p.weighted) { // this CTA's round-0 rate, for the weighted shares
-          cal_ns += t_c - t_b;
-          cal_steps += ((uint64_t(n_steps) * cum_sh[kLevelWarps]) >> 32) - ((uint64_t(n_steps) * cum_sh[0]) >> 32);
-          if (S.publish) {
-            p.speed[blockIdx.x] = uint32_t(min(max(cal_steps * 4000000ull / max(cal_ns, 1ull), 1ull), 262143ull));
-            cal_ns = 0; cal_steps = 0;
-          }
-        }
-        __threadfence();
-        atomicAdd(bar, 1ull);
-        // where the time of a CTA goes, per kind of round: barrier wait, work, rounds (kept in shared memory: global
-        // read-modify-writes here would make the reporting CTA late for every barrier)
-        diag[phase * 3 + 0] += t_b - t_a;
-        diag[phase * 3 + 1] += t_c - t_b;
-        diag[phase * 3 + 2] += 1;
-        S.target += gridDim.x;
-        S.done_b1 = 0;
-        // next round of this slot (same decision in every CTA)
-        switch (phase) {
-        case PH_CLEAR:
-          S.epoch = 1; S.tag = (maxtag - 1u) << tb; S.phase = PH_L0;
-          break;
-        case PH_L0: // T_1 carries S.tag; the round that reads it writes T_2 under the next tag
-          if (S.lread >= 1u) { S.phase = PH_READ; S.L = 1; S.epoch++; S.tag_next = (maxtag - S.epoch) << tb; }
-          else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
-          break;
-        default: // PH_READ
-          if (L < S.lread) { S.L = L + 1u; S.tag = S.tag_next; S.epoch++; S.tag_next = (maxtag - S.epoch) << tb; }
-          else { S.done_b1 = batch + 1u; S.done_ki = ki; begin_stream(S); }
-          break;
-        }
-      }
-    }
-    if (!any) break;
-  }
-  for (uint32_t sl = 0; sl < p.n_slots; sl++) { // last streams of the slots (states are final and uniform here)
-    __syncthreads();
-    const SlotState& S = slots[sl];
-    if (!S.done_b1) continue;
+    __syncthreads(); // every thread of the CTA has issued its part of the interval; the next plan is written
     if (threadIdx.x == 0) {
-      while (ld_relaxed_u64(p.bars + sl) < S.target) { }
+      const unsigned long long t_c = globaltimer_ns();
+      if (main_kind == MK_R0 && P.publish && P.last_part && p.weighted) { // this CTA's round-0 rate, for the weighted shares
+        p.speed[blockIdx.x] = uint32_t(min(max(cal_steps * 4000000ull / max(cal_ns, 1ull), 1ull), 262143ull));
+        cal_ns = 0; cal_steps = 0;
+      }
       __threadfence();
+      atomicAdd(p.bars, 1ull);
+      // where the time of a CTA goes, per kind of interval: barrier wait, work, intervals (kept in shared memory:
+      // global read-modify-writes here would make the reporting CTA late for every barrier)
+      // 0 clear, 1 round 0 alone, 2 level-1 round alone, 3 late round alone, 4 round 0 + late round, 5 level-1 + late round
+      const uint32_t kind = main_kind == MK_CLEAR ? 0u : main_kind == MK_R0 ? (tail_on ? 4u : 1u) : main_kind == MK_R1 ? (tail_on ? 5u : 2u) : 3u;
+      diag[kind * 3 + 0] += t_b - t_a;
+      diag[kind * 3 + 1] += t_c - t_b;
+      diag[kind * 3 + 2] += 1;
     }
-    __syncthreads();
-    filter_final(p, S.done_b1 - 1u, S.done_ki, gtid, gthreads);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);
@@ -583,7 +723,8 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   if (c.lane == 0 && list_seen) atomicAdd(p.counters + 17, list_seen);
   if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[21] = globaltimer_ns();
   if (blockIdx.x == p.report_cta && threadIdx.x == 0)
-    for (int i = 0; i < 15; i++) p.counters[2 + i] += diag[i]; // several waves add up
+    for (uint32_t i = 0; i < kLevelDiag; i++) p.counters[kLevelDiagAt + i] += diag[i]; // several waves add up
+  if (p.cta_times && threadIdx.x < kLevelDiag) p.cta_times[blockIdx.x * 32u + threadIdx.x] = diag[threadIdx.x];
 }
 
 int levels_max_grid(int sm_count, int ctas_per_sm)
@@ -596,8 +737,6 @@ int levels_max_grid(int sm_count, int ctas_per_sm)
   if (const char* e = std::getenv("GP_LEVEL_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e))); // experiments
   return sm_count * per_sm;
 }
-
-int levels_max_slots() { return kMaxSlots; }
 
 void preload_levels()
 {

@@ -129,14 +129,21 @@ __device__ __forceinline__ uint64_t sror(uint64_t v, uint32_t s)
   return (hi << 33) | lo;
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ bool bf_contains(const WS& w, uint64_t fh, uint64_t rh)
 { // btllib KmerBloomFilter::contains with the four ntHash values (ntedit.cpp:1470)
   const uint64_t b = fh + rh;
   uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
   h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
   const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
-  const uint32_t w0 = __ldg(w.bf + (n0 >> 5)), w1 = __ldg(w.bf + (n1 >> 5));
-  const uint32_t w2 = __ldg(w.bf + (n2 >> 5)), w3 = __ldg(w.bf + (n3 >> 5));
+  const uint32_t w0 = __ldcg(w.bf + (n0 >> 5)), w1 = __ldcg(w.bf + (n1 >> 5));
+  const uint32_t w2 = __ldcg(w.bf + (n2 >> 5)), w3 = __ldcg(w.bf + (n3 >> 5));
   return ((w0 >> (n0 & 31u)) & (w1 >> (n1 & 31u)) & (w2 >> (n2 & 31u)) & (w3 >> (n3 & 31u)) & 1u) != 0u;
 }
 __device__ __forceinline__ bool bf_contains(const WS& w, const HashState& h) { return bf_contains(w, h.fh, h.rh); }
@@ -607,8 +614,8 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
             uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
             h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
             const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
-            pw[q][0] = __ldg(w.bf + (n0 >> 5)); pw[q][1] = __ldg(w.bf + (n1 >> 5));
-            pw[q][2] = __ldg(w.bf + (n2 >> 5)); pw[q][3] = __ldg(w.bf + (n3 >> 5));
+            pw[q][0] = __ldcg(w.bf + (n0 >> 5)); pw[q][1] = __ldcg(w.bf + (n1 >> 5));
+            pw[q][2] = __ldcg(w.bf + (n2 >> 5)); pw[q][3] = __ldcg(w.bf + (n3 >> 5));
             pbits[q] = (n0 & 31u) | ((n1 & 31u) << 5) | ((n2 & 31u) << 10) | ((n3 & 31u) << 15);
             pend[q] = true;
           }
@@ -1069,18 +1076,20 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
     if (p.batch_done) { // pipelined with the filter build: wait until the contig's batch has its nk filters
       uint32_t ok = 1;
       if (lane == 0) {
-        const volatile uint32_t* flag = p.batch_done + p.contig_batch[ci];
-        const volatile uint32_t* progress = p.batch_done + p.n_batches; // filters finished so far, all batches
+        // acquire loads: the filter words read below (ld.global.cg, never the non-coherent path -- the build kernel
+        // is writing the pool while this kernel runs) must not be satisfied before the flag has been seen
+        const uint32_t* flag = p.batch_done + p.contig_batch[ci];
+        const uint32_t* progress = p.batch_done + p.n_batches; // filters finished so far, all batches
         unsigned long long t0 = 0, t1 = 0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        uint32_t seen = *progress, naps = 0;
+        uint32_t seen = ld_acquire_u32(progress), naps = 0;
         unsigned ns = 128;
-        while (*flag < p.nk) {
+        while (ld_acquire_u32(flag) < p.nk) {
           __nanosleep(ns);
           if (ns < 2048) ns <<= 1; // back off: hundreds of waiting warps must not hammer the two words they all read
           if ((++naps & 15u) == 0u) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            const uint32_t now = *progress;
+            const uint32_t now = ld_acquire_u32(progress);
             if (now != seen) { seen = now; t0 = t1; }
             else if (t1 - t0 > 4000000000ull) { ok = 0; break; } // 4 s without ANY new filter: the build is not running beside us
           }

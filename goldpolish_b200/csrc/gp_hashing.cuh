@@ -87,18 +87,16 @@ __device__ __forceinline__ bool hash_step(const uint64_t* __restrict__ tf, const
   return hash_from_words(tf, tr, w0, w1, m0, m1, p0, npos, lane, sc, ci, bi);
 }
 
-// the k-mer starting at position p0 + lane, from packed words w0|w1 and mask words m0|m1 that
-// hold positions p0 .. p0+63
-__device__ __forceinline__ bool hash_from_words(const uint64_t* __restrict__ tf, const uint64_t* __restrict__ tr,
-                                                uint64_t w0, uint64_t w1, uint32_t m0, uint32_t m1, uint32_t p0,
-                                                uint32_t npos, uint32_t lane, const StreamConsts& sc, uint32_t (&ci)[4],
-                                                uint32_t (&bi)[4], uint64_t* h0_out)
+// the canonical hash h0 of the k-mer starting at position p0 + lane, from packed words w0|w1 and mask words
+// m0|m1 that hold positions p0 .. p0+63; false (h0 untouched) when the k-mer holds a non-ACGT base or starts
+// beyond the last k-mer of the read
+__device__ __forceinline__ bool hash_h0(const uint64_t* __restrict__ tf, const uint64_t* __restrict__ tr, uint64_t w0,
+                                        uint64_t w1, uint32_t m0, uint32_t m1, uint32_t p0, uint32_t npos, uint32_t lane,
+                                        const StreamConsts& sc, uint64_t& h0)
 {
   const uint32_t mw = __funnelshift_r(m0, m1, lane);
   const bool valid = (p0 + lane < npos) && ((mw & sc.kmask) == 0u);
   const uint64_t w = lane ? ((w0 >> (2 * lane)) | (w1 << (64 - 2 * lane))) : w0;
-  ci[0] = 0xFFFFFFF0u; ci[1] = 0xFFFFFFF1u; ci[2] = 0xFFFFFFF2u; ci[3] = 0xFFFFFFF3u;
-  bi[0] = bi[1] = bi[2] = bi[3] = 0u;
   if (valid) {
     uint64_t fh, rh;
     switch (sc.kq) { // k is uniform per stream: pick the fully unrolled lookup (no per-byte branches)
@@ -111,7 +109,22 @@ __device__ __forceinline__ bool hash_from_words(const uint64_t* __restrict__ tf,
     case 2: hash_bytes<2>(tf, tr, w, fh, rh); break;
     default: hash_bytes<1>(tf, tr, w, fh, rh); break;
     }
-    const uint64_t h0 = fh + rh;
+    h0 = fh + rh;
+  }
+  return valid;
+}
+
+// ... and its 3 derived hashes, counter indices (mod 10485760) and filter bit indices (mod 2^22)
+__device__ __forceinline__ bool hash_from_words(const uint64_t* __restrict__ tf, const uint64_t* __restrict__ tr,
+                                                uint64_t w0, uint64_t w1, uint32_t m0, uint32_t m1, uint32_t p0,
+                                                uint32_t npos, uint32_t lane, const StreamConsts& sc, uint32_t (&ci)[4],
+                                                uint32_t (&bi)[4], uint64_t* h0_out)
+{
+  uint64_t h0 = 0;
+  const bool valid = hash_h0(tf, tr, w0, w1, m0, m1, p0, npos, lane, sc, h0);
+  ci[0] = 0xFFFFFFF0u; ci[1] = 0xFFFFFFF1u; ci[2] = 0xFFFFFFF2u; ci[3] = 0xFFFFFFF3u;
+  bi[0] = bi[1] = bi[2] = bi[3] = 0u;
+  if (valid) {
     if (h0_out) *h0_out = h0;
     uint64_t h1 = h0 * sc.mul1, h2 = h0 * sc.mul2, h3 = h0 * sc.mul3;
     h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;

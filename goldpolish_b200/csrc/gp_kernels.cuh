@@ -6,7 +6,9 @@
 
 namespace gp {
 
-constexpr int kBuildCounters = 32; // [0] k-mer ops, [1] serially resolved k-mers, [2..16] round times (levels kernel)
+constexpr int kBuildCounters = 64; // [0] k-mer ops, [1] serially resolved k-mers, [17] list entries visited, [20] / [21] first / last
+                                   // globaltimer, [32..49] interval times of the level-synchronous kernel (6 kinds x {wait, work, n})
+constexpr uint32_t kLevelDiag = 18, kLevelDiagAt = 32;
 
 struct BuildParams {
   const uint64_t* pk;               // packed reads, 32 bases per word
@@ -26,6 +28,10 @@ struct BuildParams {
   uint32_t k[kMaxK];
 };
 
+constexpr uint32_t kLevelSurvWords = 3; // words per survivor-list entry: h0 low, h0 high, time | thr << 26
+constexpr uint32_t kLevelArrays = 3;    // timestamp arrays: two for the levels >= 2 (alternating), one for T_1
+constexpr uint32_t kLevelListBufs = 2;  // list buffers: consecutive streams alternate
+
 struct LevelParams {              // level-synchronous filter build (gp_build_levels.cu)
   const uint64_t* pk;
   const uint32_t* nm;
@@ -40,17 +46,19 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   uint32_t n_batches_total;
   const uint16_t* anchor;         // [nk][anchor_stride]: global step of k index -> entry, relative to its batch
   uint64_t anchor_stride;
-  uint32_t* V;                    // per slot: 2 x kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
-  uint32_t* surv;                 // per slot: 5 arrays of surv_cap words ({4 packed indices, time|thr}), warp-private regions
-  unsigned long long* bars;       // per slot: barrier arrival counter (zeroed before a launch)
+  uint32_t* V;                    // kLevelArrays x kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
+  uint32_t* surv;                 // kLevelListBufs x kLevelSurvWords arrays of surv_cap words, warp-private regions
+  unsigned long long* bars;       // barrier arrival counter (zeroed before a launch)
   uint32_t* speed;                // per CTA: published round-0 rate (weighted shares)
-  uint32_t weighted;              // 1: shares follow the measured speed of each CTA's SM (one stream in flight only)
+  uint32_t weighted;              // 1: shares follow the measured speed of each CTA's SM
+  uint32_t overlap;               // 1: a stream's late list rounds run beside round 0 / the level-1 round of the next stream
+  uint32_t arrays;                // timestamp arrays in use: 3 (T_1 has its own: every late round can be joined), or 2 (only the last)
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
   uint32_t* bf_pool;
   uint32_t* bf_host;              // optional: device-visible pinned host copy of bf_pool, filled as filters become final
   unsigned long long* counters;
+  unsigned long long* cta_times;  // optional: 32 words per CTA, the interval-time diagnostics of every CTA (gp_build_cta_times)
   uint32_t surv_cap;
-  uint32_t n_slots;               // streams in flight (1..levels_max_slots())
   uint32_t time_bits;             // width of the time field of a timestamp entry (16..26): the longest stream fits
   uint32_t report_cta;            // which CTA fills the round-time diagnostics (GP_LEVEL_REPORT_CTA, default 0)
   uint32_t n_entries;
@@ -106,8 +114,8 @@ void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint6
                        uint32_t* nm, uint32_t n_reads, cudaStream_t s);
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s, int ctas_per_sm = 0);
-int levels_max_slots();
 void preload_levels();
+int levels_max_grid(int sm_count, int ctas_per_sm);
 void preload_edit();
 void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uint16_t* anchor, uint32_t n_entries,
                         uint32_t nk, uint64_t anchor_stride, cudaStream_t s);

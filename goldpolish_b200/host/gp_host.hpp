@@ -266,7 +266,13 @@ public:
   // src/mappings.cpp:15-35: type by file suffix; the minimizer filter only for ntLink triples
   Mappings(const std::string& path, const SeqIndex& targets, unsigned mx_min, unsigned mx_max, double mx_max_per_10kbp)
   {
-    if (endswith(path, ".sam") || endswith(path, ".bam")) load_lines(path, targets, 3);
+    // The reference reads mappings through btllib::DataSource, which pipes .bam through samtools and compressed
+    // files through their decompressors (src/mappings.cpp:136-139); this reader takes plain text only, so those
+    // inputs are refused instead of being parsed as garbage.
+    for (const char* suf : { ".bam", ".gz", ".bz2", ".xz", ".zst", ".zip", ".lrz" })
+      if (endswith(path, suf)) die("mappings file " + path + ": binary/compressed mappings are not supported here; "
+                                   "convert first (e.g. `samtools view -h` / `zcat`) and pass the text file");
+    if (endswith(path, ".sam")) load_lines(path, targets, 3);
     else if (endswith(path, ".paf")) load_lines(path, targets, 6);
     else {
       load_ntlink(path, targets, mx_min);

@@ -101,6 +101,8 @@ typedef struct {
   uint32_t build_kernel;    /* which filter-build kernel ran: 1 = one warp per stream (in order, counters in HBM),
                                2 = level-synchronous (order-free rounds, timestamps in L2) */
   uint32_t build_slots;     /* level-synchronous kernel: streams in flight */
+  uint32_t polish_reruns;   /* times gp_polish_fetch had to run the polish again since the context was created
+                               (a contig outgrew its buffers, or the overlapped edit kernel's watchdog fired) */
 } gp_stats;
 
 void gp_default_config(gp_config* cfg);
@@ -196,11 +198,14 @@ int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t reg
                        float* ms);
 
 /* Diagnostic (no reference counterpart): where the time of one CTA of the level-synchronous build
- * kernel went during the last gp_build_run, per kind of round r = 0 clear, 1 round 0 (hashing + first
- * timestamps), 2 list round: out[3r] = ns waiting at the round barrier, out[3r+1] = ns working,
- * out[3r+2] = rounds; out[15] = survivor-list entries visited by all list rounds of the launch
- * (out[9..14] unused). */
-int gp_build_round_times(gp_ctx* ctx, uint64_t out[16]);
+ * kernel went during the last gp_build_run, per kind of barrier interval r = 0 clear, 1 round 0 alone (hashing +
+ * first timestamps), 2 the level-1 list round alone, 3 a late list round alone, 4 round 0 beside the previous
+ * stream's last round, 5 the level-1 round beside it: out[3r] = ns waiting at the grid barrier, out[3r+1] = ns working,
+ * out[3r+2] = intervals; out[31] = survivor-list entries visited by all list rounds. */
+int gp_build_round_times(gp_ctx* ctx, uint64_t out[32]);
+/* The same numbers for EVERY CTA of the last level-synchronous launch (32 words per CTA, laid out as above),
+ * recorded only when the environment variable GP_LEVEL_CTA_TIMES is set: shows which CTAs the grid barrier waits for. */
+int gp_build_cta_times(gp_ctx* ctx, uint64_t* out, uint32_t cap_ctas, uint32_t* n_ctas);
 
 #ifdef __cplusplus
 }

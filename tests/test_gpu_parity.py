@@ -45,21 +45,28 @@ def test_filters_match_oracle(gp, small, bsize, algo, monkeypatch):
     assert st["build_launches"] > 0
 
 
-@pytest.mark.parametrize("slots", ["1", "2", "3"])
+@pytest.mark.parametrize("keep", [0, 1])
+@pytest.mark.parametrize("overlap", ["0", "1"])
 @pytest.mark.parametrize("bsize", [1, 8])
-def test_level_slots_match_oracle(gp, small, bsize, slots, monkeypatch):
-    """The level-synchronous kernel with 1, 2 or 3 streams in flight (split-phase barriers)."""
+def test_level_overlap_matches_oracle(gp, bsize, overlap, keep, monkeypatch):
+    """The level-synchronous kernel with one stream at a time and with the late list rounds of a stream running
+    beside round 0 / the level-1 round of the next one; with and without the extra round that materialises the
+    counter bytes (it changes which round is a stream's last, hence the schedule)."""
     monkeypatch.setenv("GP_BUILD_KERNEL", "l")
-    monkeypatch.setenv("GP_LEVEL_SLOTS", slots)
-    d, ctx = small
+    monkeypatch.setenv("GP_LEVEL_OVERLAP", overlap)
+    d = dataset(genome_len=60000)
+    ctx = gp.Context(keep_counters=keep)
+    ctx.upload_reads(d.read_seq, d.read_off)
     pl = plan(d, bsize=bsize)
     bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    assert ctx.stats()["build_slots"] == (2 if overlap == "1" else 1)
     ref = oracle_build(d, pl)
     for b in range(len(pl.batch_entry_off) - 1):
         for ki in range(4):
             assert np.array_equal(bfs[b, ki], ref[b].bfs[ki]), f"BF payload differs: batch {b} k={KS[ki]}"
-            if b == len(pl.batch_entry_off) - 2:
+            if keep and b == len(pl.batch_entry_off) - 2:
                 assert np.array_equal(ctx.fetch_cbf(b, ki), ref[b].cbfs[ki]), f"CBF differs: batch {b} k={KS[ki]}"
+    ctx.close()
 
 
 def test_filters_wave_invariance(gp, small):
