@@ -1,31 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- polished Mbp/s of the GoldPolish hot path (filter build + 4 ntEdit rounds + guard).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|5]
 
-One "step" = one pass of the hot path over one batch set of synthetic input: for every batch
-of the workload, build the 4 (counting filter, filter) pairs from its mapped reads and run the
-k=32,28,24,20 ntEdit chain over its contigs.  The N=1 workload is BASELINE.json configs[1]: a
-synthetic 5 Mbp draft cut into golden-path-sized contigs, 30x simulated ONT reads (5 % error),
-PAF-style mappings (subsample cap 40 per 10 kbp), bsize 1.  With N GPUs every rank polishes its
-own 5 Mbp shard (independent batches, no collective in the data path): weak scaling.
+One "step" = one pass of the hot path over the whole workload: for every batch, build the 4 (counting filter,
+filter) pairs from its mapped reads and run the k=32,28,24,20 ntEdit chain over its contigs, then the 0.75 guard.
+
+Workloads (BASELINE.json `configs`, numbered from 0 there and from 1 in SURVEY.md):
+  --config 3 (default)  configs[2] = SURVEY config 3: ONE synthetic 100 Mbp draft, 40x reads, bsize 8.  The same data set
+                        on every rank; its batches are sharded over the N GPUs (longest-processing-time on read bases,
+                        goldpolish_b200/shard.py), no collective in the data path, and rank 0 gathers the polished
+                        records in batch order inside the end-to-end timed region: STRONG scaling.  BASELINE.json quotes
+                        its metric ("polished Mbp/s at 1/2/4/8 B200") on this configuration, and it fits one GPU.
+  --config 2            configs[1] = SURVEY config 2: 5 Mbp draft, 30x reads, bsize 1 (round 1's bench line); with N > 1
+                        every rank polishes a private 5 Mbp data set (weak scaling of replicas).
+  --config 5            configs[4] = SURVEY config 5 shape: every rank polishes a private rank-seeded 375 Mbp shard of a
+                        3 Gbp draft (30x reads, ntLink-style mappings s=100 x=150, bsize 1), batches streamed through a
+                        bounded filter pool.  Weak by construction; meant for --gpus 8.
 
 `value`   : device-resident inputs (packed reads, staged contigs) -> kernels only.
-`e2e`     : through the C ABI with HOST buffers: H2D of reads + packing, build, D2H of the
-            filter payloads, H2D of contigs, polish, D2H of the polished sequences.
-`--impl reference` : the reference's own sources (oracle/_ref, compiled from /root/reference)
-            on the host cores, bounded sample of the same workload.
+`e2e`     : through the C ABI with HOST buffers: H2D of reads + packing, build, D2H of the filter payloads, H2D of
+            contigs, polish, D2H of the polished sequences, the guard, and (N > 1) the gather on rank 0.
+`--impl reference` : the reference's own sources (oracle/_ref, compiled from /root/reference) on the host cores,
+            a bounded sample of the same workload.  That arm never imports goldpolish_b200.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import shutil
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -36,10 +44,27 @@ if ROOT not in sys.path:
 
 METRIC = "polished_mbp_per_s"
 UNIT = "Mbp/s"
-WORKLOAD = dict(workload="configs[1]: synthetic 5 Mbp draft (contigs ~lognormal median 7 kbp) + 30x simulated ONT reads "
-                         "(5% error), PAF mappings s=40, bsize 1, k=32,28,24,20",
-                genome_len=5_000_000, coverage=30.0, bsize=1, subsample_max=40.0, ks=[32, 28, 24, 20])
+KS = [32, 28, 24, 20]
 ALGO_BYTES_PER_KMER_OP = 256  # 8 random 32-byte sector touches, SURVEY.md §8(d)
+BF_BYTES = 524288
+SEED = 20250607
+
+WORKLOADS = {
+    2: dict(workload="configs[1] (SURVEY config 2): synthetic 5 Mbp draft (contigs ~lognormal median 7 kbp) + 30x simulated "
+                     "ONT reads (5% error), PAF mappings s=40, bsize 1, k=32,28,24,20; N>1: one private data set per rank",
+            genome_len=5_000_000, coverage=30.0, bsize=1, subsample_max=40.0, mx_max=150.0, mappings="paf",
+            scaling="weak"),
+    3: dict(workload="configs[2] (SURVEY config 3): ONE synthetic 100 Mbp draft (contigs ~lognormal median 7 kbp) + 40x "
+                     "simulated ONT reads (5% error), PAF mappings s=40, bsize 8, k=32,28,24,20; batches sharded over the "
+                     "N GPUs, polished records gathered on rank 0",
+            genome_len=100_000_000, coverage=40.0, bsize=8, subsample_max=40.0, mx_max=150.0, mappings="paf",
+            scaling="strong"),
+    5: dict(workload="configs[4] (SURVEY config 5) shape: 3 Gbp draft as rank-seeded 375 Mbp shards, one per GPU, 30x "
+                     "simulated ONT reads, ntLink-style mappings (s=100, x=150, minimizer filter), bsize 1, "
+                     "k=32,28,24,20; filters streamed through a bounded pool",
+            genome_len=375_000_000, coverage=30.0, bsize=1, subsample_max=100.0, mx_max=150.0, mappings="ntlink",
+            scaling="weak"),
+}
 
 
 def log(*a):
@@ -67,19 +92,27 @@ def emit(line: dict):
         os.write(_JSON_FD, data)
 
 
-def make_dataset(rank: int, genome_len: int):
+def config_of(args) -> dict:
+    """The `config` object of the JSON line: identical in both arms (what is measured, not how)."""
+    w = WORKLOADS[args.config]
+    read_bases = w["genome_len"] * w["coverage"]
+    return {"workload": w["workload"], "genome_len": w["genome_len"], "coverage": w["coverage"], "bsize": w["bsize"],
+            "subsample_max": w["subsample_max"], "mx_max": w["mx_max"], "mappings": w["mappings"], "ks": KS,
+            "seed": SEED,
+            "l2": "inputs larger than L2: a step streams ~%.0f MB of 2-bit packed reads + masks and %.2f GB of filter "
+                  "payloads through the 126 MB L2 (the build kernel's own 80 MiB of timestamps are L2-resident by design)"
+                  % (read_bases * 0.375 / 1e6, w["genome_len"] / 9200.0 / w["bsize"] * 4 * BF_BYTES / 1e9)}
+
+
+def make_dataset(args, rank: int):
     import sim
-    return sim.simulate(genome_len=genome_len, coverage=WORKLOAD["coverage"], seed=20250607 + 1000003 * rank)
+    w = WORKLOADS[args.config]
+    seed = SEED if w["scaling"] == "strong" else SEED + 1000003 * rank
+    return sim.simulate(genome_len=w["genome_len"], coverage=w["coverage"], seed=seed)
 
 
-def make_plan(d):
-    import goldpolish_b200 as gp
-    clens = np.diff(d.contig_off)
-    rlens = np.diff(d.read_off)
-    return gp.plan_batches(clens, [d.contig_name(i) for i in range(d.n_contigs)],
-                           [d.read_name(i) for i in range(d.n_reads)], d.read_phred, rlens,
-                           d.map_read, d.map_contig, bsize=WORKLOAD["bsize"],
-                           subsample_max_per_10kbp=WORKLOAD["subsample_max"])
+def n_batches_of(d, bsize):
+    return (d.n_contigs + bsize - 1) // bsize
 
 
 class ClockSampler:
@@ -147,8 +180,7 @@ def measured_peaks():
 
 def ncu_traffic(kmer_ops_per_launch):
     """DRAM bytes per launch of the build kernel: the committed `ncu --set full` capture
-    (profiles/build_kernel_dram.json, taken on the 1 Mbp profiling workload) gives bytes per k-mer
-    op; scaled to the k-mer ops of this launch.  None when no capture is committed."""
+    (profiles/build_kernel_dram.json) gives bytes per k-mer op; scaled to the k-mer ops of this launch."""
     p = os.path.join(ROOT, "profiles", "build_kernel_dram.json")
     if os.path.exists(p):
         try:
@@ -160,133 +192,255 @@ def ncu_traffic(kmer_ops_per_launch):
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's own sources on the host cores
+# reference arm / cpu baseline: the reference's own sources on the host cores (never imports goldpolish_b200)
 # ----------------------------------------------------------------------------------------------
-def run_reference_sample(d, pl, n_sample_batches: int, threads: int, workdir: str):
-    """Times the reference's serve_batch (filter build) and ntEdit chain + guard on the first
-    n_sample_batches batches.  Returns dict(seconds_build, seconds_edit, bases, kind, cores)."""
-    import ctypes as C
+def sample_batches(args, d, threads: int) -> int:
+    """How many leading batches one CPU step covers: about --ref-bases-per-core draft bases per host core."""
+    w = WORKLOADS[args.config]
+    nb_total = n_batches_of(d, w["bsize"])
+    mean_batch = float(d.contig_off[-1]) / max(nb_total, 1)
+    nb = int(round(threads * args.ref_bases_per_core / max(mean_batch, 1.0)))
+    return max(min(nb_total, max(nb, threads, 8)), 1)
 
-    from oracle import ref_driver as rd
-    nb = min(n_sample_batches, len(pl.batch_entry_off) - 1)
-    bs = WORKLOAD["bsize"]
-    contigs = list(range(0, min(nb * bs, d.n_contigs)))
-    bases = int(sum(len(d.contig(c)) for c in contigs))
-    if rd.ref_available():
-        h = rd.harness()
-        draft, reads, paf = (os.path.join(workdir, f) for f in ("draft.fa", "reads.fq" if d.fastq else "reads.fa", "mappings.paf"))
-        if not os.path.exists(draft + ".index"):
-            rd.run_index(draft, draft + ".index")
-            rd.run_index(reads, reads + ".index")
-        bdir = os.path.join(workdir, "bfs")
-        shutil.rmtree(bdir, ignore_errors=True)
-        os.makedirs(bdir)
+
+class ReferenceSample:
+    """The first nb batches of the workload as files the reference's tools read, and one timed pass over them:
+    the reference's serve_batch (filter build) for every batch on `threads` OpenMP threads, then its ntEdit chain +
+    guard as `threads` single-thread workers (scripts/goldpolish runs ntedit-gr with -t1 per batch)."""
+
+    def __init__(self, args, d, nb: int, threads: int):
+        import sim
+        from oracle import ref_driver as rd
+        self.w = WORKLOADS[args.config]
+        self.d, self.nb, self.threads, self.rd = d, nb, threads, rd
+        self.kind = "reference" if rd.ref_available() else "port"
+        bs = self.w["bsize"]
+        self.contigs = list(range(0, min(nb * bs, d.n_contigs)))
+        self.bases = int(sum(int(d.contig_off[c + 1] - d.contig_off[c]) for c in self.contigs))
+        self.work = tempfile.mkdtemp(prefix="gp_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        if self.kind == "reference":
+            p = sim.write_subset(d, self.contigs, self.work)
+            self.draft, self.reads = p["draft"], p["reads"]
+            self.maps = p["paf"] if self.w["mappings"] == "paf" else p["tsv"]
+            rd.run_index(self.draft, self.draft + ".index")
+            rd.run_index(self.reads, self.reads + ".index")
+            self.bdir = os.path.join(self.work, "bfs")
+            for b in range(nb):
+                bd = os.path.join(self.work, f"batch{b}")
+                os.makedirs(bd, exist_ok=True)
+                with open(os.path.join(bd, "batch.fa"), "wb") as f:
+                    for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
+                        f.write(b">" + d.contig_name(c).encode() + b"\n" + d.contig(c) + b"\n")
+
+    def close(self):
+        shutil.rmtree(self.work, ignore_errors=True)
+
+    def run(self) -> dict:
+        if self.kind == "port":
+            return self._run_port()
+        import ctypes as C
+        d, nb, bs, threads = self.d, self.nb, self.w["bsize"], self.threads
+        h = self.rd.harness()
+        shutil.rmtree(self.bdir, ignore_errors=True)
+        os.makedirs(self.bdir)
         names, ids_files = [], []
         for b in range(nb):
             names.append(str(b).encode())
-            p = os.path.join(bdir, f"{b}.ids")
+            p = os.path.join(self.bdir, f"{b}.ids")
             with open(p, "w") as f:
                 for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
                     f.write(d.contig_name(c) + "\n")
             ids_files.append(p.encode())
-            bd = os.path.join(workdir, f"batch{b}")
-            os.makedirs(bd, exist_ok=True)
-            with open(os.path.join(bd, "batch.fa"), "w") as f:
-                for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
-                    f.write(f">{d.contig_name(c)}\n{d.contig(c).decode()}\n")
-        ks = (C.c_uint * 4)(*WORKLOAD["ks"])
+        ks = (C.c_uint * 4)(*KS)
         cwd = os.getcwd()
-        os.chdir(bdir)
+        os.chdir(self.bdir)
         os.environ["GP_ORACLE_QUIET"] = "1"
         try:
-            t_build = h.ref_serve_batches(draft.encode(), (draft + ".index").encode(), paf.encode(), reads.encode(),
-                                          (reads + ".index").encode(), 150.0, WORKLOAD["subsample_max"], threads, ks, 4,
+            t_build = h.ref_serve_batches(self.draft.encode(), (self.draft + ".index").encode(), self.maps.encode(),
+                                          self.reads.encode(), (self.reads + ".index").encode(), self.w["mx_max"],
+                                          self.w["subsample_max"], threads, ks, 4,
                                           (C.c_char_p * nb)(*names), (C.c_char_p * nb)(*ids_files), nb)
         finally:
             os.chdir(cwd)
         if t_build < 0:
             raise RuntimeError("reference serve_batches failed")
-        bases_arr = (C.c_char_p * nb)(*[os.path.join(workdir, f"batch{b}", "batch").encode() for b in range(nb)])
-        bfs_flat = (C.c_char_p * (nb * 4))(*[os.path.join(bdir, f"{b}-k{k}.bf").encode() for b in range(nb) for k in WORKLOAD["ks"]])
-        outs = (C.c_char_p * nb)(*[os.path.join(workdir, f"batch{b}", "batch.ntedited.fa").encode() for b in range(nb)])
+        bases_arr = (C.c_char_p * nb)(*[os.path.join(self.work, f"batch{b}", "batch").encode() for b in range(nb)])
+        bfs_flat = (C.c_char_p * (nb * 4))(*[os.path.join(self.bdir, f"{b}-k{k}.bf").encode() for b in range(nb) for k in KS])
+        outs = (C.c_char_p * nb)(*[os.path.join(self.work, f"batch{b}", "batch.ntedited.fa").encode() for b in range(nb)])
         t_edit = h.ref_ntedit_chain_many(bases_arr, bfs_flat, ks, 4, outs, nb, threads)
         if t_edit < 0:
             raise RuntimeError("reference ntedit chain failed")
-        return dict(seconds_build=t_build, seconds_edit=t_edit, bases=bases, kind="reference", cores=threads,
-                    batches=nb)
-    # oracle port, one thread
-    from oracle import oracle_lib as ol
-    t0 = time.perf_counter()
-    fsets = {}
-    for b in range(nb):
-        fs = ol.FilterSet()
-        for e in range(int(pl.batch_entry_off[b]), int(pl.batch_entry_off[b + 1])):
-            fs.add_read(d.read(int(pl.entries[e]["read_id"])), int(pl.entries[e]["kmer_threshold"]))
-        fsets[b] = fs
-    t1 = time.perf_counter()
-    for c in contigs:
-        cur = d.contig(c)
-        for ki, k in enumerate(WORKLOAD["ks"]):
-            cur, _ = ol.ntedit_contig(cur, fsets[int(pl.contig_batch[c])].bfs[ki], k)
-            if cur is None:
-                break
-    t2 = time.perf_counter()
-    return dict(seconds_build=t1 - t0, seconds_edit=t2 - t1, bases=bases, kind="port", cores=1, batches=nb)
+        return dict(seconds_build=t_build, seconds_edit=t_edit, bases=self.bases, kind="reference", cores=threads, batches=nb)
 
+    # ---- what the reference produced in the last run(), for the parity check ----
+    def filters(self, b: int) -> np.ndarray:
+        """[4, BF_BYTES] payloads of batch b (btllib files: payload = the last `bytes` bytes)."""
+        out = np.empty((4, BF_BYTES), dtype=np.uint8)
+        for i, k in enumerate(KS):
+            with open(os.path.join(self.bdir, f"{b}-k{k}.bf"), "rb") as f:
+                data = f.read()
+            out[i] = np.frombuffer(data[len(data) - BF_BYTES:], dtype=np.uint8)
+        return out
 
-def write_files(d, workdir):
-    import ctypes as C
+    def polished(self, b: int) -> list[tuple[str, bytes]]:
+        """(name, sequence) records of batch.ntedited.fa of batch b (after the reference's 0.75 guard)."""
+        recs = []
+        with open(os.path.join(self.work, f"batch{b}", "batch.ntedited.fa"), "rb") as f:
+            lines = f.read().split(b"\n")
+        for i in range(0, len(lines) - 1, 2):
+            if lines[i].startswith(b">"):
+                recs.append((lines[i][1:].decode().split()[0], lines[i + 1]))
+        return recs
 
-    import sim
-    # regenerate through the simulator's own writer (same seed -> same data) to get the files
-    p = dict(d.params)
-    sim.simulate(write_dir=workdir, **{k: v for k, v in p.items()})
+    def _run_port(self) -> dict:
+        """No compiled reference on this machine: the single-thread C restatement (oracle/gp_oracle.c)."""
+        from oracle import oracle_lib as ol
+        d, bs = self.d, self.w["bsize"]
+        rlens = np.diff(d.read_off)
+        per_contig = {}
+        for r, c in zip(d.map_read.tolist(), d.map_contig.tolist()):
+            if c < len(self.contigs) and r not in per_contig.setdefault(c, {}):
+                per_contig[c][r] = True
+        t0 = time.perf_counter()
+        fsets = {}
+        for b in range(self.nb):
+            fs = ol.FilterSet()
+            for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
+                ids = list(per_contig.get(c, {}))
+                if not ids:
+                    continue
+                chosen, thr = ol.select_reads([d.read_name(i) for i in ids], [d.read_phred[i] for i in ids],
+                                              [int(rlens[i]) for i in ids], int(d.contig_off[c + 1] - d.contig_off[c]),
+                                              self.w["subsample_max"])
+                for j in chosen:
+                    fs.add_read(d.read(ids[j]), thr)
+            fsets[b] = fs
+        t1 = time.perf_counter()
+        for c in self.contigs:
+            cur = d.contig(c)
+            for ki, k in enumerate(KS):
+                cur, _ = ol.ntedit_contig(cur, fsets[c // bs].bfs[ki], k)
+                if cur is None:
+                    break
+        t2 = time.perf_counter()
+        return dict(seconds_build=t1 - t0, seconds_edit=t2 - t1, bases=self.bases, kind="port", cores=1, batches=self.nb)
 
 
 def reference_arm(args, rank, world):
     if rank != 0:
         return
-    genome = args.genome_len
-    d = make_dataset(0, genome)
-    pl = make_plan(d)
+    d = make_dataset(args, 0)
+    w = WORKLOADS[args.config]
+    nb_total = n_batches_of(d, w["bsize"])
     threads = os.cpu_count() or 1
-    work = tempfile.mkdtemp(prefix="gp_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    nb = sample_batches(args, d, threads)
+    rs = ReferenceSample(args, d, nb, threads)
     try:
-        write_files(d, work)
-        nb_total = len(pl.batch_entry_off) - 1
-        # bounded sample: ~3 batches per core per step keeps a K-step run within minutes
-        nb = min(nb_total, max(threads * args.ref_batches_per_core, 8))
-        times = []
-        res = None
+        times, res = [], None
         for it in range(args.warmup + args.steps):
-            res = run_reference_sample(d, pl, nb, threads, work)
+            res = rs.run()
             if it >= args.warmup:
                 times.append(res["seconds_build"] + res["seconds_edit"])
         t = float(np.mean(times))
         val = res["bases"] / 1e6 / t
-        line = {
+        sample = (f"first {res['batches']} of {nb_total} batches ({res['bases']} of {int(d.contig_off[-1])} draft bases) per step; "
+                  f"last step: build {res['seconds_build']:.2f}s + edit {res['seconds_edit']:.2f}s; "
+                  f"steps min/mean/max {min(times):.2f}/{t:.2f}/{max(times):.2f}s; value = sample bases / mean step time")
+        emit({
             "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "u8/u64 integer", "data": "synthetic (seeded simulator, sim/gpsim.c)", "impl": "reference",
-            "config": dict(WORKLOAD, genome_len=genome, sample=f"first {res['batches']} of {nb_total} batches per step"),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
-                             "sample": f"first {res['batches']} of {nb_total} batches ({res['bases']} draft bases), "
-                                       f"build {res['seconds_build']:.2f}s + edit {res['seconds_edit']:.2f}s"},
+            "config": config_of(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-        }
-        emit(line)
+        })
+        assert "goldpolish_b200" not in sys.modules, "the reference arm must not load the product"
     finally:
-        shutil.rmtree(work, ignore_errors=True)
+        rs.close()
 
 
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+class LocalShare:
+    """This rank's part of the workload: its batches (global indices, ascending), their contigs and the reads their
+    entries name, re-indexed into a rank-local read store."""
+
+    def __init__(self, d, pl, my_batches, bsize):
+        self.batches = np.asarray(my_batches, dtype=np.int64)
+        off = pl.batch_entry_off.astype(np.int64)
+        ent_idx = np.concatenate([np.arange(off[b], off[b + 1]) for b in my_batches]) if len(my_batches) else np.zeros(0, np.int64)
+        ents = pl.entries[ent_idx]
+        self.batch_entry_off = np.concatenate([[0], np.cumsum([off[b + 1] - off[b] for b in my_batches])]).astype(np.uint64)
+        # local read store: reads in first-use order
+        uniq, first = np.unique(ents["read_id"], return_index=True)
+        order = uniq[np.argsort(first)]
+        remap = np.full(d.n_reads, -1, dtype=np.int64)
+        remap[order] = np.arange(len(order))
+        self.entries = ents.copy()
+        self.entries["read_id"] = remap[ents["read_id"]].astype(np.uint32)
+        rl = np.diff(d.read_off)[order]
+        self.read_off = np.concatenate([[0], np.cumsum(rl)]).astype(np.int64)
+        self.read_seq = np.empty(int(self.read_off[-1]), dtype=np.uint8)
+        for i, r in enumerate(order.tolist()):
+            self.read_seq[self.read_off[i]:self.read_off[i + 1]] = d.read_seq[d.read_off[r]:d.read_off[r + 1]]
+        self.n_reads = len(order)
+        # local contigs, in global order
+        self.contigs = np.concatenate([np.arange(b * bsize, min((b + 1) * bsize, d.n_contigs)) for b in my_batches]) \
+            if len(my_batches) else np.zeros(0, np.int64)
+        cl = np.diff(d.contig_off)[self.contigs]
+        self.contig_off = np.concatenate([[0], np.cumsum(cl)]).astype(np.int64)
+        self.contig_seq = np.empty(int(self.contig_off[-1]), dtype=np.uint8)
+        for i, c in enumerate(self.contigs.tolist()):
+            self.contig_seq[self.contig_off[i]:self.contig_off[i + 1]] = d.contig_seq[d.contig_off[c]:d.contig_off[c + 1]]
+        local_batch_of = {int(b): i for i, b in enumerate(my_batches)}
+        self.contig_batch = np.array([local_batch_of[int(c) // bsize] for c in self.contigs], dtype=np.uint32)
+        self.name_len = np.array([len(d.contig_name(int(c))) for c in self.contigs], dtype=np.int64)
+        self.draft_bases = int(self.contig_off[-1])
+
+
+def apply_guard(share, out, off, dropped, guard_fn):
+    """scripts/goldpolish-ntedit:31-40 per batch: bytes(last _edited.fa) / bytes(batch.fa) < 0.75 (bc scale=4) -> the
+    batch keeps its ORIGINAL records.  File sizes count '>' + name + '\\n' + sequence + '\\n' per record; a dropped
+    record is absent from the output file.  Returns (out, off, dropped, rejected batch count); out/off are replaced
+    only when a batch is rejected (rare)."""
+    n = len(share.contigs)
+    if n == 0:
+        return out, off, dropped, 0
+    if hasattr(out, "numpy"):
+        out = out.numpy()
+    in_len = np.diff(share.contig_off)
+    out_len = np.diff(off.astype(np.int64))
+    keep = dropped == 0
+    in_sz = share.name_len + 3 + in_len
+    out_sz = np.where(keep, share.name_len + 3 + out_len, 0)
+    nb = len(share.batches)
+    bi = np.zeros(nb, dtype=np.int64)
+    bo = np.zeros(nb, dtype=np.int64)
+    np.add.at(bi, share.contig_batch, in_sz)
+    np.add.at(bo, share.contig_batch, out_sz)
+    rejected = (bo * 10000) // np.maximum(bi, 1) < 7500
+    n_rej = int(rejected.sum())
+    if n_rej == 0:
+        return out, off, dropped, 0
+    assert all(bool(guard_fn(int(bi[b]), int(bo[b]))) for b in np.nonzero(rejected)[0][:4])  # same rule as the C ABI's
+    rej_c = rejected[share.contig_batch]
+    new_len = np.where(rej_c, in_len, np.where(keep, out_len, 0))
+    new_off = np.concatenate([[0], np.cumsum(new_len)]).astype(np.uint64)
+    new_out = np.empty(int(new_off[-1]), dtype=np.uint8)
+    for i in range(n):
+        src = share.contig_seq[share.contig_off[i]:share.contig_off[i + 1]] if rej_c[i] else out[int(off[i]):int(off[i + 1])]
+        new_out[int(new_off[i]):int(new_off[i + 1])] = src
+    new_dropped = np.where(rej_c, 0, dropped).astype(np.uint8)
+    return new_out, new_off, new_dropped, n_rej
+
+
 def ours(args, rank, world, local_rank):
     import torch
 
     import goldpolish_b200 as gp
+    from goldpolish_b200 import shard
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; goldpolish_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -295,20 +449,37 @@ def ours(args, rank, world, local_rank):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    genome = args.genome_len
+    w = WORKLOADS[args.config]
+    strong = w["scaling"] == "strong"
     t0 = time.time()
-    d = make_dataset(rank, genome)
-    pl = make_plan(d)
-    n_batches = len(pl.batch_entry_off) - 1
-    draft_bases = int(d.contig_off[-1])
-    log(f"[rank {rank}] data: {d.n_contigs} contigs / {draft_bases} bp, {d.n_reads} reads / {int(d.read_off[-1])} bp, "
-        f"{n_batches} batches, {len(pl.entries)} read entries ({time.time() - t0:.1f}s)")
+    d = make_dataset(args, rank)
+    clens, rlens = np.diff(d.contig_off), np.diff(d.read_off)
+    pl = gp.plan_batches(clens, [d.contig_name(i) for i in range(d.n_contigs)],
+                         [d.read_name(i) for i in range(d.n_reads)], d.read_phred, rlens, d.map_read, d.map_contig,
+                         bsize=w["bsize"], subsample_max_per_10kbp=w["subsample_max"],
+                         map_mx=d.map_mx if w["mappings"] == "ntlink" else None, mx_max_per_10kbp=w["mx_max"])
+    nb_total = len(pl.batch_entry_off) - 1
+    # sharding: batches are independent (private filters): LPT on read bases; every rank derives the same assignment
+    if strong and world > 1:
+        off = pl.batch_entry_off.astype(np.int64)
+        ent_bases = rlens[pl.entries["read_id"]]
+        csum = np.concatenate([[0], np.cumsum(ent_bases)])
+        work = (csum[off[1:]] - csum[off[:-1]]) + 1
+        assignment = shard.assign_batches(work.tolist(), world)
+    else:
+        assignment = None
+    my_batches = assignment[rank] if assignment is not None else list(range(nb_total))
+    sh = LocalShare(d, pl, my_batches, w["bsize"])
+    n_batches = len(my_batches)
+    log(f"[rank {rank}] data: {d.n_contigs} contigs / {int(d.contig_off[-1])} bp, {d.n_reads} reads / {int(d.read_off[-1])} bp, "
+        f"{nb_total} batches; this rank: {n_batches} batches, {sh.draft_bases} draft bp, {sh.n_reads} reads / "
+        f"{int(sh.read_off[-1])} bp, {len(sh.entries)} read entries ({time.time() - t0:.1f}s)")
 
     # pinned host buffers (e2e copies come from / go to these)
-    reads_h = torch.from_numpy(d.read_seq).pin_memory()
-    contigs_h = torch.from_numpy(d.contig_seq).pin_memory()
-    bf_h = torch.empty((n_batches, 4, gp.BF_BYTES), dtype=torch.uint8).pin_memory()
-    out_h = torch.empty(draft_bases + draft_bases // 4 + 65536, dtype=torch.uint8).pin_memory()
+    reads_h = torch.from_numpy(sh.read_seq).pin_memory()
+    contigs_h = torch.from_numpy(sh.contig_seq).pin_memory()
+    bf_h = torch.empty((max(n_batches, 1), 4, gp.BF_BYTES), dtype=torch.uint8).pin_memory()
+    out_h = torch.empty(sh.draft_bases + sh.draft_bases // 4 + 65536, dtype=torch.uint8).pin_memory()
 
     ctx = gp.Context(device=local_rank)
     # a non-default torch stream: the library's kernels are launched on it so that the
@@ -316,9 +487,9 @@ def ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    ctx.upload_reads(reads_h, d.read_off)
-    ctx.build_stage(pl.batch_entry_off, pl.entries)
-    ctx.polish_stage(contigs_h, d.contig_off, pl.contig_batch)
+    ctx.upload_reads(reads_h, sh.read_off)
+    ctx.build_stage(sh.batch_entry_off, sh.entries)
+    ctx.polish_stage(contigs_h, sh.contig_off, sh.contig_batch)
 
     # one step = filter build of every batch + the 4-round ntEdit chain over every contig, as one overlapped
     # pass (gp_pipeline_run: the edit kernel starts on a contig when its batch's filters are final); with
@@ -330,18 +501,90 @@ def ours(args, rank, world, local_rank):
         else:
             ctx.pipeline_run()
 
+    # ---- host gather in batch order (scripts/goldpolish-reaper:51-73): rank 0 receives every rank's polished
+    # records over NCCL (device staging buffers), and lays them out in contig order ----
+    gather_state = {}
+    if dist is not None and strong:
+        all_contigs = [np.concatenate([np.arange(b * w["bsize"], min((b + 1) * w["bsize"], d.n_contigs)) for b in bl])
+                       if len(bl) else np.zeros(0, np.int64) for bl in assignment]
+        max_bytes = max(int(clens[c].sum()) + int(clens[c].sum()) // 4 + 65536 for c in all_contigs)
+        max_contigs = max(len(c) for c in all_contigs)
+        gather_state.update(all_contigs=all_contigs, max_bytes=max_bytes, max_contigs=max_contigs,
+                            dev=torch.empty(max_bytes, dtype=torch.uint8, device="cuda"),
+                            lens=torch.zeros(max_contigs, dtype=torch.int64, device="cuda"))
+        if rank == 0:
+            gather_state["recv"] = [torch.empty(max_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            gather_state["recv_lens"] = [torch.zeros(max_contigs, dtype=torch.int64, device="cuda") for _ in range(world)]
+            gather_state["host"] = torch.empty((world, max_bytes), dtype=torch.uint8).pin_memory()
+
+    def gather(out, off, dropped):
+        """-> (sequence bytes in contig order, per-contig lengths with 0 for dropped records) on rank 0, None elsewhere"""
+        lens_local = np.where(dropped == 0, np.diff(off.astype(np.int64)), 0).astype(np.int64)
+        nbytes = int(off[-1])
+        if dist is None or not strong:
+            return np.asarray(out[:nbytes]), lens_local
+        g = gather_state
+        src = out if isinstance(out, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(out))
+        g["dev"][:nbytes].copy_(src[:nbytes], non_blocking=True)
+        g["lens"].zero_()
+        g["lens"][:len(lens_local)].copy_(torch.from_numpy(lens_local), non_blocking=True)
+        dist.gather(g["dev"], g.get("recv"), dst=0)
+        dist.gather(g["lens"], g.get("recv_lens"), dst=0)
+        if rank != 0:
+            return None
+        lens_all = np.zeros(d.n_contigs, dtype=np.int64)
+        rl = [t.cpu().numpy() for t in g["recv_lens"]]
+        for r in range(world):
+            lens_all[g["all_contigs"][r]] = rl[r][:len(g["all_contigs"][r])]
+            used = int(rl[r].sum())
+            g["host"][r, :used].copy_(g["recv"][r][:used], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        goff = np.concatenate([[0], np.cumsum(lens_all)])
+        final = np.empty(int(goff[-1]), dtype=np.uint8)
+        hostnp = g["host"].numpy()
+        for r in range(world):
+            cs = g["all_contigs"][r]
+            loff = np.concatenate([[0], np.cumsum(lens_all[cs])])
+            # consecutive contigs of one batch are consecutive on both sides: copy batch by batch
+            bs = w["bsize"]
+            i = 0
+            while i < len(cs):
+                j = min(i + bs - int(cs[i]) % bs, len(cs))
+                final[goff[cs[i]]:goff[cs[j - 1] + 1]] = hostnp[r, loff[i]:loff[j]]
+                i = j
+        return final, lens_all
+
+    e2e_info = {}
+
     def step_e2e():
-        ctx.upload_reads(reads_h, d.read_off)
-        ctx.build_stage(pl.batch_entry_off, pl.entries)
-        ctx.polish_stage(contigs_h, d.contig_off, pl.contig_batch)
+        ctx.upload_reads(reads_h, sh.read_off)
+        ctx.build_stage(sh.batch_entry_off, sh.entries)
+        ctx.polish_stage(contigs_h, sh.contig_off, sh.contig_batch)
         step_resident()
         ctx.build_fetch(out=bf_h)
-        return ctx.polish_fetch(out=out_h)
+        out, off, dropped = ctx.polish_fetch(out=out_h)
+        out, off, dropped, n_rej = apply_guard(sh, out, off, dropped, gp.guard_rejects)
+        e2e_info.update(rejected=n_rej, local=(out, off, dropped))
+        return gather(out, off, dropped)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x: int) -> int:
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
 
     # ---- device-resident timing ----
     for _ in range(args.warmup):
@@ -351,17 +594,16 @@ def ours(args, rank, world, local_rank):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    build_kernel_ms = 0.0
-    edit_kernel_ms = 0.0
     for _ in range(args.steps):
         step_resident()
     e1.record(stream)
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_step = allmax(e0.elapsed_time(e1) / args.steps)
     clocks = sampler.stop()
     st = ctx.stats()  # of the last step
     build_kernel_ms_overlapped = st["build_kernel_ms"]  # device timer when overlapped with the edit kernel
     edit_kernel_ms = st["edit_kernel_ms"]
+    launches_per_step = allsum(st["build_launches"] + st["polish_launches"])
     # roofline leg: the dominant (build) kernel alone, CUDA events on the launching stream around each launch
     ctx.build_run()
     alone = []
@@ -369,17 +611,7 @@ def ours(args, rank, world, local_rank):
         ctx.build_run()
         alone.append(ctx.stats()["build_kernel_ms"])
     build_kernel_ms = float(np.mean(alone))
-    ms_step = ms_total / args.steps
-    if dist is not None:
-        t = torch.tensor([ms_step], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item())
-    launches_per_step = st["build_launches"] + st["polish_launches"]
-    total_bases = draft_bases
-    if dist is not None:
-        tb = torch.tensor([draft_bases], device="cuda", dtype=torch.int64)
-        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
-        total_bases = int(tb.item())
+    total_bases = int(d.contig_off[-1]) if strong else allsum(sh.draft_bases)
 
     # ---- end to end through the C ABI with host buffers ----
     # the pinned destination of the filter payloads is named once: the build kernel writes each filter there as
@@ -387,107 +619,153 @@ def ours(args, rank, world, local_rank):
     ctx.build_output(bf_h)
     step_e2e()
     barrier()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
     t_e2e0 = time.perf_counter()
-    for _ in range(args.steps):
-        out, off, dropped = step_e2e()
+    for _ in range(e2e_steps):
+        gathered = step_e2e()
     barrier()
-    e2e_s = (time.perf_counter() - t_e2e0) / args.steps
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = allmax((time.perf_counter() - t_e2e0) / e2e_steps)
     st2 = ctx.stats()
-    h2d = int(d.read_off[-1]) + (d.n_reads + 1) * 8 * 2 + d.n_reads * 4 + (n_batches + 1) * 8 + len(pl.entries) * 8 \
-        + n_batches * 4 * 4 + draft_bases + (d.n_contigs + 1) * 8 * 3 + d.n_contigs * 8
-    d2h = n_batches * 4 * gp.BF_BYTES + int(off[-1]) + d.n_contigs * 5 + 4
-
-    # guard (scripts/goldpolish-ntedit:31-40) on the fetched result: host rule, counted for info
-    rejected = 0
-    bs = WORKLOAD["bsize"]
-    for b in range(n_batches):
-        cs = range(b * bs, min((b + 1) * bs, d.n_contigs))
-        in_sz = sum(len(d.contig_name(c)) + 3 + int(d.contig_off[c + 1] - d.contig_off[c]) for c in cs)
-        out_sz = sum(len(d.contig_name(c)) + 3 + int(off[c + 1] - off[c]) for c in cs if not dropped[c])
-        rejected += int(gp.guard_rejects(in_sz, out_sz))
+    if st2["polish_reruns"]:
+        log(f"[rank {rank}] note: gp_polish_fetch re-ran the polish {st2['polish_reruns']} time(s) (buffer growth / watchdog); "
+            "the timed steps include those re-runs")
+    out_l, off_l, dropped_l = e2e_info["local"]
+    h2d = allsum(int(sh.read_off[-1]) + (sh.n_reads + 1) * 8 * 2 + sh.n_reads * 4 + (n_batches + 1) * 8 + len(sh.entries) * 8
+                 + n_batches * 4 * 4 + sh.draft_bases + (len(sh.contigs) + 1) * 8 * 3 + len(sh.contigs) * 8)
+    d2h = allsum(n_batches * 4 * gp.BF_BYTES + int(off_l[-1]) + len(sh.contigs) * 5 + 4)
+    rejected = allsum(e2e_info["rejected"])
+    gathered_sha = None
+    if rank == 0:
+        seqs, lens_all = gathered
+        hsh = hashlib.sha256()
+        hsh.update(np.ascontiguousarray(lens_all, dtype=np.int64).tobytes())
+        hsh.update(np.ascontiguousarray(seqs).tobytes())
+        gathered_sha = hsh.hexdigest()
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         kops = st["kmer_ops"]
-        achieved = kops * ALGO_BYTES_PER_KMER_OP / (build_kernel_ms * 1e-3) / 1e9 if build_kernel_ms > 0 else 0.0
+        ops_per_s = kops / (build_kernel_ms * 1e-3) if build_kernel_ms > 0 else 0.0
+        achieved = ops_per_s * ALGO_BYTES_PER_KMER_OP / 1e9
         kname = {1: "gp::build_filters_kernel (one warp per stream, counters in HBM)",
                  2: "gp::build_filters_levels_kernel (level-synchronous rounds, timestamps in L2)"}.get(st["build_kernel"], "?")
+        read_bases_local = int(np.diff(sh.read_off)[sh.entries["read_id"]].sum())
+        hashing_gbs = read_bases_local * 4 * 0.375 / (build_kernel_ms * 1e-3) / 1e9 if build_kernel_ms > 0 else 0.0
         roof = {"bound": "hbm", "achieved": achieved, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
                 "frac": achieved / float(peaks["hbm_gbs"]), "traffic": ncu_traffic(kops),
-                "traffic_source": "profiles/build_kernel_dram.json (ncu dram__bytes_read+write per k-mer op at 1 Mbp) x k-mer ops of this launch",
+                "traffic_source": "profiles/build_kernel_dram.json (ncu dram__bytes_read+write per k-mer op) x k-mer ops of this launch",
                 "kernel": kname, "kernel_ms": build_kernel_ms, "kmer_ops_per_launch": kops,
                 "algorithmic_bytes_per_kmer_op": ALGO_BYTES_PER_KMER_OP, "peak_source": peak_src,
-                "kmer_ops_per_s": kops / (build_kernel_ms * 1e-3) if build_kernel_ms > 0 else 0.0,
-                "build_slots": st["build_slots"], "kernel_ms_inside_step": build_kernel_ms_overlapped,
-                "edit_kernel_ms": edit_kernel_ms,
+                "kmer_ops_per_s": ops_per_s, "streams_in_flight": st["build_slots"],
+                "kernel_ms_inside_step": build_kernel_ms_overlapped, "edit_kernel_ms": edit_kernel_ms,
+                "frac_of_hbm_copy_peak": achieved / float(peaks["hbm_gbs"]), "hbm_copy_peak_gbs": float(peaks["hbm_gbs"]),
+                # the sequential side of the same kernel: every entry's read is streamed once per k, 2 bits per base
+                # + 1 mask bit per base; three orders of magnitude below the copy peak -- the kernel lives on random
+                # 32-byte-sector touches, not on this stream
+                "hashing_stream_gbs": hashing_gbs, "hashing_stream_frac_of_hbm_copy_peak": hashing_gbs / float(peaks["hbm_gbs"]),
                 "overlap": "edit kernel runs beside the build kernel (its span includes waiting for filters)" if not args.separate
                            else "none (--separate)"}
         if args.roof:
             # measured random-access roofs (sector touches / s), same access shapes as the kernels:
             #   hbm : private 10 MiB counter regions per warp (the one-warp-per-stream kernel's mix)
             #   l2_ld / l2_red : random 4-byte loads / atomicMin over one shared 40 MiB array
-            # a k-mer op needs at least 4 loads + 4 atomics -> ops/s roof = 1 / (4/ld + 4/red)
+            #   l2_mix : rounds of 4 loads alternating with rounds of 4 atomicMin in the same launch (they overlap)
+            # a k-mer op needs at least 4 loads + 4 atomics -> ops/s roof = 1 / (4/ld + 4/red); the overlapped
+            # variant (l2_mix / 8) is the higher roof
             try:
                 r = {}
-                for name, mode, region in (("hbm", "0", gp.CBF_BYTES), ("l2_ld", "5", 4096), ("l2_red", "4", 4096)):
+                for name, mode, region in (("hbm", "0", gp.CBF_BYTES), ("l2_ld", "5", 4096), ("l2_red", "4", 4096), ("l2_mix", "3", 4096)):
                     os.environ["GP_ROOF_MODE"] = mode
                     r[name], _ = ctx.roof_microbench(148 * 24, 4000 if mode != "0" else 2000, region)
                 os.environ.pop("GP_ROOF_MODE", None)
                 roof["random_access_roof_sectors_per_s"] = r
                 if st["build_kernel"] == 2:
                     ops_roof = 1.0 / (4.0 / r["l2_ld"] + 4.0 / r["l2_red"])
+                    roof["bound"] = "l2_random_access"
+                    roof["peak_source"] = ("measured live: gp_roof_microbench, random 4-byte loads and atomicMin over one 40 MiB array in "
+                                           "L2 (the kernel's access shape); peak = 1 / (4/loads_per_s + 4/atomics_per_s) k-mer ops/s x 256 B")
                 else:
                     ops_roof = r["hbm"] / 8.0
+                    roof["bound"] = "hbm_random_access"
+                    roof["peak_source"] = "measured live: gp_roof_microbench, private 10 MiB counter regions in HBM; peak = sectors_per_s / 8 x 256 B"
+                roof["peak"] = ops_roof * ALGO_BYTES_PER_KMER_OP / 1e9
+                roof["frac"] = ops_per_s / ops_roof if ops_roof else None
                 roof["random_access_roof_kmer_ops_per_s"] = ops_roof
-                roof["frac_of_random_access_roof"] = roof["kmer_ops_per_s"] / ops_roof if ops_roof else None
+                roof["frac_of_random_access_roof"] = roof["frac"]
+                roof["overlapped_roof_kmer_ops_per_s"] = r["l2_mix"] / 8.0
+                roof["frac_of_overlapped_roof"] = ops_per_s / (r["l2_mix"] / 8.0) if r["l2_mix"] else None
                 # against the HBM random-access roof the north star names (8 touches per op at the HBM sector rate):
                 # above 1 because the level-synchronous kernel keeps the touched state in L2
-                roof["frac_of_hbm_random_access_roof"] = roof["kmer_ops_per_s"] * 8.0 / r["hbm"] if r["hbm"] else None
+                roof["frac_of_hbm_random_access_roof"] = ops_per_s * 8.0 / r["hbm"] if r["hbm"] else None
             except Exception as e:  # measurement aid only
                 roof["random_access_roof_error"] = str(e)
-        cpu = None
-        if args.cpu_baseline:
-            work = tempfile.mkdtemp(prefix="gp_cpu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        cpu, parity = None, None
+        if args.cpu_baseline and world == 1:
+            rs = None
             try:
                 threads = os.cpu_count() or 1
-                from oracle import ref_driver as rd
-                if rd.ref_available():
-                    write_files(d, work)
-                nb = min(n_batches, max(threads * args.ref_batches_per_core, 8))
-                r = run_reference_sample(d, pl, nb, threads, work)
+                nb = sample_batches(args, d, threads)
+                rs = ReferenceSample(args, d, nb, threads)
+                r = rs.run()
                 tt = r["seconds_build"] + r["seconds_edit"]
                 cpu = {"value": r["bases"] / 1e6 / tt, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                       "sample": f"first {r['batches']} of {n_batches} batches ({r['bases']} draft bases): "
-                                 f"build {r['seconds_build']:.2f}s + edit {r['seconds_edit']:.2f}s"}
+                       "sample": f"first {r['batches']} of {nb_total} batches ({r['bases']} of {int(d.contig_off[-1])} draft bases), "
+                                 f"one pass: build {r['seconds_build']:.2f}s + edit {r['seconds_edit']:.2f}s"}
+                if r["kind"] == "reference":
+                    # parity at the benched size: what the reference's own code wrote for the sampled batches against
+                    # what the GPU produced for the same batches in the timed end-to-end step
+                    bf_np = bf_h.numpy()
+                    bf_equal, fasta_equal, n_rec = True, True, 0
+                    bs = w["bsize"]
+                    for b in range(r["batches"]):
+                        if not np.array_equal(rs.filters(b), bf_np[b]):
+                            bf_equal = False
+                            log(f"PARITY: filter payloads of batch {b} differ from the reference")
+                        ours_recs = []
+                        for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
+                            if not dropped_l[c]:
+                                ours_recs.append((d.contig_name(c), np.asarray(out_l[int(off_l[c]):int(off_l[c + 1])]).tobytes()))
+                        ref_recs = rs.polished(b)
+                        n_rec += len(ref_recs)
+                        if ours_recs != ref_recs:
+                            fasta_equal = False
+                            log(f"PARITY: polished records of batch {b} differ from the reference")
+                    parity = {"batches": r["batches"], "records": n_rec, "bf_equal": bf_equal, "fasta_equal": fasta_equal,
+                              "against": "oracle/_ref (the reference's own serve_batch + ntEdit chain + guard) on the same batches"}
             except Exception as e:
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "error", "sample": str(e)}
             finally:
-                shutil.rmtree(work, ignore_errors=True)
+                if rs is not None:
+                    rs.close()
         line = {
             "metric": METRIC, "value": total_bases / 1e6 / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer",
+            "scaling": w["scaling"], "vs_baseline": None, "dtype": "u8/u64 integer",
             "data": "synthetic (seeded simulator, sim/gpsim.c)",
-            "config": dict(WORKLOAD, genome_len=genome, per_gpu_draft_bases=draft_bases, batches_per_gpu=n_batches,
-                           l2="inputs larger than L2: every step reads %.0f MB of packed reads + step anchors and writes %.2f GB of filters "
-                              "(126 MB L2); the kernel's own 80 MiB of timestamps are L2-resident by design"
-                              % ((int(d.read_off[-1]) * 0.375 + int(d.read_off[-1]) / 32 * 4 * 2) / 1e6, n_batches * 4 * gp.BF_BYTES / 1e9),
-                           guard_rejected_batches=rejected, parallelism=f"batches sharded over {world} GPU(s), no collective"),
+            "config": config_of(args),
+            "detail": {"total_draft_bases": total_bases, "batches_total": nb_total, "batches_rank0": n_batches,
+                       "draft_bases_rank0": sh.draft_bases, "guard_rejected_batches": rejected,
+                       "parallelism": (f"batches of one data set sharded over {world} GPU(s) by LPT on read bases, no collective in "
+                                       "the data path; rank 0 gathers the polished records (NCCL gather of device staging "
+                                       "buffers + host layout in contig order) inside the e2e step") if strong else
+                                      f"{world} independent data sets, one per GPU, no collective",
+                       "gathered_sha256": gathered_sha},
             "clocks": clocks,
             "e2e": {"value": total_bases / 1e6 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-                    "includes": "H2D reads+pack, H2D contigs, build + polish, D2H filter payloads, D2H polished"},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                    "includes": "H2D reads+pack, H2D contigs, build + polish, D2H filter payloads, D2H polished, guard"
+                                + (", gather on rank 0" if strong and world > 1 else "")},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "parity": parity,
             "stats": {k: st2[k] for k in ("kmer_ops", "serial_kmers", "triggers", "edits", "masked", "rollbacks",
-                                          "build_ms", "polish_ms", "pack_ms", "build_kernel_ms", "edit_kernel_ms")},
+                                          "build_ms", "polish_ms", "pack_ms", "build_kernel_ms", "edit_kernel_ms", "polish_reruns")},
         }
         emit(line)
+        if parity is not None and not (parity["bf_equal"] and parity["fasta_equal"]):
+            ctx.close()
+            raise SystemExit("bench.py: PARITY FAILURE against the reference on the sampled batches (see stderr)")
     ctx.close()
     if dist is not None:
         dist.barrier()
@@ -500,16 +778,24 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genome-len", type=int, default=WORKLOAD["genome_len"])
+    ap.add_argument("--config", type=int, default=3, choices=sorted(WORKLOADS))
+    ap.add_argument("--genome-len", type=int, default=None, help="override the workload's draft size (experiments)")
+    ap.add_argument("--coverage", type=float, default=None)
+    ap.add_argument("--bsize", type=int, default=None, help="contigs per batch (parity/scale experiments)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-roof", dest="roof", action="store_false")
-    ap.add_argument("--ref-batches-per-core", type=int, default=2)
-    ap.add_argument("--bsize", type=int, default=WORKLOAD["bsize"], help="contigs per batch (parity/scale experiments)")
-    ap.add_argument("--coverage", type=float, default=WORKLOAD["coverage"])
+    ap.add_argument("--ref-bases-per-core", type=float, default=76000.0,
+                    help="draft bases per host core in one CPU step (reference arm / cpu_baseline sample)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="end-to-end steps timed (at most --steps)")
     ap.add_argument("--separate", action="store_true", help="build, then polish (no overlap of the two kernels)")
     args = ap.parse_args()
-    WORKLOAD["bsize"] = args.bsize
-    WORKLOAD["coverage"] = args.coverage
+    w = WORKLOADS[args.config]
+    if args.genome_len is not None:
+        w["genome_len"] = args.genome_len
+    if args.coverage is not None:
+        w["coverage"] = args.coverage
+    if args.bsize is not None:
+        w["bsize"] = args.bsize
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -36,18 +36,56 @@ class BatchPlan:
     kmer_ops_bases: int           # sum of read lengths over entries (k-mer ops ~= 4x this)
 
 
+MX_THRESHOLD_MIN, MX_THRESHOLD_MAX = 1, 30  # src/goldpolish_targeted_bfs.cpp:34-35
+
+
+def filter_ntlink(reads, mx, target_len, mx_max_per_10kbp, mx_min=MX_THRESHOLD_MIN, mx_max=MX_THRESHOLD_MAX):
+    """AllMappings::filter for one target (src/mappings.cpp:230-320): at most ceil(L * x / 10000) reads are wanted;
+    the smallest minimizer threshold in (mx_min, mx_max] that leaves no more than that (binary search), reads kept
+    in their original order."""
+    import math
+    if not reads:
+        return reads
+    max_reads = int(math.ceil(float(target_len) * mx_max_per_10kbp / 10000.0))
+    count_ge = lambda t: sum(1 for m in mx if m >= t)
+    lo, hi = mx_min, mx_max
+    if len(reads) <= max_reads:
+        thr = lo
+    elif count_ge(hi) > max_reads:
+        thr = hi
+    else:
+        while hi - lo > 1:
+            mid = (hi + lo) // 2
+            if count_ge(mid) > max_reads:
+                lo = mid
+            else:
+                hi = mid
+        thr = hi
+    return [r for r, m in zip(reads, mx) if m >= thr]
+
+
 def plan_batches(contig_lens, contig_names, read_names, read_phred, read_lens, map_read, map_contig,
-                 bsize=1, subsample_max_per_10kbp=40.0, name_bytes=True) -> BatchPlan:
+                 bsize=1, subsample_max_per_10kbp=40.0, name_bytes=True, map_mx=None, mx_max_per_10kbp=150.0) -> BatchPlan:
     """Batches of `bsize` consecutive contigs (scripts/goldpolish:344-354), each contig's
     mapped reads de-duplicated in first-seen order (mappings.cpp:65-70), selected and ordered
-    as serve_batch does."""
+    as serve_batch does.  With `map_mx` (ntLink-style triples: minimizers per mapping) rows below MX_THRESHOLD_MIN
+    are dropped at load (mappings.cpp:96-99) and every target goes through the minimizer filter first."""
     n_contigs = len(contig_lens)
     per_contig: list[list[int]] = [[] for _ in range(n_contigs)]
+    per_contig_mx: list[list[int]] = [[] for _ in range(n_contigs)]
     seen: list[set] = [set() for _ in range(n_contigs)]
-    for r, c in zip(map_read.tolist(), map_contig.tolist()):
+    mxs = map_mx.tolist() if map_mx is not None else None
+    for i, (r, c) in enumerate(zip(map_read.tolist(), map_contig.tolist())):
+        if mxs is not None and mxs[i] < MX_THRESHOLD_MIN:
+            continue
         if r not in seen[c]:
             seen[c].add(r)
             per_contig[c].append(r)
+            if mxs is not None:
+                per_contig_mx[c].append(mxs[i])
+    if mxs is not None:
+        for c in range(n_contigs):
+            per_contig[c] = filter_ntlink(per_contig[c], per_contig_mx[c], int(contig_lens[c]), mx_max_per_10kbp)
     names_key = [n.encode() if name_bytes and isinstance(n, str) else n for n in read_names]
     off = [0]
     ents = []

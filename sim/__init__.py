@@ -93,6 +93,10 @@ class SimData:
     truth: np.ndarray
     fastq: bool
     params: dict = field(default_factory=dict)
+    read_qchar: np.ndarray = None   # FASTQ: quality character of all but the last base of a read ...
+    read_qlast: np.ndarray = None   # ... and of its last base (the index ignores it, src/seqindex.cpp:45)
+    map_strand: np.ndarray = None
+    map_overlap: np.ndarray = None
 
     @property
     def n_contigs(self) -> int:
@@ -146,6 +150,8 @@ def simulate(write_dir: str | None = None, **kw) -> SimData:
             truth=_arr(s.truth, s.truth_len, np.uint8),
             fastq=bool(s.fastq),
             params={k: getattr(p, k) for k, _ in _Params._fields_},
+            read_qchar=_arr(s.read_qchar, nr, np.uint8), read_qlast=_arr(s.read_qlast, nr, np.uint8),
+            map_strand=_arr(s.map_strand, nm, np.uint8), map_overlap=_arr(s.map_overlap, nm, np.uint32),
         )
         if write_dir is not None:
             os.makedirs(write_dir, exist_ok=True)
@@ -159,3 +165,40 @@ def simulate(write_dir: str | None = None, **kw) -> SimData:
     finally:
         lib.gpsim_free(g)
     return d
+
+
+def write_subset(d: SimData, contigs, write_dir: str) -> dict:
+    """Write draft.fa, reads.fq|reads.fa, mappings.paf and mappings.tsv for a SUBSET of the contigs (and the reads
+    mapped to them), byte-compatible with gpsim_write_files: what the reference's tools see for these contigs is
+    what they would see in the full data set (targets are independent).  Returns the paths."""
+    os.makedirs(write_dir, exist_ok=True)
+    contigs = [int(c) for c in contigs]
+    cset = np.zeros(d.n_contigs, dtype=bool)
+    cset[contigs] = True
+    msel = np.nonzero(cset[d.map_contig])[0]
+    reads = np.unique(d.map_read[msel])
+    paths = {"draft": os.path.join(write_dir, "draft.fa"),
+             "reads": os.path.join(write_dir, "reads.fq" if d.fastq else "reads.fa"),
+             "paf": os.path.join(write_dir, "mappings.paf"), "tsv": os.path.join(write_dir, "mappings.tsv")}
+    with open(paths["draft"], "wb") as f:
+        for c in contigs:
+            f.write(b">" + d.contig_name(c).encode() + b"\n" + d.contig(c) + b"\n")
+    with open(paths["reads"], "wb") as f:
+        for r in reads.tolist():
+            seq = d.read(r)
+            if d.fastq:
+                q = bytes([int(d.read_qchar[r])]) * (len(seq) - 1) + bytes([int(d.read_qlast[r])]) if seq else b""
+                f.write(b"@%s len=%d\n" % (d.read_name(r).encode(), len(seq)) + seq + b"\n+\n" + q + b"\n")
+            else:
+                f.write(b">" + d.read_name(r).encode() + b"\n" + seq + b"\n")
+    rlen = np.diff(d.read_off)
+    clen = np.diff(d.contig_off)
+    with open(paths["paf"], "w") as f, open(paths["tsv"], "w") as g:
+        for m in msel.tolist():
+            r, c = int(d.map_read[m]), int(d.map_contig[m])
+            ov = int(d.map_overlap[m])
+            f.write(f"{d.read_name(r)}\t{int(rlen[r])}\t0\t{int(rlen[r])}\t{'-' if d.map_strand[m] else '+'}\t"
+                    f"{d.contig_name(c)}\t{int(clen[c])}\t{int(d.map_tstart[m])}\t{int(d.map_tend[m])}\t"
+                    f"{int(ov * 0.9)}\t{ov}\t60\n")
+            g.write(f"{d.read_name(r)} {d.contig_name(c)} {int(d.map_mx[m])}\n")
+    return paths
