@@ -203,129 +203,6 @@ def sample_batches(args, d, threads: int) -> int:
     return max(min(nb_total, max(nb, threads, 8)), 1)
 
 
-class ReferenceSample:
-    """The first nb batches of the workload as files the reference's tools read, and one timed pass over them:
-    the reference's serve_batch (filter build) for every batch on `threads` OpenMP threads, then its ntEdit chain +
-    guard as `threads` single-thread workers (scripts/goldpolish runs ntedit-gr with -t1 per batch)."""
-
-    def __init__(self, args, d, nb: int, threads: int):
-        import sim
-        from oracle import ref_driver as rd
-        self.w = WORKLOADS[args.config]
-        self.d, self.nb, self.threads, self.rd = d, nb, threads, rd
-        self.kind = "reference" if rd.ref_available() else "port"
-        bs = self.w["bsize"]
-        self.contigs = list(range(0, min(nb * bs, d.n_contigs)))
-        self.bases = int(sum(int(d.contig_off[c + 1] - d.contig_off[c]) for c in self.contigs))
-        self.work = tempfile.mkdtemp(prefix="gp_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-        if self.kind == "reference":
-            p = sim.write_subset(d, self.contigs, self.work)
-            self.draft, self.reads = p["draft"], p["reads"]
-            self.maps = p["paf"] if self.w["mappings"] == "paf" else p["tsv"]
-            rd.run_index(self.draft, self.draft + ".index")
-            rd.run_index(self.reads, self.reads + ".index")
-            self.bdir = os.path.join(self.work, "bfs")
-            for b in range(nb):
-                bd = os.path.join(self.work, f"batch{b}")
-                os.makedirs(bd, exist_ok=True)
-                with open(os.path.join(bd, "batch.fa"), "wb") as f:
-                    for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
-                        f.write(b">" + d.contig_name(c).encode() + b"\n" + d.contig(c) + b"\n")
-
-    def close(self):
-        shutil.rmtree(self.work, ignore_errors=True)
-
-    def run(self) -> dict:
-        if self.kind == "port":
-            return self._run_port()
-        import ctypes as C
-        d, nb, bs, threads = self.d, self.nb, self.w["bsize"], self.threads
-        h = self.rd.harness()
-        shutil.rmtree(self.bdir, ignore_errors=True)
-        os.makedirs(self.bdir)
-        names, ids_files = [], []
-        for b in range(nb):
-            names.append(str(b).encode())
-            p = os.path.join(self.bdir, f"{b}.ids")
-            with open(p, "w") as f:
-                for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
-                    f.write(d.contig_name(c) + "\n")
-            ids_files.append(p.encode())
-        ks = (C.c_uint * 4)(*KS)
-        cwd = os.getcwd()
-        os.chdir(self.bdir)
-        os.environ["GP_ORACLE_QUIET"] = "1"
-        try:
-            t_build = h.ref_serve_batches(self.draft.encode(), (self.draft + ".index").encode(), self.maps.encode(),
-                                          self.reads.encode(), (self.reads + ".index").encode(), self.w["mx_max"],
-                                          self.w["subsample_max"], threads, ks, 4,
-                                          (C.c_char_p * nb)(*names), (C.c_char_p * nb)(*ids_files), nb)
-        finally:
-            os.chdir(cwd)
-        if t_build < 0:
-            raise RuntimeError("reference serve_batches failed")
-        bases_arr = (C.c_char_p * nb)(*[os.path.join(self.work, f"batch{b}", "batch").encode() for b in range(nb)])
-        bfs_flat = (C.c_char_p * (nb * 4))(*[os.path.join(self.bdir, f"{b}-k{k}.bf").encode() for b in range(nb) for k in KS])
-        outs = (C.c_char_p * nb)(*[os.path.join(self.work, f"batch{b}", "batch.ntedited.fa").encode() for b in range(nb)])
-        t_edit = h.ref_ntedit_chain_many(bases_arr, bfs_flat, ks, 4, outs, nb, threads)
-        if t_edit < 0:
-            raise RuntimeError("reference ntedit chain failed")
-        return dict(seconds_build=t_build, seconds_edit=t_edit, bases=self.bases, kind="reference", cores=threads, batches=nb)
-
-    # ---- what the reference produced in the last run(), for the parity check ----
-    def filters(self, b: int) -> np.ndarray:
-        """[4, BF_BYTES] payloads of batch b (btllib files: payload = the last `bytes` bytes)."""
-        out = np.empty((4, BF_BYTES), dtype=np.uint8)
-        for i, k in enumerate(KS):
-            with open(os.path.join(self.bdir, f"{b}-k{k}.bf"), "rb") as f:
-                data = f.read()
-            out[i] = np.frombuffer(data[len(data) - BF_BYTES:], dtype=np.uint8)
-        return out
-
-    def polished(self, b: int) -> list[tuple[str, bytes]]:
-        """(name, sequence) records of batch.ntedited.fa of batch b (after the reference's 0.75 guard)."""
-        recs = []
-        with open(os.path.join(self.work, f"batch{b}", "batch.ntedited.fa"), "rb") as f:
-            lines = f.read().split(b"\n")
-        for i in range(0, len(lines) - 1, 2):
-            if lines[i].startswith(b">"):
-                recs.append((lines[i][1:].decode().split()[0], lines[i + 1]))
-        return recs
-
-    def _run_port(self) -> dict:
-        """No compiled reference on this machine: the single-thread C restatement (oracle/gp_oracle.c)."""
-        from oracle import oracle_lib as ol
-        d, bs = self.d, self.w["bsize"]
-        rlens = np.diff(d.read_off)
-        per_contig = {}
-        for r, c in zip(d.map_read.tolist(), d.map_contig.tolist()):
-            if c < len(self.contigs) and r not in per_contig.setdefault(c, {}):
-                per_contig[c][r] = True
-        t0 = time.perf_counter()
-        fsets = {}
-        for b in range(self.nb):
-            fs = ol.FilterSet()
-            for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
-                ids = list(per_contig.get(c, {}))
-                if not ids:
-                    continue
-                chosen, thr = ol.select_reads([d.read_name(i) for i in ids], [d.read_phred[i] for i in ids],
-                                              [int(rlens[i]) for i in ids], int(d.contig_off[c + 1] - d.contig_off[c]),
-                                              self.w["subsample_max"])
-                for j in chosen:
-                    fs.add_read(d.read(ids[j]), thr)
-            fsets[b] = fs
-        t1 = time.perf_counter()
-        for c in self.contigs:
-            cur = d.contig(c)
-            for ki, k in enumerate(KS):
-                cur, _ = ol.ntedit_contig(cur, fsets[c // bs].bfs[ki], k)
-                if cur is None:
-                    break
-        t2 = time.perf_counter()
-        return dict(seconds_build=t1 - t0, seconds_edit=t2 - t1, bases=self.bases, kind="port", cores=1, batches=self.nb)
-
-
 def reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -334,7 +211,8 @@ def reference_arm(args, rank, world):
     nb_total = n_batches_of(d, w["bsize"])
     threads = os.cpu_count() or 1
     nb = sample_batches(args, d, threads)
-    rs = ReferenceSample(args, d, nb, threads)
+    from oracle.ref_sample import ReferenceSample
+    rs = ReferenceSample(WORKLOADS[args.config], d, range(nb), threads)
     try:
         times, res = [], None
         for it in range(args.warmup + args.steps):
@@ -705,13 +583,14 @@ def ours(args, rank, world, local_rank):
             try:
                 threads = os.cpu_count() or 1
                 nb = sample_batches(args, d, threads)
-                rs = ReferenceSample(args, d, nb, threads)
+                from oracle.ref_sample import ReferenceSample
+                rs = ReferenceSample(w, d, range(nb), threads)
                 r = rs.run()
                 tt = r["seconds_build"] + r["seconds_edit"]
                 cpu = {"value": r["bases"] / 1e6 / tt, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                        "sample": f"first {r['batches']} of {nb_total} batches ({r['bases']} of {int(d.contig_off[-1])} draft bases), "
                                  f"one pass: build {r['seconds_build']:.2f}s + edit {r['seconds_edit']:.2f}s"}
-                if r["kind"] == "reference":
+                if r["kind"] in ("reference", "port"):
                     # parity at the benched size: what the reference's own code wrote for the sampled batches against
                     # what the GPU produced for the same batches in the timed end-to-end step
                     bf_np = bf_h.numpy()
@@ -731,7 +610,8 @@ def ours(args, rank, world, local_rank):
                             fasta_equal = False
                             log(f"PARITY: polished records of batch {b} differ from the reference")
                     parity = {"batches": r["batches"], "records": n_rec, "bf_equal": bf_equal, "fasta_equal": fasta_equal,
-                              "against": "oracle/_ref (the reference's own serve_batch + ntEdit chain + guard) on the same batches"}
+                              "against": ("oracle/_ref (the reference's own serve_batch + ntEdit chain + guard)" if r["kind"] == "reference"
+                                          else "oracle/gp_oracle.c (C restatement; oracle/_ref is not built on this machine)") + " on the same batches"}
             except Exception as e:
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "error", "sample": str(e)}
             finally:

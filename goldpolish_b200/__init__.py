@@ -5,9 +5,9 @@ The product is the CUDA shared library ``libgoldpolish_b200.so`` behind the C AB
 package is the thin ctypes binding used by the tests, ``bench.py`` and Python callers; it holds
 no compute of its own and raises if the CUDA library is missing -- there is no CPU path.
 """
-from .api import (BF_BYTES, CBF_BYTES, DEFAULT_KS, Context, GpError, guard_rejects, kmer_threshold,
+from .api import (BF_BYTES, CBF_BYTES, DEFAULT_KS, Context, GpError, flagged_bed, guard_rejects, kmer_threshold,
                   lib_path, load_library, mappings_cap)
 from .host import BatchPlan, plan_batches, select_reads_for_target
 
-__all__ = ["BF_BYTES", "CBF_BYTES", "DEFAULT_KS", "Context", "GpError", "guard_rejects", "kmer_threshold",
+__all__ = ["BF_BYTES", "CBF_BYTES", "DEFAULT_KS", "Context", "GpError", "flagged_bed", "guard_rejects", "kmer_threshold",
            "lib_path", "load_library", "mappings_cap", "BatchPlan", "plan_batches", "select_reads_for_target"]

@@ -52,7 +52,7 @@ EXPORTS = ["gp_default_config", "gp_ctx_create", "gp_ctx_destroy", "gp_last_erro
            "gp_build_run", "gp_build_fetch", "gp_build_fetch_cbf", "gp_filters_load", "gp_polish",
            "gp_polish_stage", "gp_polish_run", "gp_polish_fetch", "gp_kmer_threshold", "gp_mappings_cap",
            "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep", "gp_build_output_host", "gp_host_alloc", "gp_host_free",
-           "gp_build_cta_times"]
+           "gp_build_cta_times", "gp_flagged_bed", "gp_debug_nthash"]
 
 
 def load_library():
@@ -96,6 +96,9 @@ def load_library():
     l.gp_roof_microbench.argtypes = [vp, u32, u32, u64, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     l.gp_build_round_times.argtypes = [vp, C.POINTER(u64)]
     l.gp_pipeline_run.argtypes = [vp]
+    l.gp_debug_nthash.argtypes = [vp, u64, u32, vp, vp, u64, C.POINTER(u64)]
+    l.gp_flagged_bed.argtypes = [vp, vp, u32, vp, vp, vp, u64]
+    l.gp_flagged_bed.restype = u64
     l.gp_build_cta_times.argtypes = [vp, vp, u32, C.POINTER(u32)]
     l.gp_build_output_host.argtypes = [vp, vp]
     l.gp_host_alloc.argtypes = [u64]
@@ -117,6 +120,24 @@ def mappings_cap(target_len: int, subsample_max_per_10kbp: float) -> int:
 
 def guard_rejects(input_bytes: int, output_bytes: int) -> bool:
     return bool(load_library().gp_guard_rejects(int(input_bytes), int(output_bytes)))
+
+
+def flagged_bed(seqs, offsets, names=None):
+    """Flagged (soft-masked, ntedit.cpp:1131-1146) regions of polished records as BED rows (name, start, end):
+    one per maximal run of lower-case letters, 0-based half-open.  `names` defaults to the record indices."""
+    l = load_library()
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(off) - 1
+    cap = 1024
+    while True:
+        rec = np.zeros(cap, dtype=np.uint32)
+        st = np.zeros(cap, dtype=np.uint64)
+        en = np.zeros(cap, dtype=np.uint64)
+        got = int(l.gp_flagged_bed(_ptr(seqs), _ptr(off), n, _ptr(rec), _ptr(st), _ptr(en), cap))
+        if got <= cap:
+            break
+        cap = got
+    return [((names[int(rec[i])] if names is not None else int(rec[i])), int(st[i]), int(en[i])) for i in range(got)]
 
 
 def _ptr(a):
@@ -294,6 +315,22 @@ class Context:
         return r
 
     INTERVAL_KINDS = ("clear", "round0", "level1", "late", "round0+late", "level1+late")
+
+    def debug_nthash(self, read_id: int, k: int):
+        """(positions, hashes[n, 4]) of the valid k-mers of an uploaded read, as the device computes them."""
+        n = C.c_uint64()
+        cap = 1 << 16
+        while True:
+            hs = np.zeros((cap, 4), dtype=np.uint64)
+            valid = np.zeros(cap, dtype=np.uint8)
+            rc = self._l.gp_debug_nthash(self._h, read_id, k, _ptr(hs), _ptr(valid), cap, C.byref(n))
+            if rc == -1 and n.value > cap:
+                cap = n.value
+                continue
+            self._ck(rc)
+            break
+        pos = np.nonzero(valid[:n.value])[0]
+        return pos, hs[pos]
 
     def build_cta_times(self) -> np.ndarray:
         """[n_ctas, 6 kinds, 3] ns / counts of every CTA (needs GP_LEVEL_CTA_TIMES=1 during the build)."""

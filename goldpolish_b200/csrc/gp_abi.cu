@@ -683,6 +683,34 @@ int gp_build_round_times(gp_ctx* ctx, uint64_t out[32])
   return GP_OK;
 }
 
+int gp_debug_nthash(gp_ctx* ctx, uint64_t read_id, uint32_t k, uint64_t* hashes, uint8_t* valid, uint64_t cap_positions,
+                    uint64_t* n_positions)
+{
+  if (!ctx || !hashes || !valid || !n_positions) return GP_ERR_ARG;
+  if (read_id >= ctx->n_reads) GP_FAIL(ctx, GP_ERR_ARG, "read_id out of range (upload reads first)");
+  if (k < 4 || k > 32 || k % 4 != 0) GP_FAIL(ctx, GP_ERR_ARG, "k must be a multiple of 4 within 4..32");
+  cudaSetDevice(ctx->cfg.device);
+  const uint32_t len = ctx->h_read_len[read_id];
+  const uint64_t npos = len >= k ? uint64_t(len) - k + 1 : 0;
+  *n_positions = npos;
+  if (npos == 0) return GP_OK;
+  if (npos > cap_positions) GP_FAIL(ctx, GP_ERR_ARG, "gp_debug_nthash: output too small (needed positions are in n_positions)");
+  uint64_t boff = 0;
+  GP_CUDA(ctx, cudaMemcpy(&boff, ctx->d_read_boff.as<uint64_t>() + read_id, 8, cudaMemcpyDeviceToHost));
+  DevBuf dh, dv;
+  GP_CUDA(ctx, dh.ensure(npos * 32));
+  cudaError_t e = dv.ensure(npos);
+  if (e != cudaSuccess) { dh.release(); GP_CUDA(ctx, e); }
+  gp::launch_debug_nthash(ctx->d_pk.as<uint64_t>(), ctx->d_nm.as<uint32_t>(), boff >> 5, len, k, dh.as<uint64_t>(), dv.as<uint8_t>(), ctx->stream);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hashes, dh.p, npos * 32, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(valid, dv.p, npos, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dh.release(); dv.release();
+  GP_CUDA(ctx, e);
+  return GP_OK;
+}
+
 int gp_build_cta_times(gp_ctx* ctx, uint64_t* out, uint32_t cap_ctas, uint32_t* n_ctas)
 {
   if (!ctx || !out || !n_ctas) return GP_ERR_ARG;
@@ -1133,6 +1161,33 @@ int gp_polish(gp_ctx* ctx, uint32_t n_contigs, const char* seqs, const uint64_t*
   if (rc) return rc;
   if ((rc = gp_polish_run(ctx))) return rc;
   return gp_polish_fetch(ctx, out_seqs, out_cap, out_offsets, out_dropped);
+}
+
+// ------------------------------------------------------------------------------------
+// flagged regions (derived from the soft-masking of ntedit.cpp:1131-1146)
+// ------------------------------------------------------------------------------------
+uint64_t gp_flagged_bed(const char* seqs, const uint64_t* offsets, uint32_t n_records, uint32_t* run_record,
+                        uint64_t* run_start, uint64_t* run_end, uint64_t cap)
+{
+  if (!offsets || (!seqs && n_records && offsets[n_records])) return 0;
+  uint64_t n = 0;
+  for (uint32_t r = 0; r < n_records; r++) {
+    const char* s = seqs + offsets[r];
+    const uint64_t len = offsets[r + 1] - offsets[r];
+    for (uint64_t i = 0; i < len;) {
+      if (s[i] < 'a' || s[i] > 'z') { i++; continue; }
+      uint64_t j = i + 1;
+      while (j < len && s[j] >= 'a' && s[j] <= 'z') j++;
+      if (n < cap) {
+        if (run_record) run_record[n] = r;
+        if (run_start) run_start[n] = i;
+        if (run_end) run_end[n] = j;
+      }
+      n++;
+      i = j;
+    }
+  }
+  return n;
 }
 
 // ------------------------------------------------------------------------------------

@@ -729,6 +729,43 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   if (p.cta_times && threadIdx.x < kLevelDiag) p.cta_times[blockIdx.x * 32u + threadIdx.x] = diag[threadIdx.x];
 }
 
+// ---- known-answer support: the hashes exactly as the build kernels compute them ----
+// Every k-mer start of one uploaded read through the device's own path (packed words + mask window, shared-memory byte
+// tables, hash_h0, the multiply-xorshift extra hashes): h[4 * pos .. 4 * pos + 3] and valid[pos] for pos < npos.
+__global__ void __launch_bounds__(kLevelWarps * 32) debug_nthash_kernel(const uint64_t* __restrict__ pk, const uint32_t* __restrict__ nm,
+                                                                        uint64_t wbase, uint32_t len, uint32_t k,
+                                                                        uint64_t* __restrict__ h, uint8_t* __restrict__ valid)
+{
+  __shared__ uint64_t tf[8 * 256];
+  __shared__ uint64_t tr[8 * 256];
+  fill_hash_tables(tf, tr);
+  __syncthreads();
+  if (len < k) return;
+  const StreamConsts sc = stream_consts(k);
+  const uint32_t npos = len - k + 1, lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t s = warp; s * 32u < npos; s += nwarps) {
+    const uint64_t w0 = __ldg(pk + wbase + s), w1 = __ldg(pk + wbase + s + 1);
+    const uint32_t m0 = __ldg(nm + wbase + s), m1 = __ldg(nm + wbase + s + 1);
+    uint64_t h0 = 0;
+    const bool ok = hash_h0(tf, tr, w0, w1, m0, m1, s * 32u, npos, lane, sc, h0);
+    const uint32_t pos = s * 32u + lane;
+    if (pos < npos) {
+      valid[pos] = ok ? 1 : 0;
+      uint64_t h1 = h0 * sc.mul1, h2 = h0 * sc.mul2, h3 = h0 * sc.mul3;
+      h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
+      h[4 * uint64_t(pos) + 0] = ok ? h0 : 0; h[4 * uint64_t(pos) + 1] = ok ? h1 : 0;
+      h[4 * uint64_t(pos) + 2] = ok ? h2 : 0; h[4 * uint64_t(pos) + 3] = ok ? h3 : 0;
+    }
+  }
+}
+
+void launch_debug_nthash(const uint64_t* pk, const uint32_t* nm, uint64_t wbase, uint32_t len, uint32_t k, uint64_t* h,
+                         uint8_t* valid, cudaStream_t s)
+{
+  debug_nthash_kernel<<<8, kLevelWarps * 32, 0, s>>>(pk, nm, wbase, len, k, h, valid);
+}
+
 int levels_max_grid(int sm_count, int ctas_per_sm)
 {
   int per_sm = 0;

@@ -115,6 +115,8 @@ void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint6
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s, int ctas_per_sm = 0);
 void preload_levels();
+void launch_debug_nthash(const uint64_t* pk, const uint32_t* nm, uint64_t wbase, uint32_t len, uint32_t k, uint64_t* h,
+                         uint8_t* valid, cudaStream_t s);
 int levels_max_grid(int sm_count, int ctas_per_sm);
 void preload_edit();
 void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uint16_t* anchor, uint32_t n_entries,

@@ -491,6 +491,28 @@ inline Header load(const std::string& path, std::vector<uint8_t>& payload)
 } // namespace bf_format
 
 // ---------------------------------------------------------------------------------------
+// flagged-region BED: the lower-case runs that ntEdit -a1 leaves (ntedit.cpp:1131-1146), one row per run
+// ---------------------------------------------------------------------------------------
+inline void write_flagged_bed(const std::string& path, const std::vector<std::string>& names, const char* seqs,
+                              const std::vector<uint64_t>& offsets)
+{
+  const uint32_t n = uint32_t(names.size());
+  uint64_t cap = 4096;
+  std::vector<uint32_t> rec;
+  std::vector<uint64_t> st, en;
+  uint64_t got;
+  for (;;) {
+    rec.resize(cap); st.resize(cap); en.resize(cap);
+    got = gp_flagged_bed(seqs, offsets.data(), n, rec.data(), st.data(), en.data(), cap);
+    if (got <= cap) break;
+    cap = got;
+  }
+  std::ofstream o(path);
+  if (!o.good()) die("cannot write " + path);
+  for (uint64_t i = 0; i < got; i++) o << names[rec[i]] << '\t' << st[i] << '\t' << en[i] << '\n';
+}
+
+// ---------------------------------------------------------------------------------------
 // FASTA/FASTQ reader with kseq semantics: gz or plain, multi-line sequences, name = text up
 // to the first whitespace, comment = rest of the header line
 // ---------------------------------------------------------------------------------------

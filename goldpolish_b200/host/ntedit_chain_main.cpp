@@ -82,6 +82,20 @@ int main(int argc, char** argv)
     }
   }
   std::remove(outfile.c_str());
+  if (const char* bed = std::getenv("GP_FLAGGED_BED")) { // the flagged regions of what <outfile> will hold
+    const bool rejected = gp_guard_rejects(input_size, output_size) != 0;
+    std::vector<std::string> names;
+    std::vector<uint64_t> eoff(1, 0);
+    std::string eseq;
+    for (size_t i = 0; i < recs.size(); i++) {
+      if (!rejected && dropped[i]) continue;
+      names.push_back(recs[i].name);
+      if (rejected) eseq += recs[i].seq;
+      else eseq.append(out.data() + ooff[i], size_t(ooff[i + 1] - ooff[i]));
+      eoff.push_back(eseq.size());
+    }
+    write_flagged_bed(bed, names, eseq.data(), eoff);
+  }
   if (gp_guard_rejects(input_size, output_size)) { // :31-37
     if (symlink(in_path.c_str(), outfile.c_str()) != 0) die("symlink failed");
     std::cout << "goldpolish-ntedit: skipped " << in_path << "\n";

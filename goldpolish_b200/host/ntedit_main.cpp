@@ -22,7 +22,9 @@ const struct option longopts[] = {                                   // :124-147
   { "outfile_prefix", required_argument, nullptr, 'b' }, { "mode", required_argument, nullptr, 'm' },
   { "snv", required_argument, nullptr, 's' }, { "mask", required_argument, nullptr, 'a' },
   { "verbose", required_argument, nullptr, 'v' }, { "help", no_argument, nullptr, 1 },
-  { "version", no_argument, nullptr, 2 }, { nullptr, 0, nullptr, 0 }
+  { "version", no_argument, nullptr, 2 },
+  { "bed", required_argument, nullptr, 3 }, // extension: write the flagged (soft-masked, -a1) regions as BED rows
+  { nullptr, 0, nullptr, 0 }
 };
 void assert_readable(const std::string& p)
 { // :346-353
@@ -39,7 +41,7 @@ int main(int argc, char** argv)
   gp_default_config(&cfg);
   cfg.max_insertions = 5; cfg.max_deletions = 5; cfg.mode = 0; cfg.mask = 0; // ntedit.cpp:86-87,109,111
   cfg.use_ratio = 0;
-  std::string draft, bloom, bloomrep, prefix;
+  std::string draft, bloom, bloomrep, prefix, bed;
   unsigned nthreads = 1;
   int snv = 0, verbose = 0;
   bool dieflag = false;
@@ -68,6 +70,7 @@ int main(int argc, char** argv)
     case 'v': arg >> verbose; break;
     case 1: std::cerr << "ntedit v1.3.5 (goldpolish_b200 GPU drop-in)\n"; return 0;
     case 2: std::cerr << "ntedit version 1.3.5 (goldpolish_b200 GPU drop-in)\n"; return 0;
+    case 3: arg >> bed; break;
     default: break;
     }
     if (optarg != nullptr && (!arg.eof() || arg.fail())) { // :1944-1947
@@ -132,6 +135,19 @@ int main(int argc, char** argv)
     o << "\n";
     o.write(out.data() + ooff[i], std::streamsize(ooff[i + 1] - ooff[i]));
     o << "\n";
+  }
+  if (bed.empty() && std::getenv("GP_FLAGGED_BED")) bed = std::getenv("GP_FLAGGED_BED");
+  if (!bed.empty()) { // emitted records only, coordinates of the polished record
+    std::vector<std::string> names;
+    std::vector<uint64_t> eoff(1, 0);
+    std::string eseq;
+    for (size_t i = 0; i < recs.size(); i++) {
+      if (dropped[i]) continue;
+      names.push_back(recs[i].name);
+      eseq.append(out.data() + ooff[i], size_t(ooff[i + 1] - ooff[i]));
+      eoff.push_back(eseq.size());
+    }
+    write_flagged_bed(bed, names, eseq.data(), eoff);
   }
   gp_ctx_destroy(ctx);
   return 0;

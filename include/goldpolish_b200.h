@@ -21,6 +21,8 @@
  *                        contig, subprojects/ntedit/ntedit.cpp:1414-1867, chained over the
  *                        context's k list as scripts/goldpolish-ntedit:20-29 chains processes
  *   gp_guard_rejects     the 0.75 size guard, scripts/goldpolish-ntedit:31-40
+ *   gp_flagged_bed       the soft-masked ("flagged") regions of ntEdit -a1, subprojects/ntedit/ntedit.cpp:1131-1146,
+ *                        as BED intervals (the reference itself only lower-cases the bases)
  *   gp_kmer_threshold    mappings_bases_to_kmer_threshold, src/goldpolish_targeted_bfs.cpp:45-53
  *   gp_mappings_cap      mappings_num_max, src/goldpolish_targeted_bfs.cpp:96-99
  */
@@ -181,6 +183,17 @@ int gp_prep(gp_ctx* ctx, uint32_t n_records, const char* seqs, const uint64_t* o
  * device turned out not to co-schedule the two kernels (the edit kernel's watchdog, checked after the first pass). */
 int gp_pipeline_run(gp_ctx* ctx);
 
+/* ---- flagged regions ---------------------------------------------------------------- */
+/* The reference flags what it could not fix by soft-masking: ntEdit -a1 lower-cases the draft base at every position
+ * whose k-mer stayed absent (subprojects/ntedit/ntedit.cpp:1131-1146; the flag is passed at scripts/goldpolish-ntedit:27)
+ * and writes NO BED file of its own.  The flagged-region BED is therefore DERIVED from the polished FASTA: one
+ * interval per maximal run of lower-case letters, 0-based half-open [start, end) in the coordinates of the polished
+ * record.  (Lower-case bases that were already soft-masked in the input survive polishing and are reported too.)
+ * Pure host code: records in CSR form as gp_polish returns them; fills record index / start / end of up to `cap`
+ * runs in record order and returns the total number of runs (call again with a larger cap if it exceeds cap). */
+uint64_t gp_flagged_bed(const char* seqs, const uint64_t* offsets, uint32_t n_records, uint32_t* run_record,
+                        uint64_t* run_start, uint64_t* run_end, uint64_t cap);
+
 /* ---- host-side rules shared with the reference ------------------------------------ */
 int gp_kmer_threshold(uint64_t mappings_bases);
 uint64_t gp_mappings_cap(uint64_t target_len, double subsample_max_per_10kbp);
@@ -196,6 +209,13 @@ int gp_guard_rejects(uint64_t input_bytes, uint64_t output_bytes);
  * 4 touches per iteration are counted). */
 int gp_roof_microbench(gp_ctx* ctx, uint32_t warps, uint32_t iters, uint64_t region_bytes, double* sectors_per_s,
                        float* ms);
+
+/* Known-answer support: the four ntHash values (btllib::NtHash::hashes(), spec in subprojects/ntedit/lib/nthash.hpp:
+ * 293-314) of every k-mer start of uploaded read `read_id`, computed by the device code the build kernels use (2-bit
+ * packed words + mask window, shared-memory byte tables, multiply-xorshift extra hashes).  hashes[4 p .. 4 p + 3] and
+ * valid[p] (0: the k-mer holds a non-ACGT base and is skipped, as NtHash::roll does) for p < *n_positions = len-k+1. */
+int gp_debug_nthash(gp_ctx* ctx, uint64_t read_id, uint32_t k, uint64_t* hashes, uint8_t* valid, uint64_t cap_positions,
+                    uint64_t* n_positions);
 
 /* Diagnostic (no reference counterpart): where the time of one CTA of the level-synchronous build
  * kernel went during the last gp_build_run, per kind of barrier interval r = 0 clear, 1 round 0 alone (hashing +

@@ -1,6 +1,7 @@
-"""GPU, BASELINE.json configs[1] size (5 Mbp draft, 30x reads, 543 batches): size-independent
-properties, since the CPU oracle needs minutes at this size.  (Bit-exactness itself is pinned at
-oracle-sized inputs in test_gpu_parity.py / test_gpu_golden.py.)"""
+"""GPU, BASELINE.json configs[1] size (5 Mbp draft, 30x reads, 543 batches) and a 10 Mbp bsize-8 cut of configs[2]:
+the whole workload through the device paths, a stratified sample of its batches against the reference's own code
+(oracle/_ref: serve_batch + ntEdit chain + guard; the C restatement where oracle/_ref is not built), and
+size-independent properties.  (Small-input bit-exactness: test_gpu_parity.py / test_gpu_golden.py.)"""
 import hashlib
 import os
 
@@ -139,3 +140,98 @@ def test_config3_size_paths_agree():
         digests["pipe_polish"] = hashlib.sha256(out2[:int(off2[-1])].tobytes()).hexdigest()
     assert digests["s"] == digests["l"] == digests["pipe"]
     assert digests["polish"] == digests["pipe_polish"] and np.array_equal(dropped, dropped2)
+
+
+def _check_batches_against_reference(gp, d, pl, bsize, batches, bfs, out, off, dropped):
+    """Filters and polished records (guard applied, as goldpolish-ntedit leaves them) of the given batches against the
+    reference's own code run on exactly those batches.  Returns the number of records compared."""
+    from oracle.ref_sample import ReferenceSample
+    w = dict(bsize=bsize, subsample_max=40.0, mx_max=150.0, mappings="paf")
+    rs = ReferenceSample(w, d, batches, threads=os.cpu_count() or 1)
+    n = 0
+    try:
+        rs.run()
+        for i, b in enumerate(batches):
+            assert np.array_equal(rs.filters(i), bfs[b]), f"filter payloads of batch {b} differ from the reference ({rs.kind})"
+            cs = range(b * bsize, min((b + 1) * bsize, d.n_contigs))
+            mine = [(d.contig_name(c), out[int(off[c]):int(off[c + 1])].tobytes()) for c in cs if not dropped[c]]
+            in_sz = sum(len(d.contig_name(c)) + 3 + int(d.contig_off[c + 1] - d.contig_off[c]) for c in cs)
+            out_sz = sum(len(nm) + 3 + len(sq) for nm, sq in mine)
+            if gp.guard_rejects(in_sz, out_sz):  # scripts/goldpolish-ntedit:31-40
+                mine = [(d.contig_name(c), d.contig(c)) for c in cs]
+            assert mine == rs.polished(i), f"polished records of batch {b} differ from the reference ({rs.kind})"
+            n += len(mine)
+    finally:
+        rs.close()
+    return n
+
+
+def _rollbacks_in(d, bfs, bsize, batches):
+    """Low-complexity insertion rollbacks (ntedit.cpp:1038-1066) that the C restatement counts in these batches."""
+    from oracle import oracle_lib as ol
+    n = 0
+    for b in batches:
+        for c in range(b * bsize, min((b + 1) * bsize, d.n_contigs)):
+            cur = d.contig(c)
+            for ki, k in enumerate(KS):
+                cur, st = ol.ntedit_contig(cur, bfs[b, ki], k)
+                if cur is None:
+                    break
+                n += st["rollbacks"]
+    return n
+
+
+def test_config2_size_sample_matches_reference(full):
+    """The benched workload itself (543 batches: ~34 k edits, ~3 M masked positions, ~90 rollbacks per pass), through the
+    overlapped pipeline; then the most loaded batch, 30 random ones and -- if the random ones held none -- a batch with
+    a low-complexity rollback are compared with what the reference's own code produces for them."""
+    gp, d, pl, ctx = full
+    ctx.build_stage(pl.batch_entry_off, pl.entries)
+    ctx.polish_stage(d.contig_seq, d.contig_off, pl.contig_batch)
+    ctx.pipeline_run()
+    bfs = ctx.build_fetch()
+    out, off, dropped = ctx.polish_fetch()
+    st = ctx.stats()
+    assert st["rollbacks"] > 0 and st["edits"] > 10000
+    n_batches = len(pl.batch_entry_off) - 1
+    load = np.diff(pl.batch_entry_off.astype(np.int64))
+    rng = np.random.default_rng(20250607)
+    batches = [int(np.argmax(load))] + sorted(int(b) for b in rng.choice(n_batches, size=30, replace=False))
+    batches = list(dict.fromkeys(batches))
+    if _rollbacks_in(d, bfs, 1, batches) == 0:
+        for b in range(n_batches):
+            if b not in batches and _rollbacks_in(d, bfs, 1, [b]):
+                batches.append(b)
+                break
+    assert _rollbacks_in(d, bfs, 1, batches) > 0, "the checked sample must exercise the rollback path"
+    assert _check_batches_against_reference(gp, d, pl, 1, batches, bfs, out, off, dropped) >= 30
+
+
+def test_10mbp_bsize8_paths_agree_and_loaded_batches_match_reference(monkeypatch):
+    """A 10 Mbp / 40x / bsize 8 cut of configs[2] (streams of ~6 M k-mers into counting filters loaded well beyond one
+    touch per counter, where an order-free update differs -- SURVEY Appendix C): the in-order kernel, the
+    level-synchronous kernel and the overlapped pipeline agree on every batch, and the 6 most loaded batches match the
+    reference's own code."""
+    import goldpolish_b200 as gp
+    d = dataset(genome_len=10_000_000, coverage=40.0)
+    pl = plan(d, bsize=8)
+    with gp.Context() as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        monkeypatch.setenv("GP_BUILD_KERNEL", "s")
+        a = ctx.build_filters(pl.batch_entry_off, pl.entries)
+        monkeypatch.setenv("GP_BUILD_KERNEL", "l")
+        b = ctx.build_filters(pl.batch_entry_off, pl.entries)
+        assert ctx.stats()["build_kernel"] == 2 and np.array_equal(a, b)
+        ctx.build_stage(pl.batch_entry_off, pl.entries)
+        ctx.polish_stage(d.contig_seq, d.contig_off, pl.contig_batch)
+        ctx.pipeline_run()
+        c = ctx.build_fetch()
+        out, off, dropped = ctx.polish_fetch()
+        assert np.array_equal(a, c)
+    rl = np.diff(d.read_off)
+    ent_bases = rl[pl.entries["read_id"]]
+    eo = pl.batch_entry_off.astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(ent_bases)])
+    load = cs[eo[1:]] - cs[eo[:-1]]
+    batches = [int(x) for x in np.argsort(-load)[:6]]
+    assert _check_batches_against_reference(gp, d, pl, 8, batches, c, out, off, dropped) >= 40

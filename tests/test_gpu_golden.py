@@ -116,3 +116,22 @@ def test_edge_inputs(gp):
             ctx.build_filters(np.array([0, 1], dtype=np.uint64), np.array([(9, 5)], dtype=ent.dtype))  # bad read id
         bfs0 = ctx.build_filters(np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=ent.dtype))
         assert bfs0.shape[0] == 0
+
+
+def test_nthash_known_answers_on_device(gp):
+    """A6 pinned directly: h0..h3 of every valid k-mer as the build kernels' own device code computes them (packed words,
+    mask window, byte tables) against the KATs minted from the reference's hashing (tests/golden/nthash_kat.json: random
+    32/28/24/20-mers, lower case, N runs)."""
+    kats = _load("nthash_kat.json")
+    seqs = [r["seq"].encode() for r in kats]
+    data = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    off = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint64)
+    n = 0
+    with gp.Context() as ctx:
+        ctx.upload_reads(data, off)
+        for i, rec in enumerate(kats):
+            pos, hs = ctx.debug_nthash(i, rec["k"])
+            assert pos.tolist() == rec["pos"], i
+            assert [[str(x) for x in row] for row in hs.tolist()] == rec["hashes"], i
+            n += len(rec["pos"])
+    assert n > 1000
