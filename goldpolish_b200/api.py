@@ -31,7 +31,8 @@ class _Config(C.Structure):
                 ("edit_ratio", C.c_float), ("jump", C.c_uint32), ("min_contig_len", C.c_uint32),
                 ("max_resident_batches", C.c_uint32), ("use_ratio", C.c_int32),
                 ("missing_threshold", C.c_float), ("edit_threshold", C.c_float), ("keep_counters", C.c_int32),
-                ("prep_mode", C.c_int32), ("prep_k", C.c_uint32), ("to_upper", C.c_int32)]
+                ("prep_mode", C.c_int32), ("prep_k", C.c_uint32), ("to_upper", C.c_int32),
+                ("max_resident_filters", C.c_uint32)]
 
 
 class _Stats(C.Structure):
@@ -52,7 +53,7 @@ EXPORTS = ["gp_default_config", "gp_ctx_create", "gp_ctx_destroy", "gp_last_erro
            "gp_build_run", "gp_build_fetch", "gp_build_fetch_cbf", "gp_filters_load", "gp_polish",
            "gp_polish_stage", "gp_polish_run", "gp_polish_fetch", "gp_kmer_threshold", "gp_mappings_cap",
            "gp_guard_rejects", "gp_roof_microbench", "gp_build_round_times", "gp_pipeline_run", "gp_prep", "gp_build_output_host", "gp_host_alloc", "gp_host_free",
-           "gp_build_cta_times", "gp_flagged_bed", "gp_debug_nthash"]
+           "gp_build_cta_times", "gp_flagged_bed", "gp_debug_nthash", "gp_reads_begin", "gp_reads_append", "gp_reads_end"]
 
 
 def load_library():
@@ -96,6 +97,9 @@ def load_library():
     l.gp_roof_microbench.argtypes = [vp, u32, u32, u64, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     l.gp_build_round_times.argtypes = [vp, C.POINTER(u64)]
     l.gp_pipeline_run.argtypes = [vp]
+    l.gp_reads_begin.argtypes = [vp, u64, vp]
+    l.gp_reads_append.argtypes = [vp, vp, u64]
+    l.gp_reads_end.argtypes = [vp]
     l.gp_debug_nthash.argtypes = [vp, u64, u32, vp, vp, u64, C.POINTER(u64)]
     l.gp_flagged_bed.argtypes = [vp, vp, u32, vp, vp, vp, u64]
     l.gp_flagged_bed.restype = u64
@@ -161,7 +165,7 @@ class Context:
 
     def __init__(self, device: int = 0, ks=DEFAULT_KS, max_insertions=5, max_deletions=5, mode=1, mask=1,
                  missing_ratio=0.5, edit_ratio=0.5, jump=3, min_contig_len=100, max_resident_batches=0,
-                 keep_counters=0, prep_mode=0, prep_k=0, to_upper=0):
+                 keep_counters=0, prep_mode=0, prep_k=0, to_upper=0, max_resident_filters=0):
         self._l = load_library()
         cfg = _Config()
         self._l.gp_default_config(C.byref(cfg))
@@ -174,6 +178,7 @@ class Context:
         cfg.max_resident_batches = max_resident_batches
         cfg.keep_counters = keep_counters
         cfg.prep_mode, cfg.prep_k, cfg.to_upper = prep_mode, prep_k, to_upper
+        cfg.max_resident_filters = max_resident_filters
         h = C.c_void_p()
         rc = self._l.gp_ctx_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -220,6 +225,16 @@ class Context:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         self._keep = (seqs, offsets)
         self._ck(self._l.gp_reads_upload(self._h, _ptr(seqs), _ptr(offsets), len(offsets) - 1))
+
+    def upload_reads_piecewise(self, lens, pieces):
+        """gp_reads_begin / gp_reads_append / gp_reads_end: `lens` = all read lengths, `pieces` = iterable of
+        (uint8 array of the bases of consecutive reads back to back, number of reads in it)."""
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        self._ck(self._l.gp_reads_begin(self._h, len(lens), _ptr(lens)))
+        for seqs, n in pieces:
+            seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+            self._ck(self._l.gp_reads_append(self._h, _ptr(seqs) if seqs.size else None, int(n)))
+        self._ck(self._l.gp_reads_end(self._h))
 
     # ---- filter build ----
     def build_stage(self, batch_entry_off, entries):

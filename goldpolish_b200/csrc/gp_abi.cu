@@ -60,14 +60,20 @@ struct gp_ctx {
 
   // read store
   uint64_t n_reads = 0;
+  uint64_t reads_total = 0, reads_next = 0, read_slab = 0; // gp_reads_begin / _append / _end in progress
   std::vector<uint32_t> h_read_len;
+  std::vector<uint64_t> h_read_boff;
   DevBuf d_ascii, d_ascii_off, d_pk, d_nm, d_read_boff, d_read_len;
 
   // build
   uint32_t n_batches = 0;      // batches of the current filter set
-  bool filters_ready = false;
+  bool filters_ready = false; // the context's current filter set is resident (gp_polish can run)
+  bool build_done = false;    // a staged build has run (its payloads can be fetched)
   bool build_staged = false;
   uint32_t wave_batches = 0;
+  bool bf_all_resident = true;                        // the filter pool holds every batch of the call (else: one wave at a time)
+  std::vector<uint32_t> h_bf_slot;                    // pool slot of every batch when it does not
+  DevBuf d_bf_slot;
   std::vector<uint32_t> wave_first, wave_count, wave_order_off;
   DevBuf d_batch_entry_off, d_entries, d_bf_pool, d_cbf_pool, d_stream_order, d_next, d_counters;
   // level-synchronous build
@@ -86,6 +92,7 @@ struct gp_ctx {
   std::vector<uint64_t> h_in_off, h_cap_off, h_node_off;
   std::vector<uint32_t> h_len, h_order, h_batch;
   std::vector<uint32_t> h_batch_order, h_order_pipe;  // gp_pipeline_run: batches / contigs in build order
+  std::vector<uint32_t> h_wave_contig_off;            // ... and where every wave's contigs start in h_order_pipe
   DevBuf d_batch_order, d_batch_done, d_order_pipe;
   DevBuf d_input, d_in_off, d_buf0, d_buf1, d_cap_off, d_cur_len, d_which, d_dropped, d_nodes, d_node_off,
     d_contig_batch, d_order, d_pnext, d_pcounters, d_error, d_out, d_out_off;
@@ -222,7 +229,7 @@ void gp_ctx_destroy(gp_ctx* ctx)
                      &ctx->d_next, &ctx->d_counters, &ctx->d_step_pre, &ctx->d_batch_max_thr, &ctx->d_V, &ctx->d_alive, &ctx->d_anchor, &ctx->d_entry_rel, &ctx->d_input, &ctx->d_in_off, &ctx->d_buf0, &ctx->d_buf1,
                      &ctx->d_cap_off, &ctx->d_cur_len, &ctx->d_which, &ctx->d_dropped, &ctx->d_nodes, &ctx->d_node_off,
                      &ctx->d_contig_batch, &ctx->d_order, &ctx->d_pnext, &ctx->d_pcounters, &ctx->d_error, &ctx->d_out,
-                     &ctx->d_out_off, &ctx->d_batch_order, &ctx->d_batch_done, &ctx->d_order_pipe, &ctx->d_stream_tab, &ctx->d_cta_times };
+                     &ctx->d_out_off, &ctx->d_batch_order, &ctx->d_batch_done, &ctx->d_order_pipe, &ctx->d_stream_tab, &ctx->d_cta_times, &ctx->d_bf_slot };
   for (auto* b : bufs) b->release();
   if (ctx->l2_window_set) { cudaCtxResetPersistingL2Cache(); cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0); }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -298,48 +305,108 @@ int gp_get_stats(const gp_ctx* cctx, gp_stats* out)
 // ------------------------------------------------------------------------------------
 // read store
 // ------------------------------------------------------------------------------------
-int gp_reads_upload(gp_ctx* ctx, const char* seqs, const uint64_t* offsets, uint64_t n_reads)
+// The store is laid out from the read lengths alone; the bases then arrive in slabs, are packed on the device
+// (2 bits + 1 mask bit per base) and the ASCII staging is reused: the device never holds more than
+// kReadSlabBytes (or the longest read) of ASCII next to the packed store (0.375 B/base).
+static const uint64_t kReadSlabBytes = 256ull << 20;
+
+int gp_reads_begin(gp_ctx* ctx, uint64_t n_reads, const uint32_t* lens)
 {
-  if (!ctx || (!seqs && n_reads) || !offsets) return GP_ERR_ARG;
+  if (!ctx || (!lens && n_reads)) return GP_ERR_ARG;
   if (n_reads > 0xFFFFFFF0ull) GP_FAIL(ctx, GP_ERR_ARG, "too many reads");
   cudaSetDevice(ctx->cfg.device);
-  const uint64_t n_ascii = offsets[n_reads];
-  std::vector<uint64_t> boff(n_reads + 1);
-  ctx->h_read_len.resize(n_reads);
-  uint64_t b = 0;
+  ctx->n_reads = 0;
+  ctx->reads_next = 0;
+  ctx->h_read_len.assign(lens, lens + n_reads);
+  ctx->h_read_boff.resize(n_reads + 1);
+  uint64_t b = 0, longest = 0;
   for (uint64_t r = 0; r < n_reads; r++) {
-    const uint64_t len = offsets[r + 1] - offsets[r];
-    if (len >= (1ull << 31)) GP_FAIL(ctx, GP_ERR_ARG, "read longer than 2^31 bases");
-    boff[r] = b;
-    ctx->h_read_len[r] = uint32_t(len);
-    b += (len + 31) & ~31ull;
+    if (lens[r] >= (1u << 31)) GP_FAIL(ctx, GP_ERR_ARG, "read longer than 2^31 bases");
+    ctx->h_read_boff[r] = b;
+    b += (uint64_t(lens[r]) + 31) & ~31ull;
+    longest = std::max<uint64_t>(longest, lens[r]);
   }
-  boff[n_reads] = b;
+  ctx->h_read_boff[n_reads] = b;
   const uint64_t words = b / 32 + 2; // one spare word past the last read for the window loads
-  GP_CUDA(ctx, ctx->d_ascii.ensure(n_ascii + 16));
-  GP_CUDA(ctx, ctx->d_ascii_off.ensure((n_reads + 1) * 8));
+  ctx->read_slab = std::max(kReadSlabBytes, longest);
+  if (const char* e = std::getenv("GP_READ_SLAB_BYTES")) ctx->read_slab = std::max<uint64_t>(uint64_t(std::atoll(e)), std::max<uint64_t>(longest, 1));
   GP_CUDA(ctx, ctx->d_read_boff.ensure((n_reads + 1) * 8));
   GP_CUDA(ctx, ctx->d_read_len.ensure((n_reads + 1) * 4));
   GP_CUDA(ctx, ctx->d_pk.ensure(words * 8));
   GP_CUDA(ctx, ctx->d_nm.ensure(words * 4));
   cudaStream_t s = ctx->stream;
-  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_ascii.p, seqs, n_ascii, cudaMemcpyHostToDevice, s));
-  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_ascii_off.p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_read_boff.p, boff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_read_len.p, ctx->h_read_len.data(), n_reads * 4, cudaMemcpyHostToDevice, s));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_read_boff.p, ctx->h_read_boff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+  if (n_reads) GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_read_len.p, ctx->h_read_len.data(), n_reads * 4, cudaMemcpyHostToDevice, s));
   // the two spare words must read as "no seed"
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_nm.as<uint32_t>() + (words - 2), 0xFF, 8, s));
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pk.as<uint64_t>() + (words - 2), 0, 16, s));
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
-  gp::launch_pack_reads(ctx->d_ascii.as<char>(), ctx->d_ascii_off.as<uint64_t>(), ctx->d_read_boff.as<uint64_t>(),
-                        ctx->d_pk.as<uint64_t>(), ctx->d_nm.as<uint32_t>(), uint32_t(n_reads), s);
-  GP_CUDA(ctx, cudaGetLastError());
-  GP_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
-  ctx->pack_timed = true;
-  ctx->stats.pack_launches = n_reads ? 1 : 0;
-  GP_CUDA(ctx, cudaStreamSynchronize(s)); // boff (host vector) must outlive the copy
-  ctx->n_reads = n_reads;
+  GP_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->reads_total = n_reads;
+  ctx->stats.pack_launches = 0;
   return GP_OK;
+}
+
+int gp_reads_append(gp_ctx* ctx, const char* seqs, uint64_t n)
+{
+  if (!ctx || (!seqs && n)) return GP_ERR_ARG;
+  if (ctx->reads_next + n > ctx->reads_total) GP_FAIL(ctx, GP_ERR_STATE, "gp_reads_append: more reads than gp_reads_begin announced");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t s = ctx->stream;
+  uint64_t r = ctx->reads_next, done = 0; // `done` = bytes of seqs consumed
+  const uint64_t r_end = r + n;
+  std::vector<uint64_t> aoff;
+  while (r < r_end) {
+    // a slab: as many whole reads as fit (at least one)
+    uint64_t r1 = r, bytes = 0;
+    while (r1 < r_end && (r1 == r || bytes + ctx->h_read_len[r1] <= ctx->read_slab)) bytes += ctx->h_read_len[r1++];
+    const uint64_t cnt = r1 - r;
+    aoff.resize(cnt + 1);
+    aoff[0] = 0;
+    for (uint64_t i = 0; i < cnt; i++) aoff[i + 1] = aoff[i] + ctx->h_read_len[r + i];
+    GP_CUDA(ctx, ctx->d_ascii.ensure(bytes + 16));
+    GP_CUDA(ctx, ctx->d_ascii_off.ensure((cnt + 1) * 8));
+    if (bytes) GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_ascii.p, seqs + done, bytes, cudaMemcpyHostToDevice, s));
+    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_ascii_off.p, aoff.data(), (cnt + 1) * 8, cudaMemcpyHostToDevice, s));
+    gp::launch_pack_reads(ctx->d_ascii.as<char>(), ctx->d_ascii_off.as<uint64_t>(), ctx->d_read_boff.as<uint64_t>() + r,
+                          ctx->d_pk.as<uint64_t>(), ctx->d_nm.as<uint32_t>(), uint32_t(cnt), s);
+    GP_CUDA(ctx, cudaGetLastError());
+    ctx->stats.pack_launches++;
+    GP_CUDA(ctx, cudaStreamSynchronize(s)); // the staging buffers (device slab, host offsets) are reused by the next slab
+    done += bytes;
+    r = r1;
+  }
+  ctx->reads_next = r_end;
+  return GP_OK;
+}
+
+int gp_reads_end(gp_ctx* ctx)
+{
+  if (!ctx) return GP_ERR_ARG;
+  if (ctx->reads_next != ctx->reads_total) GP_FAIL(ctx, GP_ERR_STATE, "gp_reads_end: fewer reads appended than gp_reads_begin announced");
+  cudaSetDevice(ctx->cfg.device);
+  GP_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->pack_timed = true;
+  // the ASCII staging slab stays (the next upload reuses it) unless an extraordinarily long read blew it up
+  if (ctx->d_ascii.cap > 2 * kReadSlabBytes) ctx->d_ascii.release();
+  ctx->n_reads = ctx->reads_total;
+  return GP_OK;
+}
+
+int gp_reads_upload(gp_ctx* ctx, const char* seqs, const uint64_t* offsets, uint64_t n_reads)
+{
+  if (!ctx || (!seqs && n_reads) || !offsets) return GP_ERR_ARG;
+  std::vector<uint32_t> lens(n_reads);
+  for (uint64_t r = 0; r < n_reads; r++) {
+    const uint64_t len = offsets[r + 1] - offsets[r];
+    if (len >= (1ull << 31)) GP_FAIL(ctx, GP_ERR_ARG, "read longer than 2^31 bases");
+    lens[r] = uint32_t(len);
+  }
+  if (int rc = gp_reads_begin(ctx, n_reads, lens.data())) return rc;
+  if (n_reads)
+    if (int rc = gp_reads_append(ctx, seqs + offsets[0], n_reads)) return rc;
+  return gp_reads_end(ctx);
 }
 
 // ------------------------------------------------------------------------------------
@@ -442,21 +509,34 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     ctx->build_algo_resolved = algo;
   }
   const bool uses_cbf = ctx->build_algo_resolved == 1 || c.keep_counters;
-  // how many batches can hold their counting filters at once
-  const uint64_t per_batch = uint64_t(c.nk) * gp::kCbfCounters;
-  const uint64_t bf_bytes = uint64_t(n_batches) * c.nk * gp::kBfBytes;
-  GP_CUDA(ctx, ctx->d_bf_pool.ensure(std::max<uint64_t>(bf_bytes, 4)));
+  // Residency.  Filters (nk x 512 KiB per batch): all batches of the call when they fit and max_resident_filters allows
+  // it; otherwise the pool holds one wave and is reused wave after wave (gp_pipeline_run polishes a wave before its
+  // filters go, gp_build_output_host receives the payloads).  Counting filters (nk x 10 MiB per batch, in-order kernel
+  // and keep_counters only) are always per wave.
+  const uint64_t per_batch = uint64_t(c.nk) * gp::kCbfCounters, per_batch_bf = uint64_t(c.nk) * gp::kBfBytes;
   uint32_t wave = n_batches;
   if (c.max_resident_batches) wave = std::min(wave, c.max_resident_batches);
-  if (uses_cbf) {
+  {
     size_t free_b = 0, total_b = 0;
     GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t usable = uint64_t(free_b) + ctx->d_cbf_pool.cap;
-    const uint64_t headroom = 2ull << 30;
-    const uint64_t fit = usable > headroom ? (usable - headroom) / per_batch : 0;
-    if (fit == 0 && n_batches) GP_FAIL(ctx, GP_ERR_OOM, "not enough device memory for one batch of counting filters");
-    wave = uint32_t(std::min<uint64_t>(wave, fit));
+    const uint64_t usable = uint64_t(free_b) + ctx->d_cbf_pool.cap + ctx->d_bf_pool.cap;
+    const uint64_t headroom = 3ull << 30;
+    uint64_t bf_limit = n_batches;
+    if (c.max_resident_filters) bf_limit = std::min<uint64_t>(bf_limit, c.max_resident_filters);
+    // the pool may take up to half of what is free (the polish buffers and the lists come after it)
+    const uint64_t fit_bf = usable > headroom ? (usable - headroom) / 2 / per_batch_bf : 0;
+    if (fit_bf == 0 && n_batches) GP_FAIL(ctx, GP_ERR_OOM, "not enough device memory for one batch of filters");
+    bf_limit = std::min(bf_limit, fit_bf);
+    ctx->bf_all_resident = bf_limit >= n_batches;
+    if (!ctx->bf_all_resident) wave = uint32_t(std::min<uint64_t>(wave, bf_limit));
+    if (uses_cbf) {
+      const uint64_t left = usable > headroom ? usable - headroom - (ctx->bf_all_resident ? uint64_t(n_batches) * per_batch_bf : 0) : 0;
+      const uint64_t fit = left / (per_batch + (ctx->bf_all_resident ? 0 : per_batch_bf));
+      if (fit == 0 && n_batches) GP_FAIL(ctx, GP_ERR_OOM, "not enough device memory for one batch of counting filters");
+      wave = uint32_t(std::min<uint64_t>(wave, fit));
+    }
   }
+  GP_CUDA(ctx, ctx->d_bf_pool.ensure(std::max<uint64_t>(uint64_t(ctx->bf_all_resident ? n_batches : wave) * per_batch_bf, 4)));
   if (n_batches && uses_cbf) {
     cudaError_t e = ctx->d_cbf_pool.ensure(uint64_t(wave) * per_batch);
     while (e != cudaSuccess && wave > 1) { cudaGetLastError(); wave = (wave + 1) / 2; e = ctx->d_cbf_pool.ensure(uint64_t(wave) * per_batch); }
@@ -495,35 +575,53 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
   ctx->n_batches = n_batches;
   ctx->build_staged = true;
   ctx->filters_ready = false;
+  ctx->build_done = false;
   return GP_OK;
 }
 
-// level-synchronous build of every wave on stream s; batch_order / batch_done / ctas_per_sm are
-// gp_pipeline_run's (NULL, NULL, 0 otherwise)
-static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, uint32_t* batch_done,
-                               int ctas_per_sm, uint32_t* launches_out)
+// per stream, in launch order: steps, largest thr, batch (the level kernel reads it one stream ahead); build_order:
+// the batches of a wave in gp_pipeline_run's order (h_batch_order)
+static int build_stream_tab(gp_ctx* ctx, cudaStream_t s, bool build_order)
 {
   const gp_config& c = ctx->cfg;
-  uint32_t launches = 0;
-  // per stream, in launch order: steps, largest thr, batch (the kernel reads it one stream ahead)
+  const size_t total = size_t(ctx->n_batches) * c.nk;
+  ctx->h_stream_tab.resize(std::max<size_t>(total, 1));
+  const size_t ne1 = size_t(ctx->n_entries) + 1;
+  size_t w = 0;
+  for (size_t wv = 0; wv < ctx->wave_first.size(); wv++)
+    for (uint32_t st = 0; st < ctx->wave_count[wv] * c.nk; st++, w++) {
+      const uint32_t lb = st / c.nk, ki = st - lb * c.nk;
+      const uint32_t b = build_order ? ctx->h_batch_order[ctx->wave_first[wv] + lb] : ctx->wave_first[wv] + lb;
+      const uint32_t* pk = ctx->h_pre.data() + size_t(ki) * ne1;
+      const uint32_t steps = pk[ctx->h_batch_entry_off[b + 1]] - pk[ctx->h_batch_entry_off[b]];
+      ctx->h_stream_tab[w] = make_uint4(steps, ctx->h_maxthr[b] - 2u + ki, b, 0u);
+    }
+  GP_CUDA(ctx, ctx->d_stream_tab.ensure(ctx->h_stream_tab.size() * sizeof(uint4)));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_stream_tab.p, ctx->h_stream_tab.data(), ctx->h_stream_tab.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  return GP_OK;
+}
+
+// pool slot of every batch when the pool holds one wave at a time: its position inside its wave (waves are uniform
+// runs of wave_batches positions of the launch order)
+static int upload_bf_slots(gp_ctx* ctx, cudaStream_t s, bool build_order)
+{
+  if (ctx->bf_all_resident) return GP_OK;
+  const uint32_t nb = ctx->n_batches, wave = std::max(ctx->wave_batches, 1u);
+  ctx->h_bf_slot.resize(nb);
+  for (uint32_t pos = 0; pos < nb; pos++) ctx->h_bf_slot[build_order ? ctx->h_batch_order[pos] : pos] = pos % wave;
+  GP_CUDA(ctx, ctx->d_bf_slot.ensure(std::max<size_t>(nb, 1) * 4));
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_bf_slot.p, ctx->h_bf_slot.data(), size_t(nb) * 4, cudaMemcpyHostToDevice, s));
+  return GP_OK;
+}
+
+// level-synchronous build of wave wv on stream s (build_stream_tab first); batch_done / ctas_per_sm are
+// gp_pipeline_run's (NULL, 0 otherwise)
+static int build_launch_levels_wave(gp_ctx* ctx, cudaStream_t s, size_t wv, uint32_t* batch_done, int ctas_per_sm)
+{
+  const gp_config& c = ctx->cfg;
   {
-    const size_t total = size_t(ctx->n_batches) * c.nk;
-    ctx->h_stream_tab.resize(std::max<size_t>(total, 1));
-    const size_t ne1 = size_t(ctx->n_entries) + 1;
-    size_t w = 0;
-    for (size_t wv = 0; wv < ctx->wave_first.size(); wv++)
-      for (uint32_t st = 0; st < ctx->wave_count[wv] * c.nk; st++, w++) {
-        const uint32_t lb = st / c.nk, ki = st - lb * c.nk;
-        const uint32_t b = build_order ? ctx->h_batch_order[ctx->wave_first[wv] + lb] : ctx->wave_first[wv] + lb;
-        const uint32_t* pk = ctx->h_pre.data() + size_t(ki) * ne1;
-        const uint32_t steps = pk[ctx->h_batch_entry_off[b + 1]] - pk[ctx->h_batch_entry_off[b]];
-        ctx->h_stream_tab[w] = make_uint4(steps, ctx->h_maxthr[b] - 2u + ki, b, 0u);
-      }
-    GP_CUDA(ctx, ctx->d_stream_tab.ensure(ctx->h_stream_tab.size() * sizeof(uint4)));
-    GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_stream_tab.p, ctx->h_stream_tab.data(), ctx->h_stream_tab.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
-  }
-  size_t tab_off = 0;
-  for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
+    size_t tab_off = 0;
+    for (size_t i = 0; i < wv; i++) tab_off += size_t(ctx->wave_count[i]) * c.nk;
     // level-synchronous: all SMs on one stream at a time, timestamps resident in L2
     gp::LevelParams p;
     std::memset(&p, 0, sizeof p);
@@ -547,13 +645,13 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
     if (const char* f = std::getenv("GP_LEVEL_REPORT_CTA")) p.report_cta = uint32_t(std::atoi(f));
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
     p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
+    p.bf_slot = ctx->bf_all_resident ? nullptr : ctx->d_bf_slot.as<uint32_t>();
     p.counters = ctx->d_counters.as<unsigned long long>();
     p.surv_cap = ctx->surv_cap;
     p.n_entries = ctx->n_entries;
     p.n_streams = ctx->wave_count[wv] * c.nk;
     p.first_batch = ctx->wave_first[wv];
     p.stream_tab = ctx->d_stream_tab.as<uint4>() + tab_off;
-    tab_off += p.n_streams;
     p.nk = c.nk;
     for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
     if (c.keep_counters) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
@@ -571,7 +669,7 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
     p.bf_host = ctx->bf_host_dev;
     // the timestamp arrays are the kernel's random-access working set: keep them in the persisting part of L2
     // (79 of 126 MiB on B200), so that the survivor lists, the sequence and the filters streaming through do not
-    // evict them (+6 % k-mer ops/s).  Only when the window can cover them (one stream in flight).
+    // evict them (+6 % k-mer ops/s).  Only when the window can cover them.
     {
       const size_t vbytes = gp::kCbfCounters * 4 * p.arrays;
       const char* e = std::getenv("GP_L2_PERSIST");
@@ -607,10 +705,49 @@ static int build_launch_levels(gp_ctx* ctx, cudaStream_t s, bool build_order, ui
     ctx->level_grid = uint32_t(gp::levels_max_grid(ctx->sm_count, ctas_per_sm));
     GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s, ctas_per_sm));
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
-    launches += 1;
   }
-  *launches_out = launches;
-  ctx->bf_streamed = ctx->bf_host_dev != nullptr;
+  return GP_OK;
+}
+
+// in-order kernel (one warp per stream, counters in HBM), wave wv
+static int build_launch_inorder_wave(gp_ctx* ctx, cudaStream_t s, size_t wv)
+{
+  const gp_config& c = ctx->cfg;
+  gp::BuildParams p;
+  std::memset(&p, 0, sizeof p);
+  p.pk = ctx->d_pk.as<uint64_t>();
+  p.nm = ctx->d_nm.as<uint32_t>();
+  p.read_boff = ctx->d_read_boff.as<uint64_t>();
+  p.read_len = ctx->d_read_len.as<uint32_t>();
+  p.batch_entry_off = ctx->d_batch_entry_off.as<uint64_t>();
+  p.entries = ctx->d_entries.as<gp_read_entry>();
+  p.cbf_pool = ctx->d_cbf_pool.as<uint8_t>();
+  p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
+  p.bf_slot = ctx->bf_all_resident ? nullptr : ctx->d_bf_slot.as<uint32_t>();
+  p.stream_order = ctx->d_stream_order.as<uint32_t>() + ctx->wave_order_off[wv];
+  p.next_stream = ctx->d_next.as<uint32_t>() + wv;
+  p.counters = ctx->d_counters.as<unsigned long long>();
+  p.n_streams = ctx->wave_count[wv] * c.nk;
+  p.first_batch = ctx->wave_first[wv];
+  p.nk = c.nk;
+  for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
+  while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
+  GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
+  gp::launch_build_filters(p, ctx->sm_count, s);
+  GP_CUDA(ctx, cudaGetLastError());
+  GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
+  return GP_OK;
+}
+
+// a wave's filters are final on the device and the pool is about to be reused: hand the payloads over (the level
+// kernel has streamed them to the named host buffer itself; the in-order kernel has not)
+static int wave_payloads_out(gp_ctx* ctx, cudaStream_t s, size_t wv, bool kernel_streams)
+{
+  if (ctx->bf_all_resident || kernel_streams || !ctx->bf_host_user) return GP_OK;
+  const uint64_t per = uint64_t(ctx->cfg.nk) * gp::kBfBytes;
+  GP_CUDA(ctx, cudaMemcpyAsync(ctx->bf_host_user + uint64_t(ctx->wave_first[wv]) * per, ctx->d_bf_pool.p,
+                               uint64_t(ctx->wave_count[wv]) * per, cudaMemcpyDeviceToHost, s));
   return GP_OK;
 }
 
@@ -621,58 +758,46 @@ int gp_build_run(gp_ctx* ctx)
   cudaSetDevice(ctx->cfg.device);
   const gp_config& c = ctx->cfg;
   cudaStream_t s = ctx->stream;
+  if (!ctx->bf_all_resident && !ctx->bf_host_user)
+    GP_FAIL(ctx, GP_ERR_STATE, "the filters of this call are not all resident at once (max_resident_filters / device memory): "
+                               "name a page-locked destination with gp_build_output_host, or use gp_pipeline_run");
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
   ctx->pipelined = false;
   uint32_t launches = 0;
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, gp::kBuildCounters * 8, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + 20, 0xFF, 8, s)); // first start time: atomicMin
+  const uint64_t per_bf = uint64_t(c.nk) * gp::kBfBytes;
   if (ctx->n_batches) {
     GP_CUDA(ctx, cudaMemsetAsync(ctx->d_next.p, 0, ctx->wave_first.size() * 4, s));
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->n_batches) * c.nk * gp::kBfBytes, s));
+    if (ctx->bf_all_resident) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->n_batches) * per_bf, s));
   }
   const int algo = ctx->build_algo_resolved;
-  if (algo == 2) {
-    // level-synchronous: all SMs on one stream at a time, timestamps resident in L2
-    if (int rc = build_launch_levels(ctx, s, false, nullptr, 0, &launches)) return rc;
-  }
-  if (algo == 1) ctx->bf_streamed = false;
-  for (size_t wv = 0; algo == 1 && wv < ctx->wave_first.size(); wv++) {
-    gp::BuildParams p;
-    p.pk = ctx->d_pk.as<uint64_t>();
-    p.nm = ctx->d_nm.as<uint32_t>();
-    p.read_boff = ctx->d_read_boff.as<uint64_t>();
-    p.read_len = ctx->d_read_len.as<uint32_t>();
-    p.batch_entry_off = ctx->d_batch_entry_off.as<uint64_t>();
-    p.entries = ctx->d_entries.as<gp_read_entry>();
-    p.cbf_pool = ctx->d_cbf_pool.as<uint8_t>();
-    p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
-    p.stream_order = ctx->d_stream_order.as<uint32_t>() + ctx->wave_order_off[wv];
-    p.next_stream = ctx->d_next.as<uint32_t>() + wv;
-    p.counters = ctx->d_counters.as<unsigned long long>();
-    p.n_streams = ctx->wave_count[wv] * c.nk;
-    p.first_batch = ctx->wave_first[wv];
-    p.nk = c.nk;
-    for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
-    while (ctx->wave_ev.size() < 2 * (wv + 1)) { cudaEvent_t e2 = nullptr; cudaEventCreate(&e2); ctx->wave_ev.push_back(e2); }
-    GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv], s));
-    gp::launch_build_filters(p, ctx->sm_count, s);
-    GP_CUDA(ctx, cudaGetLastError());
-    GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
+  if (int rc = upload_bf_slots(ctx, s, false)) return rc;
+  if (algo == 2)
+    if (int rc = build_stream_tab(ctx, s, false)) return rc;
+  for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
+    if (!ctx->bf_all_resident) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->wave_count[wv]) * per_bf, s));
+    if (algo == 2) { if (int rc = build_launch_levels_wave(ctx, s, wv, nullptr, 0)) return rc; }
+    else if (int rc = build_launch_inorder_wave(ctx, s, wv)) return rc;
+    if (int rc = wave_payloads_out(ctx, s, wv, algo == 2 && ctx->bf_host_dev)) return rc;
     launches += 1;
   }
+  // the named host buffer holds every payload after this run: written by the level kernel itself, or wave by wave
+  ctx->bf_streamed = ctx->bf_host_user && ((algo == 2 && ctx->bf_host_dev) || !ctx->bf_all_resident);
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
   ctx->build_timed = true;
   ctx->stats.build_launches = launches;
   ctx->stats.build_kernel = uint32_t(algo);
   ctx->stats.build_slots = algo == 2 ? ctx->level_slots : 0;
-  ctx->filters_ready = true;
+  ctx->filters_ready = ctx->bf_all_resident; // (a later gp_polish needs them all)
+  ctx->build_done = true;
   return GP_OK;
 }
 
 int gp_build_round_times(gp_ctx* ctx, uint64_t out[32])
 {
   if (!ctx || !out) return GP_ERR_ARG;
-  if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
+  if (!ctx->build_done) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
   cudaSetDevice(ctx->cfg.device);
   GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   unsigned long long c[gp::kBuildCounters];
@@ -714,7 +839,7 @@ int gp_debug_nthash(gp_ctx* ctx, uint64_t read_id, uint32_t k, uint64_t* hashes,
 int gp_build_cta_times(gp_ctx* ctx, uint64_t* out, uint32_t cap_ctas, uint32_t* n_ctas)
 {
   if (!ctx || !out || !n_ctas) return GP_ERR_ARG;
-  if (!ctx->filters_ready || !ctx->d_cta_times.p) GP_FAIL(ctx, GP_ERR_STATE, "no per-CTA times were recorded (set GP_LEVEL_CTA_TIMES=1 before the build)");
+  if (!ctx->build_done || !ctx->d_cta_times.p) GP_FAIL(ctx, GP_ERR_STATE, "no per-CTA times were recorded (set GP_LEVEL_CTA_TIMES=1 before the build)");
   cudaSetDevice(ctx->cfg.device);
   GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *n_ctas = std::min(cap_ctas, ctx->level_grid);
@@ -755,14 +880,18 @@ int gp_build_output_host(gp_ctx* ctx, uint8_t* bf_out_pinned)
 int gp_build_fetch(gp_ctx* ctx, uint8_t* bf_out)
 {
   if (!ctx) return GP_ERR_ARG;
-  if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
+  if (!ctx->build_done && !ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
   cudaSetDevice(ctx->cfg.device);
   if (bf_out && bf_out == ctx->bf_host_user && ctx->bf_streamed) {
-    // the build kernel streamed every final filter into this buffer already; streams without k-mers are zeros
+    // every final filter is in this buffer already (written by the build kernel, or copied wave by wave); streams
+    // without k-mers are zeros
     GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (uint32_t sidx : ctx->h_empty_streams) std::memset(bf_out + uint64_t(sidx) * gp::kBfBytes, 0, gp::kBfBytes);
     return GP_OK;
   }
+  if (bf_out && !ctx->bf_all_resident)
+    GP_FAIL(ctx, GP_ERR_STATE, "the filters of earlier waves are no longer resident: their payloads went to the buffer named with "
+                               "gp_build_output_host (pass that pointer)");
   if (bf_out && ctx->n_batches)
     GP_CUDA(ctx, cudaMemcpyAsync(bf_out, ctx->d_bf_pool.p, uint64_t(ctx->n_batches) * ctx->cfg.nk * gp::kBfBytes,
                                  cudaMemcpyDeviceToHost, ctx->stream));
@@ -773,7 +902,7 @@ int gp_build_fetch(gp_ctx* ctx, uint8_t* bf_out)
 int gp_build_fetch_cbf(gp_ctx* ctx, uint32_t batch, uint32_t k_index, uint8_t* cbf_out)
 {
   if (!ctx || !cbf_out) return GP_ERR_ARG;
-  if (!ctx->filters_ready) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
+  if (!ctx->build_done) GP_FAIL(ctx, GP_ERR_STATE, "no filters have been built");
   if (batch >= ctx->n_batches || k_index >= ctx->cfg.nk) GP_FAIL(ctx, GP_ERR_ARG, "batch / k index out of range");
   if (ctx->build_algo_resolved == 2 && !ctx->cfg.keep_counters)
     GP_FAIL(ctx, GP_ERR_STATE, "counting-filter bytes were not materialised: create the context with keep_counters = 1");
@@ -807,7 +936,9 @@ int gp_filters_load(gp_ctx* ctx, uint32_t n_batches, const uint8_t* bf_payloads)
   GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_batches = n_batches;
   ctx->filters_ready = true;
+  ctx->bf_all_resident = true;
   ctx->build_staged = false;
+  ctx->build_done = false;
   return GP_OK;
 }
 
@@ -893,6 +1024,7 @@ static int polish_prepare(gp_ctx* ctx)
   const uint32_t n = ctx->n_contigs;
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pnext.p, 0, 4, s));
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pcounters.p, 0, 64, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pcounters.as<unsigned long long>() + 4, 0xFF, 8, s)); // first start time: atomicMin
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_error.p, 0, 4, s));
   if (n == 0) return GP_OK;
   const uint32_t grid = std::min<uint32_t>(n, uint32_t(ctx->sm_count) * 8u);
@@ -904,10 +1036,10 @@ static int polish_prepare(gp_ctx* ctx)
 
 // the edit kernel on stream es (the context's stream unless pipelined: then `order`, `batch_done` and
 // alongside are gp_pipeline_run's)
-static int polish_edit(gp_ctx* ctx, cudaStream_t es, const uint32_t* order, const uint32_t* batch_done, bool alongside)
+static int polish_edit(gp_ctx* ctx, cudaStream_t es, const uint32_t* order, uint32_t n_order, const uint32_t* batch_done, bool alongside)
 {
   const gp_config& c = ctx->cfg;
-  const uint32_t n = ctx->n_contigs;
+  const uint32_t n = order ? n_order : ctx->n_contigs; // slots of `order` this launch works through
   if (n == 0) return GP_OK;
   gp::EditParams p;
   std::memset(&p, 0, sizeof p);
@@ -922,6 +1054,7 @@ static int polish_edit(gp_ctx* ctx, cudaStream_t es, const uint32_t* order, cons
   p.node_off = ctx->d_node_off.as<uint64_t>();
   p.contig_batch = ctx->d_contig_batch.as<uint32_t>();
   p.bf_pool = ctx->d_bf_pool.as<uint32_t>();
+  p.bf_slot = ctx->bf_all_resident ? nullptr : ctx->d_bf_slot.as<uint32_t>();
   p.order = order ? order : ctx->d_order.as<uint32_t>();
   p.batch_done = batch_done;
   p.n_batches = ctx->n_batches;
@@ -976,7 +1109,7 @@ static int prep_launch(gp_ctx* ctx, int32_t mode, uint32_t k, int32_t to_upper)
 static int polish_launch(gp_ctx* ctx)
 {
   if (int rc = polish_prepare(ctx)) return rc;
-  if (int rc = polish_edit(ctx, ctx->stream, nullptr, nullptr, false)) return rc;
+  if (int rc = polish_edit(ctx, ctx->stream, nullptr, 0, nullptr, false)) return rc;
   return prep_launch(ctx, ctx->cfg.prep_mode, ctx->cfg.prep_k, ctx->cfg.to_upper);
 }
 
@@ -984,6 +1117,9 @@ int gp_polish_run(gp_ctx* ctx)
 {
   if (!ctx) return GP_ERR_ARG;
   if (!ctx->polish_staged) GP_FAIL(ctx, GP_ERR_STATE, "gp_polish_run before gp_polish_stage");
+  if (!ctx->filters_ready)
+    GP_FAIL(ctx, GP_ERR_STATE, "gp_polish_run needs the whole filter set resident (build it first; when the filters do not all fit, "
+                               "gp_pipeline_run polishes wave by wave)");
   cudaSetDevice(ctx->cfg.device);
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
   if (int rc = polish_launch(ctx)) return rc;
@@ -1046,22 +1182,24 @@ int gp_pipeline_run(gp_ctx* ctx)
     int err = 0;
     GP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->d_error.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->overlap_state = err == 2 ? -1 : 1; // 2 = its watchdog fired: this device does not co-schedule the kernels
+    if (ctx->overlap_state == 0) ctx->overlap_state = err == 2 ? -1 : 1; // 2 = its watchdog fired: this device does not co-schedule the kernels
   }
-  const bool overlap = ctx->build_algo_resolved == 2 && ctx->wave_first.size() == 1 && n && nb && !c.keep_counters &&
-                       ctx->overlap_state >= 0 && !std::getenv("GP_NO_OVERLAP");
-  if (!overlap) { // nothing to overlap with (or the in-order kernel, which fills the SMs): one after the other
+  const int algo = ctx->build_algo_resolved;
+  const bool overlap = algo == 2 && n && nb && !c.keep_counters && ctx->overlap_state >= 0 && !std::getenv("GP_NO_OVERLAP");
+  if (!overlap && ctx->bf_all_resident) { // nothing to overlap with (or the in-order kernel, which fills the SMs): one after the other
     if (int rc = gp_build_run(ctx)) return rc;
     return gp_polish_run(ctx);
   }
-  // build order: batches with the longest contigs first (their edit chains are the critical path);
-  // contigs in the build order of their batches, longest first inside a batch
+  // Launch order of the batches: (overlapped) those with the longest contigs first -- their edit chains are the critical
+  // path -- else as given; contigs in the order of their batches, longest first inside a batch.  Waves are runs of
+  // wave_batches positions of that order.
   {
     std::vector<uint32_t> maxlen(nb, 0), pos(nb, 0);
     for (uint32_t i = 0; i < n; i++) maxlen[ctx->h_batch[i]] = std::max(maxlen[ctx->h_batch[i]], ctx->h_len[i]);
     ctx->h_batch_order.resize(nb);
     std::iota(ctx->h_batch_order.begin(), ctx->h_batch_order.end(), 0u);
-    std::stable_sort(ctx->h_batch_order.begin(), ctx->h_batch_order.end(), [&](uint32_t a, uint32_t b) { return maxlen[a] > maxlen[b]; });
+    if (overlap)
+      std::stable_sort(ctx->h_batch_order.begin(), ctx->h_batch_order.end(), [&](uint32_t a, uint32_t b) { return maxlen[a] > maxlen[b]; });
     for (uint32_t i = 0; i < nb; i++) pos[ctx->h_batch_order[i]] = i;
     ctx->h_order_pipe.resize(n);
     std::iota(ctx->h_order_pipe.begin(), ctx->h_order_pipe.end(), 0u);
@@ -1069,35 +1207,65 @@ int gp_pipeline_run(gp_ctx* ctx)
       const uint32_t pa = pos[ctx->h_batch[a]], pb = pos[ctx->h_batch[b]];
       return pa != pb ? pa < pb : ctx->h_len[a] > ctx->h_len[b];
     });
+    // contigs of every wave: a contiguous range of h_order_pipe
+    ctx->h_wave_contig_off.assign(ctx->wave_first.size() + 1, 0);
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t p = pos[ctx->h_batch[i]];
+      size_t wv = ctx->wave_batches ? p / ctx->wave_batches : 0;
+      if (wv >= ctx->wave_first.size()) wv = ctx->wave_first.size() - 1;
+      ctx->h_wave_contig_off[wv + 1]++;
+    }
+    for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) ctx->h_wave_contig_off[wv + 1] += ctx->h_wave_contig_off[wv];
   }
   cudaStream_t s = ctx->stream;
-  GP_CUDA(ctx, ctx->d_batch_order.ensure(size_t(nb) * 4));
+  GP_CUDA(ctx, ctx->d_batch_order.ensure(std::max<size_t>(nb, 1) * 4));
   GP_CUDA(ctx, ctx->d_batch_done.ensure((size_t(nb) + 1) * 4));
-  GP_CUDA(ctx, ctx->d_order_pipe.ensure(size_t(n) * 4));
+  GP_CUDA(ctx, ctx->d_order_pipe.ensure(std::max<size_t>(n, 1) * 4));
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
   GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch_order.p, ctx->h_batch_order.data(), size_t(nb) * 4, cudaMemcpyHostToDevice, s));
   GP_CUDA(ctx, cudaMemcpyAsync(ctx->d_order_pipe.p, ctx->h_order_pipe.data(), size_t(n) * 4, cudaMemcpyHostToDevice, s));
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_batch_done.p, 0, (size_t(nb) + 1) * 4, s));
   GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, gp::kBuildCounters * 8, s));
-  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(nb) * c.nk * gp::kBfBytes, s));
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + 20, 0xFF, 8, s)); // first start time: atomicMin
+  GP_CUDA(ctx, cudaMemsetAsync(ctx->d_next.p, 0, ctx->wave_first.size() * 4, s));
+  const uint64_t per_bf = uint64_t(c.nk) * gp::kBfBytes;
+  if (ctx->bf_all_resident) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(nb) * per_bf, s));
+  if (int rc = upload_bf_slots(ctx, s, true)) return rc;
+  if (algo == 2)
+    if (int rc = build_stream_tab(ctx, s, true)) return rc;
   if (int rc = polish_prepare(ctx)) return rc;
-  // the build kernel (2 CTAs per SM) signals `launch_dependents` as it starts; the edit kernel (persistent,
-  // one 3-warp CTA per SM) is launched behind it in the SAME stream with programmatic stream serialization, so
-  // it becomes resident next to the running build, takes the contigs in build order and waits for each one's
-  // filters.  No event may sit between the two launches; their durations come from device timers.
-  uint32_t launches = 0;
-  if (int rc = build_launch_levels(ctx, s, true, ctx->d_batch_done.as<uint32_t>(), 2, &launches)) return rc;
-  if (int rc = polish_edit(ctx, s, ctx->d_order_pipe.as<uint32_t>(), ctx->d_batch_done.as<uint32_t>(), true)) return rc;
+  // Per wave: the build kernel (2 CTAs per SM when overlapped) signals `launch_dependents` as it starts; the edit
+  // kernel (persistent, one 3-warp CTA per SM) is launched behind it in the SAME stream with programmatic stream
+  // serialization, so it becomes resident next to the running build, takes the wave's contigs in build order and
+  // waits for each one's filters.  No event may sit between the two launches; their durations come from device
+  // timers.  The next wave's pool clear waits (stream order) for this wave's edit kernel.
+  uint32_t launches = 0, edit_launches = 0;
+  uint32_t* bd = overlap ? ctx->d_batch_done.as<uint32_t>() : nullptr;
+  for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
+    if (!ctx->bf_all_resident) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->wave_count[wv]) * per_bf, s));
+    if (algo == 2) { if (int rc = build_launch_levels_wave(ctx, s, wv, bd, overlap ? 2 : 0)) return rc; }
+    else if (int rc = build_launch_inorder_wave(ctx, s, wv)) return rc;
+    launches++;
+    const uint32_t c0 = ctx->h_wave_contig_off[wv], c1 = ctx->h_wave_contig_off[wv + 1];
+    if (c1 > c0) {
+      if (wv) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pnext.p, 0, 4, s));
+      if (int rc = polish_edit(ctx, s, ctx->d_order_pipe.as<uint32_t>() + c0, c1 - c0, bd, overlap)) return rc;
+      edit_launches++;
+    }
+    if (int rc = wave_payloads_out(ctx, s, wv, algo == 2 && ctx->bf_host_dev)) return rc;
+  }
+  ctx->bf_streamed = ctx->bf_host_user && ((algo == 2 && ctx->bf_host_dev) || !ctx->bf_all_resident);
   if (int rc = prep_launch(ctx, c.prep_mode, c.prep_k, c.to_upper)) return rc;
   GP_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
   ctx->pipelined = true;
   ctx->build_timed = true;
   ctx->polish_timed = true;
   ctx->stats.build_launches = launches;
-  ctx->stats.build_kernel = 2;
-  ctx->stats.build_slots = ctx->level_slots;
-  ctx->stats.polish_launches = 2 + ((c.prep_mode || c.to_upper) ? 1 : 0);
-  ctx->filters_ready = true;
+  ctx->stats.build_kernel = uint32_t(algo);
+  ctx->stats.build_slots = algo == 2 ? ctx->level_slots : 0;
+  ctx->stats.polish_launches = 1 + edit_launches + ((c.prep_mode || c.to_upper) ? 1 : 0);
+  ctx->filters_ready = ctx->bf_all_resident;
+  ctx->build_done = true;
   ctx->polish_done = true;
   return GP_OK;
 }
@@ -1121,16 +1289,19 @@ int gp_polish_fetch(gp_ctx* ctx, char* out_seqs, uint64_t out_cap, uint64_t* out
     GP_CUDA(ctx, cudaStreamSynchronize(s));
     if (!err) break;
     ctx->stats.polish_reruns++;
+    // the polish runs again on the device: from the resident filters, or -- when the pool only ever held one wave --
+    // as a whole new pass of the pipeline
+    auto rerun = [&]() { return ctx->filters_ready ? polish_launch(ctx) : gp_pipeline_run(ctx); };
     if (err == 2) { // pipelined edit kernel gave up waiting for filters (no co-residency): plain re-run, filters are final now
       ctx->overlap_state = -1; // remembered here: the re-run below clears d_error before gp_pipeline_run could look at it
-      if (int rc = polish_launch(ctx)) return rc;
+      if (int rc = rerun()) return rc;
       continue;
     }
-    // an edited contig outgrew its buffers: enlarge them and run the polish again on the device
+    // an edited contig outgrew its buffers: enlarge them and run the polish again
     if (ctx->grow >= 4) GP_FAIL(ctx, GP_ERR_OVERFLOW, "edited contig outgrew its device buffers");
     ctx->grow++;
     if (int rc = polish_layout(ctx)) return rc;
-    if (int rc = polish_launch(ctx)) return rc;
+    if (int rc = rerun()) return rc;
   }
   uint64_t o = 0;
   for (uint32_t i = 0; i < n; i++) {

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, GP_BUILD_MIN_CTAS) build_fil
     const uint32_t batch = p.first_batch + lb;
     const StreamConsts sc = stream_consts(p.k[ki]);
     uint8_t* __restrict__ cbf = p.cbf_pool + uint64_t(sid) * kCbfCounters;
-    uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
+    uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(p.bf_slot ? p.bf_slot[batch] : batch) * p.nk + ki) * kBfWords;
 
     const uint64_t e0 = p.batch_entry_off[batch], e1 = p.batch_entry_off[batch + 1];
     for (uint64_t e = e0; e < e1; e++) {
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kPairs * 64) build_filters_paired_kernel(Build
     if (type == kMsgQuit) break;
     if (type == kMsgBegin) {
       cbf = p.cbf_pool + uint64_t(sl->sid) * kCbfCounters;
-      bf = p.bf_pool + (uint64_t(sl->batch) * p.nk + sl->ki) * kBfWords;
+      bf = p.bf_pool + (uint64_t(p.bf_slot ? p.bf_slot[sl->batch] : sl->batch) * p.nk + sl->ki) * kBfWords;
       __syncwarp();
       tail++;
       if (lane == 0) ring->tail = tail;

@@ -394,12 +394,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 // A stream's filter is final (its last barrier has drained on this CTA): stream it to the caller's pinned
 // host buffer if there is one -- every CTA copies its slice straight over PCIe, under the following rounds, so
 // that no bulk D2H is left at the end -- and tell the edit kernel (gp_pipeline_run).
-__device__ __forceinline__ void filter_final(const LevelParams& p, uint32_t batch, uint32_t ki, uint32_t gtid, uint32_t gthreads)
+__device__ __forceinline__ void filter_final(const LevelParams& p, uint32_t batch, uint32_t ki, uint32_t slot, uint32_t gtid, uint32_t gthreads)
 {
   if (p.bf_host) {
-    const uint64_t o = (uint64_t(batch) * p.nk + ki) * kBfWords;
-    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.bf_pool + o);
-    uint4* __restrict__ dst = reinterpret_cast<uint4*>(p.bf_host + o);
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.bf_pool + (uint64_t(slot) * p.nk + ki) * kBfWords);
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(p.bf_host + (uint64_t(batch) * p.nk + ki) * kBfWords);
     for (uint32_t i = gtid; i < kBfWords / 4u; i += gthreads) dst[i] = __ldcg(src + i);
   }
   if (p.batch_done && gtid == 0) {
@@ -427,6 +426,7 @@ enum : uint32_t { MK_NONE = 0, MK_CLEAR = 1, MK_R0 = 2, MK_R1 = 3 };
 struct StreamSt {       // one stream in flight (uniform over the grid: every CTA derives the same values)
   uint32_t valid;
   uint32_t sid, batch, ki, n_steps, lread;
+  uint32_t slot;        // where its filter lives in the pool
   uint32_t buf;         // which list buffer it uses
   uint32_t cum;         // which share table it uses
   uint32_t pb;          // T_L (L >= 2) lives in array (L + pb) & 1; T_1 in array 2, or (two arrays) in (1 + pb) & 1
@@ -447,7 +447,7 @@ struct Plan {           // what one interval does; written by the planner thread
   uint32_t finished, main_kind, tail_on;
   uint32_t row0, row1, part, last_part, publish, recal; // main_kind == MK_R0
   StreamSt cur, tail;   // snapshots valid for this interval
-  uint32_t done_n, done_b[2], done_ki[2]; // streams whose last round ran in the interval before
+  uint32_t done_n, done_b[2], done_ki[2], done_slot[2]; // streams whose last round ran in the interval before
 };
 
 // 3 CTAs of 8 warps per SM (80 registers); a 64-register build with 4 CTAs spills and measured 8 % slower
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   __shared__ unsigned long long red_sh[3][kLevelWarps];
   __shared__ unsigned long long diag[kLevelDiag];       // interval-time diagnostics of this CTA (thread 0)
   if (p.batch_done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the edit kernel may join us now
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[20] = globaltimer_ns();
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(p.counters + 20, globaltimer_ns()); // (several waves: the first start)
   fill_hash_tables(tf, tr);
   LevelCtx c;
   c.tf = tf; c.tr = tr;
@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       }
       const uint32_t lmax = info.y; // largest thr of the stream (kmer_threshold - 2 + k index, utils.cpp:108,121)
       S.valid = 1; S.sid = sid; S.batch = batch; S.ki = ki; S.n_steps = info.x;
+      S.slot = p.bf_slot ? __ldg(p.bf_slot + batch) : batch;
       // levels that need a read round: up to lmax-1 for the filter bits (an insert happens at
       // L = thr-1); one more when the counter bytes themselves are wanted (who reached lmax)
       S.lread = p.cbf_pool ? lmax : lmax - 1u;
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   // what the interval after `prev` does (prev == nullptr: the first one)
   auto make_plan = [&](const Plan* prev, Plan& P) {
     P.done_n = 0;
-    auto push_done = [&](const StreamSt& S) { P.done_b[P.done_n] = S.batch; P.done_ki[P.done_n] = S.ki; P.done_n++; };
+    auto push_done = [&](const StreamSt& S) { P.done_b[P.done_n] = S.batch; P.done_ki[P.done_n] = S.ki; P.done_slot[P.done_n] = S.slot; P.done_n++; };
     if (prev) { // ---- advance both streams past the interval `prev` ----
       if (prev->tail_on) {
         if (sch.tail.L >= sch.tail.lread) { push_done(sch.tail); sch.tail.valid = 0; }
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       target += gridDim.x;
     }
     __syncthreads(); // the previous interval is complete everywhere
-    for (uint32_t i = 0; i < P.done_n; i++) filter_final(p, P.done_b[i], P.done_ki[i], gtid, gthreads);
+    for (uint32_t i = 0; i < P.done_n; i++) filter_final(p, P.done_b[i], P.done_ki[i], P.done_slot[i], gtid, gthreads);
     if (P.finished) break;
     if (planner) make_plan(&P, plans[(it + 1u) & 1u]);
     if (main_kind == MK_R0 && P.part == 0u && P.recal) {
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         const uint32_t ki = P.cur.ki, batch = P.cur.batch, cb = P.cur.buf, n_steps = P.cur.n_steps;
         const uint64_t* cum = cum_sh[P.cur.cum] + wib;
         const StreamConsts sc = stream_consts(p.k[ki]);
-        uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(batch) * p.nk + ki) * kBfWords;
+        uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(P.cur.slot) * p.nk + ki) * kBfWords;
         const SurvList lst = list_of(p, cb, n_steps, cum, c.gwarp);
         uint32_t cnt = P.part ? warp_cnt[cb][wib] : 0u;
         const uint32_t tag = P.cur.tag;
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       J.lst = list_of(p, sbuf, S->n_steps, cum_sh[S->cum] + wib, c.gwarp);
       J.V = J.L == 1u ? t1_array(*S) : p.V + ((J.L + S->pb) & 1u) * kCbfCounters;
       J.Vn = p.V + ((J.L + 1u + S->pb) & 1u) * kCbfCounters;
-      J.bf = p.bf_pool + (uint64_t(S->batch) * p.nk + S->ki) * kBfWords;
+      J.bf = p.bf_pool + (uint64_t(S->slot) * p.nk + S->ki) * kBfWords;
       J.cbf = p.cbf_pool ? p.cbf_pool + uint64_t(S->sid) * kCbfCounters : nullptr;
       J.cnt = warp_cnt[sbuf][wib];
       if (c.lane == 0) list_seen += J.cnt; // (diagnostic, flushed once at the end)
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);
   if (c.lane == 0 && ops) atomicAdd(p.counters + 0, ops);
   if (c.lane == 0 && list_seen) atomicAdd(p.counters + 17, list_seen);
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[21] = globaltimer_ns();
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(p.counters + 21, globaltimer_ns());
   if (blockIdx.x == p.report_cta && threadIdx.x == 0)
     for (uint32_t i = 0; i < kLevelDiag; i++) p.counters[kLevelDiagAt + i] += diag[i]; // several waves add up
   if (p.cta_times && threadIdx.x < kLevelDiag) p.cta_times[blockIdx.x * 32u + threadIdx.x] = diag[threadIdx.x];

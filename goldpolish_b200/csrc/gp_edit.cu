@@ -1064,7 +1064,7 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.counters[4] = t;
+    atomicMin(p.counters + 4, t); // (several launches per pass: the first start)
   }
   unsigned long long n_trig = 0, n_edit = 0, n_mask = 0, n_roll = 0;
   for (;;) {
@@ -1126,7 +1126,7 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
       w.mul1 = 1ull ^ (uint64_t(w.k) * kMultiSeed);
       w.mul2 = 2ull ^ (uint64_t(w.k) * kMultiSeed);
       w.mul3 = 3ull ^ (uint64_t(w.k) * kMultiSeed);
-      w.bf = p.bf_pool + (uint64_t(p.contig_batch[ci]) * p.nk + ki) * kBfWords;
+      w.bf = p.bf_pool + (uint64_t(p.bf_slot ? p.bf_slot[p.contig_batch[ci]] : p.contig_batch[ci]) * p.nk + ki) * kBfWords;
       w.nn = 0;
       edit_round(w);
       __syncwarp();

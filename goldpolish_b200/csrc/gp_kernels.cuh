@@ -18,7 +18,8 @@ struct BuildParams {
   const uint64_t* batch_entry_off;  // global batch index -> entries
   const gp_read_entry* entries;
   uint8_t* cbf_pool;                // wave-local: stream s at s * kCbfCounters
-  uint32_t* bf_pool;                // global: (batch * nk + ki) * kBfWords
+  uint32_t* bf_pool;                // (slot * nk + ki) * kBfWords, slot = bf_slot[batch] (the batch itself without a table)
+  const uint32_t* bf_slot;          // optional: pool slot of every batch (the pool is reused wave after wave)
   const uint32_t* stream_order;     // wave-local stream ids, longest first
   uint32_t* next_stream;            // work counter (zeroed before launch)
   unsigned long long* counters;     // [0] k-mer ops, [1] serially resolved k-mers
@@ -54,8 +55,9 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   uint32_t overlap;               // 1: a stream's late list rounds run beside round 0 / the level-1 round of the next stream
   uint32_t arrays;                // timestamp arrays in use: 3 (T_1 has its own: every late round can be joined), or 2 (only the last)
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
-  uint32_t* bf_pool;
-  uint32_t* bf_host;              // optional: device-visible pinned host copy of bf_pool, filled as filters become final
+  uint32_t* bf_pool;              // (slot * nk + ki) * kBfWords, slot = bf_slot[batch] (the batch itself without a table)
+  const uint32_t* bf_slot;        // optional: pool slot of every batch (the pool is reused wave after wave)
+  uint32_t* bf_host;              // optional: device-visible pinned host copy of ALL filters ((batch * nk + ki) * kBfWords), filled as filters become final
   unsigned long long* counters;
   unsigned long long* cta_times;  // optional: 32 words per CTA, the interval-time diagnostics of every CTA (gp_build_cta_times)
   uint32_t surv_cap;
@@ -83,7 +85,8 @@ struct EditParams {
   EdNode* nodes;                // contig i at node_off[i]
   const uint64_t* node_off;     // n_contigs + 1
   const uint32_t* contig_batch;
-  const uint32_t* bf_pool;      // (batch * nk + ki) * kBfWords
+  const uint32_t* bf_pool;      // (slot * nk + ki) * kBfWords, slot = bf_slot[batch] (the batch itself without a table)
+  const uint32_t* bf_slot;
   const uint32_t* batch_done;   // optional: per batch, finished filter streams; a contig waits for nk of them ([n_batches] = total)
   uint32_t n_batches;
   const uint32_t* order;        // contig ids, longest first

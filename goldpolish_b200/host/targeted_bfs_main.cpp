@@ -1,9 +1,15 @@
 // goldpolish-targeted-bfs (B200): drop-in for bcgsc/goldpolish src/goldpolish_targeted_bfs.cpp.
 //
 // Same argv (:250-268), same named-pipe protocol in the current directory (:148-244), same
-// "<batch>-k<K>.bf" outputs (:79-84,138-140).  Differences are internal only: the mapped reads
-// are uploaded to the GPU once, 2-bit packed; batch requests that are pending at the same time
-// are built by ONE gp_build_filters call (one warp per (batch, k) stream).
+// "<batch>-k<K>.bf" outputs (:79-84,138-140).  Differences are internal only:
+//   * the mapped reads are put on the GPU(s) once, 2-bit packed, streamed from the reads file in slabs (the host
+//     never holds the read set as text; the reference re-reads a read from the file for every use, seqindex.hpp:59-102);
+//   * batch requests that are pending at the same time are built by ONE gp_build_filters call per GPU;
+//   * batches are served by a bounded pool of workers (the reference: OpenMP tasks on `threads` threads, :177-192,
+//     223-224), never one thread per batch;
+//   * GP_DEVICES=0,1,... (or GP_DEVICE=n) names the GPUs: one context and one GPU thread per device, every request goes
+//     to the device with the fewest read bases pending.  Batches are independent (:70-77), so nothing is exchanged
+//     between devices and the answers travel back through the same FIFOs.
 #include "gp_host.hpp"
 
 #include <atomic>
@@ -53,33 +59,39 @@ void bind_to_parent()
 struct Request {
   std::string batch;
   std::vector<gp_read_entry> entries;
-  std::vector<uint8_t> payload; // nk * GP_BF_BYTES once built
+  uint64_t bases = 0;            // read bases to hash (the load estimate)
+  std::vector<uint8_t> payload;  // nk * GP_BF_BYTES once built
   bool done = false;
 };
 
-struct Server {
+// One GPU: a context, the read store, a queue of pending requests and the thread that builds them.
+struct Device {
+  int ordinal = 0;
   gp_ctx* ctx = nullptr;
   std::vector<unsigned> ks;
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   std::deque<std::shared_ptr<Request>> queue;
+  uint64_t pending_bases = 0;
+  uint64_t batches_served = 0;
   bool stopping = false;
+  std::thread thread;
 
-  // GPU worker: builds every request that is pending in one call.  The payloads land in page-locked memory
-  // that the build kernel fills filter by filter as they become final (gp_build_output_host): no bulk copy
-  // after the build, and what bfs[i]->save() writes (:138-140) is ready when the call returns.
-  void gpu_loop()
+  // builds every request that is pending in one call.  The payloads land in page-locked memory that the build
+  // kernel fills filter by filter as they become final (gp_build_output_host): no bulk copy after the build, and
+  // what bfs[i]->save() writes (:138-140) is ready when the call returns.
+  void loop()
   {
     uint8_t* pinned = nullptr;
     size_t pinned_cap = 0;
+    const size_t max_per_call = 4096; // (bounds the page-locked buffer: 8 GiB)
     for (;;) {
       std::vector<std::shared_ptr<Request>> todo;
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_work.wait(lk, [&] { return stopping || !queue.empty(); });
         if (queue.empty() && stopping) { gp_build_output_host(ctx, nullptr); gp_host_free(pinned); return; }
-        todo.assign(queue.begin(), queue.end());
-        queue.clear();
+        while (!queue.empty() && todo.size() < max_per_call) { todo.push_back(queue.front()); queue.pop_front(); }
       }
       std::vector<uint64_t> off(1, 0);
       std::vector<gp_read_entry> ents;
@@ -106,12 +118,42 @@ struct Server {
         for (size_t i = 0; i < todo.size(); i++) {
           todo[i]->payload.assign(out + i * ks.size() * GP_BF_BYTES, out + (i + 1) * ks.size() * GP_BF_BYTES);
           todo[i]->done = true;
+          pending_bases -= todo[i]->bases;
         }
+        batches_served += todo.size();
       }
       cv_done.notify_all();
     }
   }
 };
+
+// A fixed number of workers serve the batches (serve_batch, :55-146): read the target ids from the batch's pipe, select
+// the reads, hand the request to a device, write the .bf files, acknowledge.
+struct Pool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::string> batches;
+  bool closing = false;
+  std::vector<std::thread> workers;
+};
+
+std::vector<int> device_list()
+{
+  std::vector<int> v;
+  if (const char* e = std::getenv("GP_DEVICES")) {
+    std::stringstream ss(e);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) {
+      if (tok.empty()) continue;
+      char* end = nullptr;
+      const long d = std::strtol(tok.c_str(), &end, 10);
+      if (*end != '\0' || d < 0) die("GP_DEVICES must be a comma-separated list of CUDA ordinals, got '" + std::string(e) + "'");
+      v.push_back(int(d));
+    }
+  }
+  if (v.empty()) v.push_back(std::getenv("GP_DEVICE") ? std::atoi(std::getenv("GP_DEVICE")) : 0);
+  return v;
+}
 
 } // namespace
 
@@ -125,7 +167,6 @@ int main(int argc, char** argv)
   const double mx_max_per_10kbp = std::stod(argv[a++]);
   const double subsample_max_per_10kbp = std::stod(argv[a++]);
   const int threads = std::stoi(argv[a++]);
-  (void)threads; // batches are concurrent on the GPU, not on host threads
   std::vector<unsigned> ks;
   while (a < argc) ks.push_back(unsigned(std::stoi(argv[a++])));
   if (ks.empty() || ks.size() > GP_MAX_K_VALUES) die("need 1..8 k values");
@@ -141,80 +182,152 @@ int main(int argc, char** argv)
 
   gp_config cfg;
   gp_default_config(&cfg);
-  if (const char* d = std::getenv("GP_DEVICE")) cfg.device = std::atoi(d);
   cfg.nk = uint32_t(ks.size());
   for (size_t i = 0; i < ks.size(); i++) cfg.k[i] = ks[i];
-  Server srv;
-  srv.ks = ks;
-  if (gp_ctx_create(&cfg, &srv.ctx) != GP_OK) die(std::string("gp_ctx_create: ") + gp_last_error(nullptr));
+  std::vector<std::unique_ptr<Device>> devs;
+  for (const int ord : device_list()) {
+    auto d = std::make_unique<Device>();
+    d->ordinal = ord;
+    d->ks = ks;
+    cfg.device = ord;
+    if (gp_ctx_create(&cfg, &d->ctx) != GP_OK) die("gp_ctx_create (device " + std::to_string(ord) + "): " + gp_last_error(nullptr));
+    devs.push_back(std::move(d));
+  }
 
-  // every read that some target maps: uploaded once (SeqIndex::get_seq<1> re-reads per use)
+  // every read that some target maps goes to every device once (SeqIndex::get_seq<1> re-reads per use), streamed from
+  // the file in slabs: the host holds one slab of text at a time
   std::unordered_map<std::string, uint32_t> read_slot;
   {
-    std::string all, one;
-    std::vector<uint64_t> off(1, 0);
+    std::vector<const std::string*> order;
+    std::vector<uint32_t> lens;
+    uint64_t total = 0;
     for (const auto& kv : maps.all())
       for (const auto& id : kv.second)
-        if (read_slot.find(id) == read_slot.end()) {
-          read_slot.emplace(id, uint32_t(off.size() - 1));
-          reads.read_seq(id, one);
-          all += one;
-          off.push_back(all.size());
+        if (read_slot.emplace(id, uint32_t(order.size())).second) {
+          order.push_back(&id);
+          lens.push_back(uint32_t(reads.at(id).len));
+          total += lens.back();
         }
-    info("Uploading " + std::to_string(off.size() - 1) + " mapped reads (" + std::to_string(all.size()) + " bases)");
-    check_gp(srv.ctx, gp_reads_upload(srv.ctx, all.data(), off.data(), off.size() - 1), "gp_reads_upload");
+    info("Uploading " + std::to_string(order.size()) + " mapped reads (" + std::to_string(total) + " bases) to " +
+         std::to_string(devs.size()) + " device(s)");
+    for (auto& d : devs) check_gp(d->ctx, gp_reads_begin(d->ctx, order.size(), lens.data()), "gp_reads_begin");
+    const size_t slab_bytes = 64u << 20;
+    std::string slab, one;
+    size_t in_slab = 0;
+    auto flush = [&] {
+      if (in_slab == 0) return;
+      for (auto& d : devs) check_gp(d->ctx, gp_reads_append(d->ctx, slab.data(), in_slab), "gp_reads_append");
+      slab.clear();
+      in_slab = 0;
+    };
+    for (const std::string* id : order) {
+      reads.read_seq(*id, one);
+      if (in_slab && slab.size() + one.size() > slab_bytes) flush();
+      slab += one;
+      in_slab++;
+    }
+    flush();
+    for (auto& d : devs) check_gp(d->ctx, gp_reads_end(d->ctx), "gp_reads_end");
   }
 
   make_pipe(BATCH_NAME_INPUT_PIPE);
   make_pipe(BATCH_TARGET_IDS_INPUT_READY_PIPE);
   info("Accepting batch names at " + BATCH_NAME_INPUT_PIPE);
-  std::thread gpu(&Server::gpu_loop, &srv);
-  std::vector<std::thread> workers;
+  for (auto& d : devs) d->thread = std::thread(&Device::loop, d.get());
+
+  auto serve_batch = [&](const std::string& batch) { // :55-146
+    const std::string ids_pipe = batch + "-target_ids_input", ready_pipe = batch + "-bfs_ready";
+    auto req = std::make_shared<Request>();
+    req->batch = batch;
+    {
+      std::ifstream in(ids_pipe);
+      std::string id;
+      while (bool(in >> id) && id != END_SYMBOL) {
+        const uint64_t tlen = targets.at(id).len;
+        const auto& mapped = maps.get(id);
+        if (mapped.empty()) continue;
+        const Selection sel = select_reads(mapped, reads, tlen, subsample_max_per_10kbp);
+        for (const auto& r : sel.reads) {
+          req->entries.push_back(gp_read_entry{ read_slot.at(r), uint32_t(sel.kmer_threshold) });
+          req->bases += reads.at(r).len;
+        }
+      }
+    }
+    // the device with the least work pending
+    Device* dev = devs[0].get();
+    if (devs.size() > 1) {
+      uint64_t best = ~0ull;
+      for (auto& d : devs) {
+        std::lock_guard<std::mutex> lk(d->mu);
+        if (d->pending_bases < best) { best = d->pending_bases; dev = d.get(); }
+      }
+    }
+    {
+      std::unique_lock<std::mutex> lk(dev->mu);
+      dev->pending_bases += req->bases;
+      dev->queue.push_back(req);
+      dev->cv_work.notify_one();
+      dev->cv_done.wait(lk, [&] { return req->done; });
+    }
+    for (size_t i = 0; i < ks.size(); i++)
+      bf_format::save(batch + "-k" + std::to_string(ks[i]) + ".bf", req->payload.data() + i * GP_BF_BYTES, GP_BF_BYTES,
+                      GP_HASH_NUM, ks[i]);
+    confirm_pipe(ready_pipe);
+    std::remove(ids_pipe.c_str());
+    std::remove(ready_pipe.c_str());
+  };
+
+  // The workers mostly wait -- for a client to write its ids, for the GPU -- so there are more of them than the
+  // `threads` the reference computes with; the number of batches in flight, and with it the size of a GPU call, is
+  // bounded by it.  GP_SERVER_WORKERS overrides.
+  size_t n_workers = size_t(std::max(2, threads)) * 4;
+  if (n_workers > 256) n_workers = 256;
+  if (const char* e = std::getenv("GP_SERVER_WORKERS")) n_workers = size_t(std::max(1, std::atoi(e)));
+  Pool pool;
+  for (size_t w = 0; w < n_workers; w++)
+    pool.workers.emplace_back([&] {
+      for (;;) {
+        std::string batch;
+        {
+          std::unique_lock<std::mutex> lk(pool.mu);
+          pool.cv.wait(lk, [&] { return pool.closing || !pool.batches.empty(); });
+          if (pool.batches.empty()) return;
+          batch = std::move(pool.batches.front());
+          pool.batches.pop_front();
+        }
+        serve_batch(batch);
+      }
+    });
   for (;;) { // process_batch_name, :148-195
     const std::string batch = read_pipe(BATCH_NAME_INPUT_PIPE);
     if (batch.empty() || batch == END_SYMBOL) break;
-    const std::string ids_pipe = batch + "-target_ids_input", ready_pipe = batch + "-bfs_ready";
-    make_pipe(ids_pipe);
-    make_pipe(ready_pipe);
+    make_pipe(batch + "-target_ids_input");
+    make_pipe(batch + "-bfs_ready");
     confirm_pipe(BATCH_TARGET_IDS_INPUT_READY_PIPE);
-    workers.emplace_back([&, batch, ids_pipe, ready_pipe] { // serve_batch, :55-146
-      auto req = std::make_shared<Request>();
-      req->batch = batch;
-      {
-        std::ifstream in(ids_pipe);
-        std::string id;
-        while (bool(in >> id) && id != END_SYMBOL) {
-          const uint64_t tlen = targets.at(id).len;
-          const auto& mapped = maps.get(id);
-          if (mapped.empty()) continue;
-          const Selection sel = select_reads(mapped, reads, tlen, subsample_max_per_10kbp);
-          for (const auto& r : sel.reads) req->entries.push_back(gp_read_entry{ read_slot.at(r), uint32_t(sel.kmer_threshold) });
-        }
-      }
-      {
-        std::unique_lock<std::mutex> lk(srv.mu);
-        srv.queue.push_back(req);
-        srv.cv_work.notify_one();
-        srv.cv_done.wait(lk, [&] { return req->done; });
-      }
-      for (size_t i = 0; i < ks.size(); i++)
-        bf_format::save(batch + "-k" + std::to_string(ks[i]) + ".bf", req->payload.data() + i * GP_BF_BYTES, GP_BF_BYTES,
-                        GP_HASH_NUM, ks[i]);
-      confirm_pipe(ready_pipe);
-      std::remove(ids_pipe.c_str());
-      std::remove(ready_pipe.c_str());
-    });
+    {
+      std::lock_guard<std::mutex> lk(pool.mu);
+      pool.batches.push_back(batch);
+    }
+    pool.cv.notify_one();
   }
-  for (auto& w : workers) w.join();
   {
-    std::lock_guard<std::mutex> lk(srv.mu);
-    srv.stopping = true;
+    std::lock_guard<std::mutex> lk(pool.mu);
+    pool.closing = true;
   }
-  srv.cv_work.notify_all();
-  gpu.join();
+  pool.cv.notify_all();
+  for (auto& w : pool.workers) w.join();
+  for (auto& d : devs) {
+    {
+      std::lock_guard<std::mutex> lk(d->mu);
+      d->stopping = true;
+    }
+    d->cv_work.notify_all();
+    d->thread.join();
+    info("device " + std::to_string(d->ordinal) + ": " + std::to_string(d->batches_served) + " batches served");
+    gp_ctx_destroy(d->ctx);
+  }
   std::remove(BATCH_NAME_INPUT_PIPE.c_str());
   std::remove(BATCH_TARGET_IDS_INPUT_READY_PIPE.c_str());
-  gp_ctx_destroy(srv.ctx);
   info("Targeted BF builder done!");
   return 0;
 }

@@ -77,6 +77,11 @@ typedef struct {
   int32_t prep_mode;               /* 0 off, 1 = goldpolish-mask -s (soft), 2 = goldpolish-mask -n (hard) */
   uint32_t prep_k;                 /* its -k (scripts/goldpolish-make:66 passes the first k value); 1..64 */
   int32_t to_upper;                /* 1: upper-case the records (after masking, if any) */
+  /* cap on batches whose Bloom filters (nk x 512 KiB each) are resident at once; 0 = every batch of a call when they fit
+   * (at most half of the free device memory), else as many as fit.  When fewer than all are resident the pool is reused
+   * wave after wave: gp_pipeline_run polishes every wave before its filters go and gp_build_output_host receives the
+   * payloads; gp_build_run needs that destination, and a separate gp_polish is not possible. */
+  uint32_t max_resident_filters;
 } gp_config;
 
 /* one read handed to fill_bfs: index into the uploaded read store + the target's kmer_threshold */
@@ -122,6 +127,14 @@ int gp_get_stats(const gp_ctx* ctx, gp_stats* out);
 /* seqs: ASCII bases of all reads back to back; read i = seqs[offsets[i] .. offsets[i+1]).
  * Host buffers; copied to the device and packed there.  Replaces any previous store. */
 int gp_reads_upload(gp_ctx* ctx, const char* seqs, const uint64_t* offsets, uint64_t n_reads);
+/* The same store filled piecewise, for callers that read sequences from a file as they go (the reference reads every
+ * sequence on demand, src/seqindex.hpp:59-102): announce all read lengths, then append the bases of consecutive reads
+ * (back to back, any number of reads per call, in read order), then end.  Neither side ever holds the whole read set
+ * as text: the device stages at most 256 MiB (or the longest read) of ASCII per slab, packs it (2 bits + 1 mask bit per
+ * base) and reuses the staging; gp_reads_upload is begin + one append + end.  Replaces any previous store. */
+int gp_reads_begin(gp_ctx* ctx, uint64_t n_reads, const uint32_t* lens);
+int gp_reads_append(gp_ctx* ctx, const char* seqs, uint64_t n_reads_in_this_call);
+int gp_reads_end(gp_ctx* ctx);
 
 /* ---- filter build ----------------------------------------------------------------- */
 /* Batch b hashes entries[batch_entry_off[b] .. batch_entry_off[b+1]) in that order, every read

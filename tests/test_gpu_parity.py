@@ -244,3 +244,62 @@ def test_polish_identity_filters(gp, small):
             assert got.upper() == d.contig(c).upper() and len(got) == len(d.contig(c))
             want = oracle_polish_contig(d.contig(c), [np.zeros(gp.BF_BYTES, np.uint8)] * 4)
             assert got == want
+
+
+def test_read_store_piecewise_and_small_slabs(gp, monkeypatch):
+    """gp_reads_begin / _append / _end (any split of the reads into pieces, device staging slabs far smaller than the
+    store) builds the same packed store as gp_reads_upload: same filters."""
+    d = dataset(genome_len=60000)
+    pl = plan(d, bsize=2)
+    with gp.Context() as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        a = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    monkeypatch.setenv("GP_READ_SLAB_BYTES", "50000")
+    lens = np.diff(d.read_off)
+    cuts = [0, 1, 2, 7, d.n_reads // 2, d.n_reads - 1, d.n_reads]
+    pieces = [(d.read_seq[d.read_off[i]:d.read_off[j]], j - i) for i, j in zip(cuts[:-1], cuts[1:])]
+    with gp.Context() as ctx:
+        ctx.upload_reads_piecewise(lens, pieces)
+        b = ctx.build_filters(pl.batch_entry_off, pl.entries)
+        ctx.upload_reads(d.read_seq, d.read_off)  # (slabbed through the same path)
+        c = ctx.build_filters(pl.batch_entry_off, pl.entries)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("algo", ["l", "s"])
+def test_bounded_filter_pool_waves(gp, algo, monkeypatch):
+    """max_resident_filters: the filter pool holds 2 batches at a time and is reused wave after wave; the overlapped
+    pipeline polishes every wave before its filters go and the payloads arrive in the named page-locked buffer.  Same
+    payloads, same polished records as with every filter resident; the calls that cannot work say so."""
+    import torch
+    monkeypatch.setenv("GP_BUILD_KERNEL", algo)
+    d = dataset(genome_len=60000)
+    pl = plan(d, bsize=1)
+    nb = len(pl.batch_entry_off) - 1
+    assert nb >= 5
+    with gp.Context() as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        ref_bf = ctx.build_filters(pl.batch_entry_off, pl.entries)
+        ref_out, ref_off, ref_dropped = ctx.polish(d.contig_seq, d.contig_off, pl.contig_batch)
+    pinned = torch.zeros((nb, 4, gp.BF_BYTES), dtype=torch.uint8).pin_memory()
+    with gp.Context(max_resident_filters=2) as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        ctx.build_stage(pl.batch_entry_off, pl.entries)
+        with pytest.raises(gp.GpError):
+            ctx.build_run()                      # nowhere to put the payloads of the earlier waves
+        ctx.build_output(pinned)
+        ctx.build_run()
+        got = ctx.build_fetch(out=pinned)
+        assert np.array_equal(got.numpy(), ref_bf)
+        with pytest.raises(gp.GpError):
+            ctx.build_fetch()                    # a pageable destination cannot be served any more
+        ctx.polish_stage(d.contig_seq, d.contig_off, pl.contig_batch)
+        with pytest.raises(gp.GpError):
+            ctx.polish_run()                     # needs every filter resident
+        pinned.zero_()
+        ctx.pipeline_run()
+        assert ctx.stats()["build_launches"] == (nb + 1) // 2
+        assert np.array_equal(ctx.build_fetch(out=pinned).numpy(), ref_bf)
+        out, off, dropped = ctx.polish_fetch()
+        assert np.array_equal(off, ref_off) and np.array_equal(dropped, ref_dropped)
+        assert np.array_equal(out[:int(off[-1])], ref_out[:int(ref_off[-1])])

@@ -197,3 +197,55 @@ def test_index_tool_threads_and_odd_inputs():
         assert subprocess.run([os.path.join(BIN, "goldpolish-index"), bad, bad + ".idx"], env=ENV, capture_output=True).returncode == 1
         if os.path.exists(ref):
             assert subprocess.run([ref, bad, bad + ".ref"], env=ENV, capture_output=True).returncode == 1
+
+
+@pytest.mark.gpu
+def test_fifo_server_two_devices_bounded_workers_concurrent_clients():
+    """GP_DEVICES: one context + GPU thread per listed device, requests dealt by pending read bases; a bounded worker
+    pool (3 workers for 9+ batches); clients that talk to the server concurrently, as the reference's driver does with
+    its up-to-200 goldpolish-polish-batch processes (scripts/goldpolish:363-426).  Same payloads as the reference server."""
+    import threading
+
+    import sim
+    import torch
+    from oracle import ref_driver as rd
+    g = _load("filters.json")
+    case = g["cases"][0]
+    devices = "0,1" if torch.cuda.device_count() >= 2 else "0,0"  # (two contexts on one GPU exercise the same code)
+    env = dict(ENV, GP_DEVICES=devices, GP_SERVER_WORKERS="3")
+    with _tmp() as w:
+        d = sim.simulate(write_dir=w, **case["sim"])
+        reads = os.path.join(w, "reads.fq" if d.fastq else "reads.fa")
+        for f in (os.path.join(w, "draft.fa"), reads):
+            subprocess.check_call([os.path.join(BIN, "goldpolish-index"), f, f + ".index"], env=ENV)
+        bs = case["bsize"]
+        bdir = os.path.join(w, "bfs")
+        nb = len(case["batches"])
+        results = {}
+        with rd.BfServer(bdir, os.path.join(w, "draft.fa"), os.path.join(w, "draft.fa.index"), os.path.join(w, "mappings.paf"),
+                         reads, reads + ".index", threads=2, binary=os.path.join(BIN, "goldpolish-targeted-bfs"), env=env) as srv:
+            rounds = 3  # every batch three times under different names: 3 * nb requests in flight
+            names = [f"{r}_{b}" for r in range(rounds) for b in range(nb)]
+            for name in names:  # the handshake on the shared pipes is sequential (scripts/goldpolish:381-384)
+                with open(os.path.join(bdir, "batch_name_input"), "w") as f:
+                    f.write(name + "\n")
+                with open(os.path.join(bdir, "batch_target_ids_input_ready")) as f:
+                    f.read()
+
+            def client(name):
+                b = int(name.split("_")[1])
+                with open(os.path.join(bdir, f"{name}-target_ids_input"), "w") as f:
+                    for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
+                        f.write(d.contig_name(c) + "\n")
+                with open(os.path.join(bdir, f"{name}-bfs_ready")) as f:
+                    f.read()
+                results[name] = [sha(_parse_bf(os.path.join(bdir, f"{name}-k{k}.bf"))[1]) for k in KS]
+
+            ths = [threading.Thread(target=client, args=(n,)) for n in names]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join(timeout=300)
+            assert all(not t.is_alive() for t in ths)
+        for name in names:
+            assert results[name] == case["batches"][int(name.split("_")[1])]["server_bf_sha256"], name

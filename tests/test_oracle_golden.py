@@ -199,3 +199,27 @@ def test_oracle_matches_reference_live():
                 break
             assert got == buf[:n].tobytes()
             cur = got
+
+
+def test_python_planner_ntlink_filter_matches_reference_server():
+    """ntLink-style triples: the planner's minimizer filter (goldpolish_b200/host.py::filter_ntlink, a restatement of
+    AllMappings::filter, src/mappings.cpp:230-320) selects the reads the reference's own server selected -- the
+    filters built from its entries equal the payloads that server wrote (binary search on the minimizer threshold at
+    mx_max = 12 per 10 kbp, so the filter really drops reads)."""
+    import sim
+    import goldpolish_b200 as gp
+    case = _load("filters.json")["ntlink"]
+    d = sim.simulate(**case["sim"])
+    pl = gp.plan_batches(np.diff(d.contig_off), [d.contig_name(i) for i in range(d.n_contigs)],
+                         [d.read_name(i) for i in range(d.n_reads)], d.read_phred, np.diff(d.read_off),
+                         d.map_read, d.map_contig, bsize=case["bsize"], subsample_max_per_10kbp=case["subsample_max"],
+                         map_mx=d.map_mx, mx_max_per_10kbp=case["mx_max"])
+    unfiltered = gp.plan_batches(np.diff(d.contig_off), [d.contig_name(i) for i in range(d.n_contigs)],
+                                 [d.read_name(i) for i in range(d.n_reads)], d.read_phred, np.diff(d.read_off),
+                                 d.map_read, d.map_contig, bsize=case["bsize"], subsample_max_per_10kbp=case["subsample_max"])
+    assert len(pl.entries) < len(unfiltered.entries)
+    for b, rec in enumerate(case["batches"]):
+        fs = ol.FilterSet(KS)
+        for e in pl.entries[int(pl.batch_entry_off[b]):int(pl.batch_entry_off[b + 1])]:
+            fs.add_read(d.read(int(e["read_id"])), int(e["kmer_threshold"]))
+        assert [sha(x) for x in fs.bfs] == rec["server_bf_sha256"], b
