@@ -7,6 +7,9 @@
 //   * batch requests that are pending at the same time are built by ONE gp_build_filters call per GPU;
 //   * batches are served by a bounded pool of workers (the reference: OpenMP tasks on `threads` threads, :177-192,
 //     223-224), never one thread per batch;
+//   * a client may append "@polish <batch.fa> <out.fa>" to its target ids (goldpolish_b200's goldpolish-polish-batch
+//     does): the batch is then polished in the same GPU pass that builds its filters, and <out.fa> is what
+//     goldpolish-ntedit would have produced from the .bf files (k chain + 0.75 guard);
 //   * GP_DEVICES=0,1,... (or GP_DEVICE=n) names the GPUs: one context and one GPU thread per device, every request goes
 //     to the device with the fewest read bases pending.  Batches are independent (:70-77), so nothing is exchanged
 //     between devices and the answers travel back through the same FIFOs.
@@ -62,6 +65,14 @@ struct Request {
   uint64_t bases = 0;            // read bases to hash (the load estimate)
   std::vector<uint8_t> payload;  // nk * GP_BF_BYTES once built
   bool done = false;
+  // "@polish <batch.fa> <out.fa>" after the target ids (goldpolish_b200's own goldpolish-polish-batch sends it): the
+  // batch's contigs are polished in the same GPU pass as its filters are built (gp_pipeline_run) -- what
+  // goldpolish-make's `%.ntedited.fa` rule would do with goldpolish-ntedit and four ntedit-gr processes
+  bool polish = false;
+  std::string seqs_path, out_path;
+  std::vector<FastaRecord> recs;
+  std::vector<std::string> polished;   // one per record ("" + dropped flag when the reference would not emit it)
+  std::vector<uint8_t> dropped;
 };
 
 // One GPU: a context, the read store, a queue of pending requests and the thread that builds them.
@@ -112,7 +123,39 @@ struct Device {
       }
       if (pinned) out = pinned;
       else { pageable.resize(need); out = pageable.data(); } // no page-locked memory to be had: plain copy
-      check_gp(ctx, gp_build_filters(ctx, uint32_t(todo.size()), off.data(), ents.data(), out), "gp_build_filters");
+      bool any_polish = false;
+      for (const auto& r : todo) any_polish |= r->polish;
+      if (!any_polish) {
+        check_gp(ctx, gp_build_filters(ctx, uint32_t(todo.size()), off.data(), ents.data(), out), "gp_build_filters");
+      } else {
+        // filters of every request + the k chain over the contigs of those that asked for it, as one overlapped pass
+        std::string seqs;
+        std::vector<uint64_t> coff(1, 0);
+        std::vector<uint32_t> cbatch;
+        for (size_t i = 0; i < todo.size(); i++)
+          if (todo[i]->polish)
+            for (const auto& rec : todo[i]->recs) { seqs += rec.seq; coff.push_back(seqs.size()); cbatch.push_back(uint32_t(i)); }
+        check_gp(ctx, gp_build_stage(ctx, uint32_t(todo.size()), off.data(), ents.data()), "gp_build_stage");
+        check_gp(ctx, gp_polish_stage(ctx, uint32_t(cbatch.size()), seqs.data(), coff.data(), cbatch.data()), "gp_polish_stage");
+        check_gp(ctx, gp_pipeline_run(ctx), "gp_pipeline_run");
+        check_gp(ctx, gp_build_fetch(ctx, out), "gp_build_fetch");
+        std::vector<char> pout(seqs.size() + seqs.size() / 2 + 65536);
+        std::vector<uint64_t> poff(cbatch.size() + 1);
+        std::vector<uint8_t> dropped(cbatch.size() + 1);
+        int rc = gp_polish_fetch(ctx, pout.data(), pout.size(), poff.data(), dropped.data());
+        if (rc == GP_ERR_ARG && poff[cbatch.size()] > pout.size()) {
+          pout.resize(poff[cbatch.size()]);
+          rc = gp_polish_fetch(ctx, pout.data(), pout.size(), poff.data(), dropped.data());
+        }
+        check_gp(ctx, rc, "gp_polish_fetch");
+        size_t c = 0;
+        for (size_t i = 0; i < todo.size(); i++)
+          if (todo[i]->polish)
+            for (size_t j = 0; j < todo[i]->recs.size(); j++, c++) {
+              todo[i]->polished.emplace_back(pout.data() + poff[c], size_t(poff[c + 1] - poff[c]));
+              todo[i]->dropped.push_back(dropped[c]);
+            }
+      }
       {
         std::lock_guard<std::mutex> lk(mu);
         for (size_t i = 0; i < todo.size(); i++) {
@@ -243,6 +286,11 @@ int main(int argc, char** argv)
       std::ifstream in(ids_pipe);
       std::string id;
       while (bool(in >> id) && id != END_SYMBOL) {
+        if (id == "@polish") { // (not a valid FASTA id: '@' opens a FASTQ header)
+          if (!(in >> req->seqs_path >> req->out_path)) die("malformed @polish request for batch " + batch);
+          req->polish = true;
+          continue;
+        }
         const uint64_t tlen = targets.at(id).len;
         const auto& mapped = maps.get(id);
         if (mapped.empty()) continue;
@@ -252,6 +300,13 @@ int main(int argc, char** argv)
           req->bases += reads.at(r).len;
         }
       }
+    }
+    uint64_t input_size = 0;
+    if (req->polish) {
+      struct stat st;
+      if (stat(req->seqs_path.c_str(), &st) != 0) die("cannot stat " + req->seqs_path);
+      input_size = uint64_t(st.st_size);
+      req->recs = read_fasta(req->seqs_path);
     }
     // the device with the least work pending
     Device* dev = devs[0].get();
@@ -272,6 +327,21 @@ int main(int argc, char** argv)
     for (size_t i = 0; i < ks.size(); i++)
       bf_format::save(batch + "-k" + std::to_string(ks[i]) + ".bf", req->payload.data() + i * GP_BF_BYTES, GP_BF_BYTES,
                       GP_HASH_NUM, ks[i]);
+    if (req->polish) { // after the .bf files: `make` must not find the polished file older than its prerequisites
+      std::string body;
+      for (size_t i = 0; i < req->recs.size(); i++) {
+        if (req->dropped[i]) continue; // ntedit.cpp:1850
+        body += ">" + req->recs[i].name + (req->recs[i].comment.empty() ? "" : " " + req->recs[i].comment) + "\n";
+        body += req->polished[i];
+        body += "\n";
+      }
+      std::ofstream o(req->out_path, std::ios::binary);
+      if (!o.good()) die("cannot write " + req->out_path);
+      if (gp_guard_rejects(input_size, body.size())) { // scripts/goldpolish-ntedit:31-37: keep the input
+        std::ifstream in(req->seqs_path, std::ios::binary);
+        o << in.rdbuf();
+      } else o << body;
+    }
     confirm_pipe(ready_pipe);
     std::remove(ids_pipe.c_str());
     std::remove(ready_pipe.c_str());

@@ -249,3 +249,67 @@ def test_fifo_server_two_devices_bounded_workers_concurrent_clients():
             assert all(not t.is_alive() for t in ths)
         for name in names:
             assert results[name] == case["batches"][int(name.split("_")[1])]["server_bf_sha256"], name
+
+
+@pytest.mark.gpu
+def test_polish_batch_dropin_fused_with_the_server():
+    """goldpolish_b200's goldpolish-polish-batch (same command line as scripts/goldpolish-polish-batch:24-54) asks the
+    server to polish the batch in the GPU pass that builds its filters; `batch.ntedited.fa` then equals what the
+    reference's goldpolish-ntedit flow (its own ntedit-gr, k chain + guard) makes of the same batch's .bf files, the .bf
+    files are deleted afterwards and the done-pipe is signalled."""
+    import shutil
+    import threading
+
+    import sim
+    from oracle import ref_driver as rd
+    if not rd.ref_available():
+        pytest.skip("oracle/_ref not built")
+    g = _load("filters.json")
+    case = g["cases"][1]
+    with _tmp() as w:
+        d = sim.simulate(write_dir=w, **case["sim"])
+        reads = os.path.join(w, "reads.fq" if d.fastq else "reads.fa")
+        for f in (os.path.join(w, "draft.fa"), reads):
+            subprocess.check_call([os.path.join(BIN, "goldpolish-index"), f, f + ".index"], env=ENV)
+        bs = case["bsize"]
+        bdir = os.path.join(w, "bfs")
+        with rd.BfServer(bdir, os.path.join(w, "draft.fa"), os.path.join(w, "draft.fa.index"), os.path.join(w, "mappings.paf"),
+                         reads, reads + ".index", threads=2, binary=os.path.join(BIN, "goldpolish-targeted-bfs"), env=ENV) as srv:
+            for b in range(len(case["batches"])):
+                cs = list(range(b * bs, min((b + 1) * bs, d.n_contigs)))
+                ids = [d.contig_name(c) for c in cs]
+                # expected: plain protocol, then the reference's own ntedit-gr chain + guard on the .bf files
+                plain = os.path.join(w, f"plain{b}")
+                os.makedirs(plain)
+                with open(os.path.join(plain, "batch.fa"), "w") as f:
+                    for c in cs:
+                        f.write(f">{d.contig_name(c)}\n{d.contig(c).decode()}\n")
+                paths = srv.build(f"p{b}", ids)
+                chosen, _ = rd.run_ntedit_chain(os.path.join(plain, "batch"), [paths[k] for k in KS])
+                expected = open(chosen).read()
+                # drop-in: the reference driver's steps (scripts/goldpolish:363-426), then our polish-batch
+                fused = os.path.join(w, f"fused{b}")
+                os.makedirs(fused)
+                shutil.copy(os.path.join(plain, "batch.fa"), os.path.join(fused, "batch.fa"))
+                with open(os.path.join(fused, "seq_ids"), "w") as f:
+                    f.write("\n".join(ids) + "\n")
+                done_pipe = os.path.join(fused, "polishing_done")
+                os.mkfifo(done_pipe)
+                name = f"f{b}"
+                with open(os.path.join(bdir, "batch_name_input"), "w") as f:
+                    f.write(name + "\n")
+                with open(os.path.join(bdir, "batch_target_ids_input_ready")) as f:
+                    f.read()
+                got_done = []
+                t = threading.Thread(target=lambda: got_done.append(open(done_pipe).read()))
+                t.start()
+                subprocess.check_call([os.path.join(BIN, "goldpolish-polish-batch"), "batch.fa", bdir, w, "pre", "4",
+                                       "-k32", "-k28", "-k24", "-k20"] + [f"-b{name}-k{k}.bf" for k in KS] +
+                                      ["--seq-ids", "seq_ids", "--bfs-ids-pipe", f"{name}-target_ids_input",
+                                       "--bfs-ready-pipe", f"{name}-bfs_ready", "--batch-done-pipe", done_pipe, "-t", "1"],
+                                      cwd=fused, env=dict(ENV, GP_POLISH_BATCH_STOP_AFTER="ntedit",
+                                                          PATH=BIN + os.pathsep + os.environ.get("PATH", "")))
+                t.join(timeout=60)
+                assert got_done and got_done[0].strip() == "1"
+                assert open(os.path.join(fused, "batch.ntedited.fa")).read() == expected, b
+                assert not any(os.path.exists(os.path.join(bdir, f"{name}-k{k}.bf")) for k in KS)

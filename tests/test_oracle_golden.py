@@ -223,3 +223,37 @@ def test_python_planner_ntlink_filter_matches_reference_server():
         for e in pl.entries[int(pl.batch_entry_off[b]):int(pl.batch_entry_off[b + 1])]:
             fs.add_read(d.read(int(e["read_id"])), int(e["kmer_threshold"]))
         assert [sha(x) for x in fs.bfs] == rec["server_bf_sha256"], b
+
+
+def test_reference_fixture_batches_through_the_port():
+    """configs[0] on the CPU: the reference's in-tree draft fixture (committed gzip) + reads simulated from its in-tree
+    expected output; the C restatement reproduces the reference's own filters and polished record (k chain + guard) of
+    a few batches -- read selection by (truncated phred, id), thresholds, FASTQ index semantics included."""
+    import fixture_reads as fr
+    g = _load("fixtures.json")
+    for which, picks in (("config1", (0, 57, 151)), ("target", (0, 6))):
+        draft, truth = fr.load_fixture(which)
+        reads, maps = fr.simulate_reads(truth)
+        gg = g[which]
+        assert len(reads) == gg["n_reads"] and sum(len(s) for _, s, _ in reads) == gg["read_bases"]
+        seq_of = {n: s for n, s, _ in reads}
+        phred_of = {n: float(q - 33) for n, s, q in reads}  # constant quality: mean of all but the last char - 33
+        by_contig = {}
+        for r, c, *_ in maps:
+            by_contig.setdefault(c, []).append(r)
+        for b in picks:
+            name, seq = draft[b]
+            ids = by_contig[name]
+            chosen, thr = ol.select_reads(ids, [phred_of[i] for i in ids], [len(seq_of[i]) for i in ids], len(seq), 40.0)
+            fs = ol.FilterSet(KS)
+            for j in chosen:
+                fs.add_read(seq_of[ids[j]], thr)
+            assert [sha(x) for x in fs.bfs] == gg["batches"][b]["bf_sha256"], (which, b)
+            cur = seq
+            for ki, k in enumerate(KS):
+                cur, _ = ol.ntedit_contig(cur, fs.bfs[ki], k)
+            rec_in = b">" + name.encode() + b"\n" + seq + b"\n"
+            rec_out = b">" + name.encode() + b"\n" + cur + b"\n"
+            if ol.lib().gpo_guard_rejects(len(rec_in), len(rec_out)):
+                rec_out = rec_in
+            assert sha(rec_out) == gg["batches"][b]["polished_sha256"], (which, b)
