@@ -3,8 +3,8 @@
 # usage: profiles/run_ncu.sh <tag> [extra bench args]  -> gpurun_out/{plain,launches,prof_build,prof_edit}_<tag>.*
 # Every ncu pass runs only after the same command exited 0 without ncu; numbers printed under ncu are not bench values.
 set -u
-TAG=${1:-r1}; shift || true
-ARGS="--steps 2 --warmup 3 --genome-len 1000000 --no-cpu-baseline --no-roof $*"
+TAG=${1:-r2}; shift || true
+ARGS="--config 2 --steps 2 --warmup 3 --genome-len 1000000 --no-cpu-baseline --no-roof $*"
 mkdir -p gpurun_out
 python bench.py $ARGS --separate > gpurun_out/plain_separate_$TAG.json 2> gpurun_out/plain_separate_$TAG.log
 python bench.py $ARGS > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.log &&
