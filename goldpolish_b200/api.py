@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libgoldpolish_b200.so")
+    """The CUDA library built in-tree (GP_LIB_PATH: another build of it, for A/B experiments)."""
+    return os.environ.get("GP_LIB_PATH") or os.path.join(_HERE, "libgoldpolish_b200.so")
 
 
 class GpError(RuntimeError):

@@ -80,7 +80,7 @@ struct gp_ctx {
   DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel, d_cta_times;
   uint32_t level_grid = 0; // CTAs of the last level-synchronous launch
   uint64_t anchor_stride = 0;
-  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_time_bits = 26;
+  uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_time_bits = 26, level_arrays = 2;
   bool levels_ok = false; // every stream fits the 26-bit occurrence clock
   int build_algo = 0;     // 0 = auto, 1 = warp per stream, 2 = level-synchronous
   int build_algo_resolved = 1;
@@ -478,12 +478,14 @@ int gp_build_stage(gp_ctx* ctx, uint32_t n_batches, const uint64_t* batch_entry_
     while (ctx->level_time_bits < 26 && (max_steps * 32) >> ctx->level_time_bits) ctx->level_time_bits++;
     GP_CUDA(ctx, ctx->d_step_pre.ensure(pre.size() * 4));
     GP_CUDA(ctx, ctx->d_batch_max_thr.ensure(maxthr.size() * 4));
-    // level-synchronous kernel: three timestamp arrays (T_1, and two that alternate for the levels above it) serve two
-    // streams in flight -- the late list rounds of one stream run beside round 0 / the level-1 round of the next
-    // (GP_LEVEL_OVERLAP=0: one stream at a time, same arrays)
+    // level-synchronous kernel: two timestamp arrays alternate between the levels of the stream in flight; the LAST list
+    // round of a stream (it only reads one of them) runs beside round 0 of the next (GP_LEVEL_OVERLAP=0: one stream at
+    // a time, same arrays)
     ctx->level_slots = 2;
     if (const char* f = std::getenv("GP_LEVEL_OVERLAP")) ctx->level_slots = f[0] == '0' ? 1u : 2u;
-    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * gp::kLevelArrays));
+    ctx->level_arrays = 2; // (three arrays let every late round be joined, but 120 MiB of timestamps do not stay in L2: 1.5x slower)
+    if (const char* f = std::getenv("GP_LEVEL_ARRAYS")) ctx->level_arrays = f[0] == '3' ? 3u : 2u;
+    GP_CUDA(ctx, ctx->d_V.ensure(gp::kCbfCounters * 4 * ctx->level_arrays));
     // warp-private survivor lists, kLevelSurvWords words per entry (a warp's region is its share of the steps,
     // rounded up, x 32), one buffer per stream in flight; then the barrier counter
     ctx->surv_cap = uint32_t(size_t(ctx->alive_words) * 32 + size_t(8192) * 9 * 32); // + (runs + 1) slack slots per warp
@@ -639,8 +641,7 @@ static int build_launch_levels_wave(gp_ctx* ctx, cudaStream_t s, size_t wv, uint
     p.surv = ctx->d_alive.as<uint32_t>();
     p.bars = reinterpret_cast<unsigned long long*>(ctx->d_alive.as<uint32_t>() + size_t(gp::kLevelSurvWords) * gp::kLevelListBufs * ctx->surv_cap);
     p.overlap = ctx->level_slots > 1 ? 1u : 0u;
-    p.arrays = 2; // three arrays let every late round be joined, but 120 MiB of timestamps do not stay in L2: measured 1.5x slower
-    if (const char* f = std::getenv("GP_LEVEL_ARRAYS")) p.arrays = f[0] == '2' ? 2u : 3u;
+    p.arrays = ctx->level_arrays;
     p.time_bits = ctx->level_time_bits;
     if (const char* f = std::getenv("GP_LEVEL_REPORT_CTA")) p.report_cta = uint32_t(std::atoi(f));
     p.cbf_pool = c.keep_counters ? ctx->d_cbf_pool.as<uint8_t>() : nullptr;
@@ -655,7 +656,7 @@ static int build_launch_levels_wave(gp_ctx* ctx, cudaStream_t s, size_t wv, uint
     p.nk = c.nk;
     for (uint32_t i = 0; i < gp::kMaxK; i++) p.k[i] = i < c.nk ? c.k[i] : 0;
     if (c.keep_counters) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cbf_pool.p, 0, uint64_t(p.n_streams) * gp::kCbfCounters, s));
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * gp::kLevelArrays, s));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->d_V.p, 0xFF, gp::kCbfCounters * 4 * ctx->level_arrays, s));
     GP_CUDA(ctx, cudaMemsetAsync(p.bars, 0, 64 + 8192, s));
     p.speed = reinterpret_cast<uint32_t*>(p.bars + 8);
     {

@@ -55,6 +55,9 @@ struct WS {
   const unsigned char* code; // byte -> 0 none, 1 A, 2 C, 3 G, 4 T (either case)
   uint64_t* seedt;           // [0..4] F, [8..12] F rotated by k, [16..23] R (by c & 7), [24..31] R rotated by k
   uint64_t* stage;           // [0..31] outF, [32..63] outR, [64..127] inF, [128..191] inRk
+  uint64_t* com;             // per call: common chains of the insertion search, [0..159] forward (length L-1, roll kk), [160..319] reverse
+  const uint64_t* insF;      // per round: [(j * 3 + d - 1) * 32 + kk] = term of inserted base d (C, G, T) that entered at roll j,
+  const uint64_t* insR;      //            seen at roll kk (0 while kk < j), forward / reverse strand
   uint32_t hp, ve;
   bool exhausted;    // refilling hit the end of the stream
   // two blocks of 32 windows starting at absolute index B (lane j: windows B+j and B+32+j)
@@ -136,14 +139,28 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
   return v;
 }
 
+// A filter word.  The build kernel may be writing OTHER batches' filters into the same pool while this kernel runs, so
+// the non-coherent path (ld.global.nc / __ldg) is out: it is only defined for data that nobody writes during the
+// kernel's lifetime.  ld.global.cg reads L2, where the build kernel's `red.or` land.  (An ordinary L1-cached load after
+// the ld.acquire.gpu of the batch's flag would also be legal; measured, it changes nothing: 237 vs 233 ms for the
+// slowest contig of the config-3 data set, 47.8 vs 45 ms for config 2 -- the chain is instruction latency, not lookups.)
+__device__ __forceinline__ uint32_t ld_filter(const uint32_t* p)
+{
+#ifdef GP_EDIT_FILTER_LOAD_CA
+  return __ldca(p);
+#else
+  return __ldcg(p);
+#endif
+}
+
 __device__ __forceinline__ bool bf_contains(const WS& w, uint64_t fh, uint64_t rh)
 { // btllib KmerBloomFilter::contains with the four ntHash values (ntedit.cpp:1470)
   const uint64_t b = fh + rh;
   uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
   h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
   const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
-  const uint32_t w0 = __ldcg(w.bf + (n0 >> 5)), w1 = __ldcg(w.bf + (n1 >> 5));
-  const uint32_t w2 = __ldcg(w.bf + (n2 >> 5)), w3 = __ldcg(w.bf + (n3 >> 5));
+  const uint32_t w0 = ld_filter(w.bf + (n0 >> 5)), w1 = ld_filter(w.bf + (n1 >> 5));
+  const uint32_t w2 = ld_filter(w.bf + (n2 >> 5)), w3 = ld_filter(w.bf + (n3 >> 5));
   return ((w0 >> (n0 & 31u)) & (w1 >> (n1 & 31u)) & (w2 >> (n2 & 31u)) & (w3 >> (n3 & 31u)) & 1u) != 0u;
 }
 __device__ __forceinline__ bool bf_contains(const WS& w, const HashState& h) { return bf_contains(w, h.fh, h.rh); }
@@ -565,62 +582,87 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
     const uint32_t nsamp = (k - 2) / w.jump + 1;
     const uint32_t need = w.thrE > 0.0f ? (uint32_t)ceilf(w.thrE) : 0u;
     const uint32_t allowed = nsamp >= need ? nsamp - need : 0u;
-    // Four candidates per lane are rolled side by side: their hash chains are independent, and
-    // the 16 filter words of a sample are in flight together instead of one lookup at a time.
+    // No candidate is rolled.  ntHash is XOR-linear in the characters of the window, so the hashes of a candidate's
+    // windows are those of the "all-A" candidate of the same length (the COMMON chain: one lane per length rolls it
+    // once, k-1 steps) XOR one precomputed term per inserted base that is not an A (w.insF / w.insR: the seed
+    // difference rotated by the distance between the base's entry and the sampled roll).  A lane takes a GROUP of four
+    // candidates that differ in their last inserted base only: the common hash and the terms of the bases they share
+    // are fetched once per sample, and only sampled rolls are ever looked at.  The 16 filter words of a sample are in
+    // flight together and are consumed one sample later.
+    uint64_t* comF = w.com, *comR = w.com + 5 * 32;
+    if (w.lane < w.max_ins) {
+      HashState t = base;
+      const uint32_t L = w.lane + 1;
+      for (uint32_t kk = 0; kk + 1 < k; kk++) { // :1294-1326 with A for every inserted base after the first
+        uint64_t inf, inr;
+        if (kk + 1 < L) { inf = w.seedt[1]; inr = w.seedt[24 + 1]; }
+        else if (kk + 1 == L) { inf = dF; inr = dRk; }   // then the draft base (:1279)
+        else { inf = inF[kk - L]; inr = inRk[kk - L]; }
+        t.fh = srol1(t.fh) ^ inf ^ outF[kk];
+        t.rh = sror1(t.rh ^ inr ^ outR[kk]);
+        comF[w.lane * 32 + kk] = t.fh;
+        comR[w.lane * 32 + kk] = t.rh;
+      }
+    }
+    __syncwarp();
+    // groups, longest strings first: 64 of length 5 (three shared bases), 16 of length 4, 4 of length 3, one of
+    // length 2 (its four candidates share nothing but the first base) and the single string of length 1
+    const uint32_t n5 = w.max_ins >= 5 ? 64u : 0u, n4 = w.max_ins >= 4 ? 16u : 0u, n3 = w.max_ins >= 3 ? 4u : 0u,
+                   n2 = w.max_ins >= 2 ? 1u : 0u, n1 = w.max_ins >= 1 ? 1u : 0u;
+    const uint32_t n_groups = n5 + n4 + n3 + n2 + n1;
     constexpr int G = 4;
-    for (uint32_t c0 = 0; c0 * 32u < ntry; c0 += G) {
-      uint32_t Lq[G], rq[G], presq[G], missq[G], pbits[G];
-      uint32_t pw[G][4];
-      HashState tq[G];
+    for (uint32_t g0 = 0; g0 < n_groups; g0 += 32) {
+      const uint32_t g = g0 + w.lane;
+      uint32_t L = 0, pre = 0;
+      if (g < n5) { L = 5; pre = g; }
+      else if (g < n5 + n4) { L = 4; pre = g - n5; }
+      else if (g < n5 + n4 + n3) { L = 3; pre = g - n5 - n4; }
+      else if (g < n5 + n4 + n3 + n2) { L = 2; }
+      else if (g < n_groups) { L = 1; }
+      const uint32_t start = L == 1 ? 0u : L == 2 ? 1u : L == 3 ? 5u : L == 4 ? 21u : 85u; // index of the class's first string
+      uint32_t presq[G], missq[G], pbits[G], pw[G][4];
       bool act[G], pend[G];
 #pragma unroll
       for (int q = 0; q < G; q++) {
-        const uint32_t i = w.lane + 32u * (c0 + q);
-        act[q] = i < ntry;
-        Lq[q] = i < 1 ? 1 : i < 5 ? 2 : i < 21 ? 3 : i < 85 ? 4 : 5;
-        rq[q] = i - (Lq[q] == 1 ? 0 : Lq[q] == 2 ? 1 : Lq[q] == 3 ? 5 : Lq[q] == 4 ? 21 : 85); // base-4 digits of s[1..L-1]
-        tq[q] = base;
+        act[q] = L >= 2 || (L == 1 && q == 0);
         presq[q] = 0; missq[q] = 0; pbits[q] = 0; pend[q] = false;
         pw[q][0] = pw[q][1] = pw[q][2] = pw[q][3] = 0;
       }
-      for (uint32_t kk = 0; kk + 1 < k; kk++) { // :1294-1326
-        const uint64_t of = outF[kk], orv = outR[kk];
+      // table rows of the shared bases (string positions 1 .. L-2 enter at rolls 0 .. L-3); 0xffffffff: an A, no term
+      uint32_t row[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const uint32_t d = (L >= 3u + j) ? (pre >> (2u * (L - 3u - j))) & 3u : 0u;
+        row[j] = d ? (uint32_t(j) * 3u + d - 1u) * 32u : 0xffffffffu;
+      }
+      const uint32_t last_row = L >= 2 ? (L - 2u) * 3u * 32u : 0u; // rows of the last inserted base (enters at roll L-2)
+      const uint32_t com_row = L ? (L - 1u) * 32u : 0u;
+      for (uint32_t kk = 0; kk + 1 < k; kk += w.jump) { // the sampled rolls only (kk % jump == 0, :1294-1310)
+        uint64_t pf = comF[com_row + kk], pr = comR[com_row + kk];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          if (row[j] != 0xffffffffu) { pf ^= w.insF[row[j] + kk]; pr ^= w.insR[row[j] + kk]; }
 #pragma unroll
         for (int q = 0; q < G; q++) {
           if (!act[q]) continue;
-          uint64_t inf, inr;
-          const uint32_t L = Lq[q];
-          if (kk < L) {
-            if (kk + 1 < L) { // next base of the insertion string
-              const uint32_t d = (rq[q] >> (2 * (L - 2 - kk))) & 3u;
-              inf = w.seedt[d + 1];
-              inr = w.seedt[24 + ((0x4731u >> (4 * d)) & 7u)];
-            } else { inf = dF; inr = dRk; } // then the draft base (:1279)
-          } else { inf = inF[kk - L]; inr = inRk[kk - L]; }
-          tq[q].fh = srol1(tq[q].fh) ^ inf ^ of;
-          tq[q].rh = sror1(tq[q].rh ^ inr ^ orv);
-        }
-        if ((w.samp >> kk) & 1ull) { // kk % jump == 0, without a runtime modulo
-#pragma unroll
-          for (int q = 0; q < G; q++) {
-            if (!act[q]) continue;
-            if (pend[q]) {
-              const uint32_t pb = pbits[q];
-              if (((pw[q][0] >> (pb & 31u)) & (pw[q][1] >> ((pb >> 5) & 31u)) & (pw[q][2] >> ((pb >> 10) & 31u)) &
-                   (pw[q][3] >> ((pb >> 15) & 31u)) & 1u) != 0u) presq[q]++; else missq[q]++;
-              if (missq[q] > allowed) { act[q] = false; pend[q] = false; continue; } // cannot qualify any more
-            }
-            const uint64_t b = tq[q].fh + tq[q].rh;
-            uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
-            h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
-            const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
-            pw[q][0] = __ldcg(w.bf + (n0 >> 5)); pw[q][1] = __ldcg(w.bf + (n1 >> 5));
-            pw[q][2] = __ldcg(w.bf + (n2 >> 5)); pw[q][3] = __ldcg(w.bf + (n3 >> 5));
-            pbits[q] = (n0 & 31u) | ((n1 & 31u) << 5) | ((n2 & 31u) << 10) | ((n3 & 31u) << 15);
-            pend[q] = true;
+          if (pend[q]) {
+            const uint32_t pb = pbits[q];
+            if (((pw[q][0] >> (pb & 31u)) & (pw[q][1] >> ((pb >> 5) & 31u)) & (pw[q][2] >> ((pb >> 10) & 31u)) &
+                 (pw[q][3] >> ((pb >> 15) & 31u)) & 1u) != 0u) presq[q]++; else missq[q]++;
+            if (missq[q] > allowed) { act[q] = false; pend[q] = false; continue; } // cannot qualify any more
           }
-          if (!__any_sync(kFull, act[0] | act[1] | act[2] | act[3])) break;
+          uint64_t f = pf, r = pr;
+          if (q) { f ^= w.insF[last_row + uint32_t(q - 1) * 32u + kk]; r ^= w.insR[last_row + uint32_t(q - 1) * 32u + kk]; }
+          const uint64_t b = f + r;
+          uint64_t h1 = b * w.mul1, h2 = b * w.mul2, h3 = b * w.mul3;
+          h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
+          const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
+          pw[q][0] = ld_filter(w.bf + (n0 >> 5)); pw[q][1] = ld_filter(w.bf + (n1 >> 5));
+          pw[q][2] = ld_filter(w.bf + (n2 >> 5)); pw[q][3] = ld_filter(w.bf + (n3 >> 5));
+          pbits[q] = (n0 & 31u) | ((n1 & 31u) << 5) | ((n2 & 31u) << 10) | ((n3 & 31u) << 15);
+          pend[q] = true;
         }
+        if (!__any_sync(kFull, act[0] | act[1] | act[2] | act[3])) break;
       }
 #pragma unroll
       for (int q = 0; q < G; q++) {
@@ -629,8 +671,9 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
           if (((pw[q][0] >> (pb & 31u)) & (pw[q][1] >> ((pb >> 5) & 31u)) & (pw[q][2] >> ((pb >> 10) & 31u)) &
                (pw[q][3] >> ((pb >> 15) & 31u)) & 1u) != 0u) presq[q]++;
         }
-        const uint32_t i = w.lane + 32u * (c0 + q);
-        if (i < ntry && float(presq[q]) >= w.thrE && (w.mode == 0 || presq[q] > 0)) { // :1333-1337, :1400
+        const bool exists = L >= 2 || (L == 1 && q == 0);
+        const uint32_t i = start + pre * 4u + uint32_t(q); // position in multi_possible_bases[first] (:198-343)
+        if (exists && i < ntry && float(presq[q]) >= w.thrE && (w.mode == 0 || presq[q] > 0)) { // :1333-1337, :1400
           const uint32_t order = 2 * i;
           const uint32_t key = (presq[q] << 12) | (order + 1);
           best_key = max(best_key, key);
@@ -835,6 +878,20 @@ __device__ __forceinline__ void edit_round(WS& w)
     const uint64_t r = cseed_of_char(lane - 8);
     w.seedt[16 + lane - 8] = r;
     w.seedt[24 + lane - 8] = srol(r, k);
+  }
+  __syncwarp();
+  // insertion-search terms: an inserted base d (instead of A) that enters at roll j shows up in the hash after roll kk
+  // as its seed difference rotated by the rolls in between (forward: kk - j; reverse, on the k-rotated seed: kk - j + 1)
+  {
+    uint64_t* tF = const_cast<uint64_t*>(w.insF);
+    uint64_t* tR = const_cast<uint64_t*>(w.insR);
+    for (uint32_t e = lane; e < 4u * 3u * 32u; e += 32) {
+      const uint32_t kk = e & 31u, jd = e >> 5, j = jd / 3u, d = jd - 3u * j + 1u;
+      const uint64_t df = w.seedt[1 + d] ^ w.seedt[1];
+      const uint64_t dr = w.seedt[24 + ((0x4731u >> (4 * d)) & 7u)] ^ w.seedt[24 + 1];
+      tF[e] = kk >= j ? srol(df, kk - j) : 0ull;
+      tR[e] = kk >= j ? sror(dr, kk - j + 1u) : 0ull;
+    }
   }
   w.samp = 0;
   for (uint32_t kk = 0; kk < k; kk += w.jump) w.samp |= 1ull << kk;
@@ -1055,6 +1112,8 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
   __shared__ unsigned char code_sh[256];
   __shared__ uint64_t seedt_sh[kEditWarps][32];
   __shared__ uint64_t stage_sh[kEditWarps][192];
+  __shared__ uint64_t com_sh[kEditWarps][2 * 5 * 32];
+  __shared__ uint64_t ins_sh[kEditWarps][2][4 * 3 * 32];
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
     const uint32_t lc = i | 0x20u;
     code_sh[i] = lc == 'a' ? 1 : lc == 'c' ? 2 : lc == 'g' ? 3 : lc == 't' ? 4 : 0;
@@ -1110,6 +1169,9 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
     w.code = code_sh;
     w.seedt = seedt_sh[warp];
     w.stage = stage_sh[warp];
+    w.com = com_sh[warp];
+    w.insF = ins_sh[warp][0];
+    w.insR = ins_sh[warp][1];
     w.nd = p.nodes + p.node_off[ci];
     w.ncap = uint32_t(p.node_off[ci + 1] - p.node_off[ci]);
     w.max_ins = p.max_insertions; w.max_del = p.max_deletions; w.jump = p.jump;

@@ -30,7 +30,6 @@ struct BuildParams {
 };
 
 constexpr uint32_t kLevelSurvWords = 3; // words per survivor-list entry: h0 low, h0 high, time | thr << 26
-constexpr uint32_t kLevelArrays = 3;    // timestamp arrays: two for the levels >= 2 (alternating), one for T_1
 constexpr uint32_t kLevelListBufs = 2;  // list buffers: consecutive streams alternate
 
 struct LevelParams {              // level-synchronous filter build (gp_build_levels.cu)
@@ -47,7 +46,7 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   uint32_t n_batches_total;
   const uint16_t* anchor;         // [nk][anchor_stride]: global step of k index -> entry, relative to its batch
   uint64_t anchor_stride;
-  uint32_t* V;                    // kLevelArrays x kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
+  uint32_t* V;                    // `arrays` x kCbfCounters tagged timestamps (cleared to 0xFFFFFFFF before a launch)
   uint32_t* surv;                 // kLevelListBufs x kLevelSurvWords arrays of surv_cap words, warp-private regions
   unsigned long long* bars;       // barrier arrival counter (zeroed before a launch)
   uint32_t* speed;                // per CTA: published round-0 rate (weighted shares)

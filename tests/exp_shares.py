@@ -28,7 +28,10 @@ if mode == "levels":  # weight a batch's read bases by the list rounds its strea
     maxthr = np.array([pl.entries["kmer_threshold"][off[b]:off[b + 1]].max() if off[b + 1] > off[b] else 4 for b in range(len(off) - 1)])
     work = work * (2 + maxthr)
 assignment = shard.assign_batches(work.tolist(), world)
+only = os.environ.get("ONLY_SHARE")
 for r, mine in enumerate(assignment):
+    if only is not None and r != int(only):
+        continue
     sh = bench.LocalShare(d, pl, mine, w["bsize"])
     with gp.Context() as ctx:
         ctx.upload_reads(sh.read_seq, sh.read_off)

@@ -10,6 +10,7 @@ import os
 import subprocess
 import tempfile
 import threading
+import time
 
 import pytest
 
@@ -47,9 +48,12 @@ def test_fixture_through_the_dropin_tools(which):
         with rd.BfServer(bdir, p["draft"], p["draft"] + ".index", p["paf"], p["reads"], p["reads"] + ".index", threads=4,
                          binary=os.path.join(BIN, "goldpolish-targeted-bfs"), env=ENV) as srv:
             # (a) a handful of batches the way an unmodified driver does it: .bf files, then goldpolish-ntedit on them
+            latencies = []
             for b in list(range(min(4, len(draft)))) + [len(draft) - 1]:
                 name, seq = draft[b]
+                t0 = time.perf_counter()
                 paths = srv.build(f"t{b}", [name])
+                latencies.append(time.perf_counter() - t0)
                 assert [sha(_payload(paths[k])) for k in KS] == g["batches"][b]["bf_sha256"], (which, b)
                 bd = os.path.join(w, f"t{b}")
                 os.makedirs(bd)
@@ -59,6 +63,11 @@ def test_fixture_through_the_dropin_tools(which):
                                        "32 28 24 20", "0.5", "0.5", "1", "batch.ntedited.fa"], cwd=bd, env=ENV,
                                       stdout=subprocess.DEVNULL)
                 assert sha(open(os.path.join(bd, "batch.ntedited.fa"), "rb").read()) == g["batches"][b]["polished_sha256"], (which, b)
+            # one batch at a time, as an unmodified driver with one client would feed the server: name -> ack -> ids ->
+            # four .bf files on disk -> ack.  (Stage + build + payload copy are well under a millisecond of GPU work; the
+            # protocol's pipe round trips and 2 MiB of file writes are the rest.)
+            print(f"{which}: per-batch server latency (ms): " + " ".join(f"{1e3 * x:.1f}" for x in latencies))
+            assert sorted(latencies)[len(latencies) // 2] < 0.5
             # (b) EVERY batch through the fused route (goldpolish-polish-batch's "@polish" request): all clients at once
             names = [f"f{b}" for b in range(len(draft))]
             for b, name in enumerate(names):
