@@ -61,9 +61,7 @@ class ReferenceSample:
     def run(self) -> dict:
         if self.kind == "port":
             return self._run_port()
-        import ctypes as C
         d, nb, bs, threads = self.d, self.nb, self.w["bsize"], self.threads
-        h = self.rd.harness()
         shutil.rmtree(self.bdir, ignore_errors=True)
         os.makedirs(self.bdir)
         names, ids_files = [], []
@@ -74,7 +72,6 @@ class ReferenceSample:
                 for c in range(b * bs, min((b + 1) * bs, d.n_contigs)):
                     f.write(d.contig_name(c) + "\n")
             ids_files.append(p.encode())
-        ks = (C.c_uint * 4)(*KS)
         # the filter build runs in a process of its own (oracle/ref_worker.py says why); the time is the one the
         # reference-side loop reports for itself, process start-up excluded
         job = dict(cwd=self.bdir, draft=self.draft, draft_index=self.draft + ".index", maps=self.maps, reads=self.reads,
@@ -88,12 +85,17 @@ class ReferenceSample:
         if p.returncode != 0:
             raise RuntimeError("reference serve_batches failed: " + p.stderr[-2000:])
         t_build = float(p.stdout.strip().splitlines()[-1])
-        bases_arr = (C.c_char_p * nb)(*[os.path.join(self.work, f"batch{b}", "batch").encode() for b in range(nb)])
-        bfs_flat = (C.c_char_p * (nb * 4))(*[os.path.join(self.bdir, f"{b}-k{k}.bf").encode() for b in range(nb) for k in KS])
-        outs = (C.c_char_p * nb)(*[os.path.join(self.work, f"batch{b}", "batch.ntedited.fa").encode() for b in range(nb)])
-        t_edit = h.ref_ntedit_chain_many(bases_arr, bfs_flat, ks, 4, outs, nb, threads)
-        if t_edit < 0:
-            raise RuntimeError("reference ntedit chain failed")
+        job = dict(kind="chain", ks=KS, threads=threads,
+                   bases=[os.path.join(self.work, f"batch{b}", "batch") for b in range(nb)],
+                   bfs_flat=[os.path.join(self.bdir, f"{b}-k{k}.bf") for b in range(nb) for k in KS],
+                   outs=[os.path.join(self.work, f"batch{b}", "batch.ntedited.fa") for b in range(nb)])
+        with open(job_path, "w") as f:
+            json.dump(job, f)
+        p = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_worker.py"), job_path],
+                           capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("reference ntedit chain failed: " + p.stderr[-2000:])
+        t_edit = float(p.stdout.strip().splitlines()[-1])
         return dict(seconds_build=t_build, seconds_edit=t_edit, bases=self.bases, kind="reference", cores=threads, batches=nb)
 
     # ---- what the reference produced in the last run(), for the parity check ----

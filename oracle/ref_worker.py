@@ -6,7 +6,8 @@ A fresh process per call is the reference's own model: SeqIndex::get_seq keeps i
 already served batches from one reads file keeps reading THAT file for every later index.
 
 usage: python ref_worker.py <job.json>   (keys: cwd, draft, draft_index, maps, reads, reads_index, mx_max,
-                                          subsample_max, threads, ks, names, ids_files)
+                                          subsample_max, threads, ks, names, ids_files; or kind = "chain", bases,
+                                          bfs_flat, outs, ks, threads for the ntEdit chain of the same batches)
 """
 import ctypes as C
 import json
@@ -21,8 +22,17 @@ def main():
     job = json.load(open(sys.argv[1]))
     os.environ["GP_ORACLE_QUIET"] = "1"
     h = rd.harness()
-    nb = len(job["names"])
     ks = (C.c_uint * len(job["ks"]))(*job["ks"])
+    if job.get("kind") == "chain":
+        # the ntEdit chain + guard of every batch on `threads` forked single-thread workers (ref_ntedit_chain_many).  Also
+        # in a process of its own: the caller may hold gigabytes of page-locked memory, which fork() copies eagerly.
+        nb = len(job["bases"])
+        t = h.ref_ntedit_chain_many((C.c_char_p * nb)(*[x.encode() for x in job["bases"]]),
+                                    (C.c_char_p * (nb * len(job["ks"])))(*[x.encode() for x in job["bfs_flat"]]), ks, len(job["ks"]),
+                                    (C.c_char_p * nb)(*[x.encode() for x in job["outs"]]), nb, int(job["threads"]))
+        print(repr(float(t)))
+        return 0 if t >= 0 else 1
+    nb = len(job["names"])
     os.chdir(job["cwd"])
     t = h.ref_serve_batches(job["draft"].encode(), job["draft_index"].encode(), job["maps"].encode(), job["reads"].encode(),
                             job["reads_index"].encode(), float(job["mx_max"]), float(job["subsample_max"]), int(job["threads"]),
