@@ -397,56 +397,14 @@ def ours(args, rank, world, local_rank):
 
     # ---- host gather in batch order (scripts/goldpolish-reaper:51-73): rank 0 receives every rank's polished
     # records over NCCL (device staging buffers), and lays them out in contig order ----
-    gather_state = {}
-    if dist is not None and strong:
-        all_contigs = [np.concatenate([np.arange(b * w["bsize"], min((b + 1) * w["bsize"], d.n_contigs)) for b in bl])
-                       if len(bl) else np.zeros(0, np.int64) for bl in assignment]
-        max_bytes = max(int(clens[c].sum()) + int(clens[c].sum()) // 4 + 65536 for c in all_contigs)
-        max_contigs = max(len(c) for c in all_contigs)
-        gather_state.update(all_contigs=all_contigs, max_bytes=max_bytes, max_contigs=max_contigs,
-                            dev=torch.empty(max_bytes, dtype=torch.uint8, device="cuda"),
-                            lens=torch.zeros(max_contigs, dtype=torch.int64, device="cuda"))
-        if rank == 0:
-            gather_state["recv"] = [torch.empty(max_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
-            gather_state["recv_lens"] = [torch.zeros(max_contigs, dtype=torch.int64, device="cuda") for _ in range(world)]
-            gather_state["host"] = torch.empty((world, max_bytes), dtype=torch.uint8).pin_memory()
+    gatherer = shard.RecordGather(clens, w["bsize"], assignment, rank, dist, device="cuda") if dist is not None and strong else None
 
     def gather(out, off, dropped):
         """-> (sequence bytes in contig order, per-contig lengths with 0 for dropped records) on rank 0, None elsewhere"""
-        lens_local = np.where(dropped == 0, np.diff(off.astype(np.int64)), 0).astype(np.int64)
-        nbytes = int(off[-1])
-        if dist is None or not strong:
-            return np.asarray(out[:nbytes]), lens_local
-        g = gather_state
-        src = out if isinstance(out, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(out))
-        g["dev"][:nbytes].copy_(src[:nbytes], non_blocking=True)
-        g["lens"].zero_()
-        g["lens"][:len(lens_local)].copy_(torch.from_numpy(lens_local), non_blocking=True)
-        dist.gather(g["dev"], g.get("recv"), dst=0)
-        dist.gather(g["lens"], g.get("recv_lens"), dst=0)
-        if rank != 0:
-            return None
-        lens_all = np.zeros(d.n_contigs, dtype=np.int64)
-        rl = [t.cpu().numpy() for t in g["recv_lens"]]
-        for r in range(world):
-            lens_all[g["all_contigs"][r]] = rl[r][:len(g["all_contigs"][r])]
-            used = int(rl[r].sum())
-            g["host"][r, :used].copy_(g["recv"][r][:used], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        goff = np.concatenate([[0], np.cumsum(lens_all)])
-        final = np.empty(int(goff[-1]), dtype=np.uint8)
-        hostnp = g["host"].numpy()
-        for r in range(world):
-            cs = g["all_contigs"][r]
-            loff = np.concatenate([[0], np.cumsum(lens_all[cs])])
-            # consecutive contigs of one batch are consecutive on both sides: copy batch by batch
-            bs = w["bsize"]
-            i = 0
-            while i < len(cs):
-                j = min(i + bs - int(cs[i]) % bs, len(cs))
-                final[goff[cs[i]]:goff[cs[j - 1] + 1]] = hostnp[r, loff[i]:loff[j]]
-                i = j
-        return final, lens_all
+        if gatherer is None:
+            lens_local = np.where(dropped == 0, np.diff(off.astype(np.int64)), 0).astype(np.int64)
+            return np.asarray(out[:int(off[-1])]), lens_local
+        return gatherer(out, off, dropped)
 
     e2e_info = {}
 
