@@ -549,6 +549,8 @@ struct Best {
   uint32_t del_len;
 };
 
+constexpr uint32_t kInsZeroRow = 4u * 3u * 32u; // w.insF / w.insR: twelve rows of terms, then a row of zeros
+
 // tryIndels + tryDeletion, :1157-1411.  Lanes share the candidates; the reference's visiting
 // order (ins_0, del_0, ins_1, del_1, ..., ins_340) breaks support ties, later wins (:1347,:1384).
 __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t index_char, uint32_t& num_deletions, Best& best)
@@ -558,6 +560,7 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
   const uint32_t an = ahead_count(w);
   uint32_t best_key = 0; // (support << 12) | order+1 for modes 1/2; mode 0 keeps the smallest order
   uint32_t first_key = 0xffffffffu;
+  uint32_t ndel = 0;     // deletions num_deletions .. max_del, one per visited insertion index (:1359-1396)
   // Stage what every candidate shares: the outgoing bases E[h..t-1] (their k-rotated forward
   // seed and plain reverse seed) and the incoming bases ahead of t (plain forward, k-rotated
   // reverse), so that one roll is four shared-memory loads and a handful of logic ops.
@@ -589,19 +592,65 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
     // candidates that differ in their last inserted base only: the common hash and the terms of the bases they share
     // are fetched once per sample, and only sampled rolls are ever looked at.  The 16 filter words of a sample are in
     // flight together and are consumed one sample later.
+    //
+    // The deletion candidates (:1359-1396, tryDeletion :1157-1234) ARE rolled -- there are at most ten of them -- in the
+    // same loop as the common chains, on lanes of their own (8 + i), their filter words pending across the rolls.
     uint64_t* comF = w.com, *comR = w.com + 5 * 32;
-    if (w.lane < w.max_ins) {
-      HashState t = base;
-      const uint32_t L = w.lane + 1;
-      for (uint32_t kk = 0; kk + 1 < k; kk++) { // :1294-1326 with A for every inserted base after the first
-        uint64_t inf, inr;
-        if (kk + 1 < L) { inf = w.seedt[1]; inr = w.seedt[24 + 1]; }
-        else if (kk + 1 == L) { inf = dF; inr = dRk; }   // then the draft base (:1279)
-        else { inf = inF[kk - L]; inr = inRk[kk - L]; }
-        t.fh = srol1(t.fh) ^ inf ^ outF[kk];
-        t.rh = sror1(t.rh ^ inr ^ outR[kk]);
-        comF[w.lane * 32 + kk] = t.fh;
-        comR[w.lane * 32 + kk] = t.rh;
+    if (num_deletions <= w.max_del) ndel = min(ntry, w.max_del - num_deletions + 1);
+    {
+      const bool role_c = w.lane < w.max_ins;
+      const bool role_d = w.lane >= 8u && w.lane < 8u + ndel;
+      const uint32_t L = w.lane + 1;                       // role C
+      const uint32_t nd = num_deletions + (w.lane - 8u);   // role D: bases deleted
+      HashState t = role_d ? w.hs : base;
+      bool d_act = false, d_pend = false;
+      uint32_t d_present = 0, d_pb = 0, d_pw[4] = { 0, 0, 0, 0 };
+      auto d_issue = [&]() {
+        const uint64_t bb = t.fh + t.rh;
+        uint64_t h1 = bb * w.mul1, h2 = bb * w.mul2, h3 = bb * w.mul3;
+        h1 ^= h1 >> kMultiShift; h2 ^= h2 >> kMultiShift; h3 ^= h3 >> kMultiShift;
+        const uint32_t n0 = bf_index(bb), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
+        d_pw[0] = ld_filter(w.bf + (n0 >> 5)); d_pw[1] = ld_filter(w.bf + (n1 >> 5));
+        d_pw[2] = ld_filter(w.bf + (n2 >> 5)); d_pw[3] = ld_filter(w.bf + (n3 >> 5));
+        d_pb = (n0 & 31u) | ((n1 & 31u) << 8) | ((n2 & 31u) << 16) | ((n3 & 31u) << 24);
+        d_pend = true;
+      };
+      auto d_consume = [&]() {
+        if (d_pend && ((d_pw[0] >> (d_pb & 31u)) & (d_pw[1] >> ((d_pb >> 8) & 31u)) & (d_pw[2] >> ((d_pb >> 16) & 31u)) &
+                       (d_pw[3] >> (d_pb >> 24)) & 1u) != 0u) d_present++;
+        d_pend = false;
+      };
+      if (role_d && nd - 1 < an) { // the character that follows the deleted run must exist
+        ws_changelast(w, t, draft_char, ahead_at(w, nd - 1)); // :1190-1197
+        d_act = true;
+        d_issue();                                             // the first k-mer always counts (:1201-1203)
+      }
+      for (uint32_t kk = 0; kk + 1 < k; kk++) {
+        if (role_c) { // :1294-1326 with A for every inserted base after the first
+          uint64_t inf, inr;
+          if (kk + 1 < L) { inf = w.seedt[1]; inr = w.seedt[24 + 1]; }
+          else if (kk + 1 == L) { inf = dF; inr = dRk; }   // then the draft base (:1279)
+          else { inf = inF[kk - L]; inr = inRk[kk - L]; }
+          t.fh = srol1(t.fh) ^ inf ^ outF[kk];
+          t.rh = sror1(t.rh ^ inr ^ outR[kk]);
+          comF[w.lane * 32 + kk] = t.fh;
+          comR[w.lane * 32 + kk] = t.rh;
+        } else if (d_act && kk + 2 < k) { // roll kk + 1 of :1204-1220
+          const uint32_t ai = nd + kk;
+          if (ai >= an) d_act = false; // roll() fails: end of contig
+          else {
+            t.fh = srol1(t.fh) ^ inF[ai] ^ outF[kk];
+            t.rh = sror1(t.rh ^ inRk[ai] ^ outR[kk]);
+            if ((w.samp >> (kk + 1)) & 1ull) { d_consume(); d_issue(); }
+          }
+        }
+      }
+      d_consume();
+      if (role_d && float(d_present) >= w.thrD && d_present > 0) { // :1226-1233 (returns 0 when rejected)
+        const uint32_t order = 2 * (w.lane - 8u) + 1;
+        const uint32_t key = (d_present << 12) | (order + 1);
+        best_key = max(best_key, key);
+        first_key = min(first_key, order);
       }
     }
     __syncwarp();
@@ -620,37 +669,28 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
       else if (g < n5 + n4 + n3 + n2) { L = 2; }
       else if (g < n_groups) { L = 1; }
       const uint32_t start = L == 1 ? 0u : L == 2 ? 1u : L == 3 ? 5u : L == 4 ? 21u : 85u; // index of the class's first string
-      uint32_t presq[G], missq[G], pbits[G], pw[G][4];
-      bool act[G], pend[G];
-#pragma unroll
-      for (int q = 0; q < G; q++) {
-        act[q] = L >= 2 || (L == 1 && q == 0);
-        presq[q] = 0; missq[q] = 0; pbits[q] = 0; pend[q] = false;
-        pw[q][0] = pw[q][1] = pw[q][2] = pw[q][3] = 0;
-      }
-      // table rows of the shared bases (string positions 1 .. L-2 enter at rolls 0 .. L-3); 0xffffffff: an A, no term
+      // table rows of the shared bases (string positions 1 .. L-2 enter at rolls 0 .. L-3); an A has no term: row of zeros
       uint32_t row[3];
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         const uint32_t d = (L >= 3u + j) ? (pre >> (2u * (L - 3u - j))) & 3u : 0u;
-        row[j] = d ? (uint32_t(j) * 3u + d - 1u) * 32u : 0xffffffffu;
+        row[j] = d ? (uint32_t(j) * 3u + d - 1u) * 32u : kInsZeroRow;
       }
       const uint32_t last_row = L >= 2 ? (L - 2u) * 3u * 32u : 0u; // rows of the last inserted base (enters at roll L-2)
       const uint32_t com_row = L ? (L - 1u) * 32u : 0u;
-      for (uint32_t kk = 0; kk + 1 < k; kk += w.jump) { // the sampled rolls only (kk % jump == 0, :1294-1310)
+      // Two samples are in flight (buffers A and B): the words of sample s+1 are requested before those of sample s are
+      // looked at, so that the L2 latency hides behind the hashing of the next sample.  Nothing below branches on a
+      // candidate -- a candidate that can no longer qualify keeps being hashed (its words are valid addresses) and
+      // only the warp-wide vote ends the loop -- so that the four candidates' chains interleave.
+      uint32_t presq[G], missq[G], pbA[G], pwA[G][4], pbB[G], pwB[G][4];
+#pragma unroll
+      for (int q = 0; q < G; q++) { presq[q] = 0; missq[q] = 0; }
+      auto issue = [&](uint32_t kk, uint32_t (&pw)[G][4], uint32_t (&pb)[G]) {
         uint64_t pf = comF[com_row + kk], pr = comR[com_row + kk];
 #pragma unroll
-        for (int j = 0; j < 3; j++)
-          if (row[j] != 0xffffffffu) { pf ^= w.insF[row[j] + kk]; pr ^= w.insR[row[j] + kk]; }
+        for (int j = 0; j < 3; j++) { pf ^= w.insF[row[j] + kk]; pr ^= w.insR[row[j] + kk]; }
 #pragma unroll
         for (int q = 0; q < G; q++) {
-          if (!act[q]) continue;
-          if (pend[q]) {
-            const uint32_t pb = pbits[q];
-            if (((pw[q][0] >> (pb & 31u)) & (pw[q][1] >> ((pb >> 5) & 31u)) & (pw[q][2] >> ((pb >> 10) & 31u)) &
-                 (pw[q][3] >> ((pb >> 15) & 31u)) & 1u) != 0u) presq[q]++; else missq[q]++;
-            if (missq[q] > allowed) { act[q] = false; pend[q] = false; continue; } // cannot qualify any more
-          }
           uint64_t f = pf, r = pr;
           if (q) { f ^= w.insF[last_row + uint32_t(q - 1) * 32u + kk]; r ^= w.insR[last_row + uint32_t(q - 1) * 32u + kk]; }
           const uint64_t b = f + r;
@@ -659,51 +699,53 @@ __device__ __forceinline__ bool try_indels(WS& w, uint32_t draft_char, uint32_t 
           const uint32_t n0 = bf_index(b), n1 = bf_index(h1), n2 = bf_index(h2), n3 = bf_index(h3);
           pw[q][0] = ld_filter(w.bf + (n0 >> 5)); pw[q][1] = ld_filter(w.bf + (n1 >> 5));
           pw[q][2] = ld_filter(w.bf + (n2 >> 5)); pw[q][3] = ld_filter(w.bf + (n3 >> 5));
-          pbits[q] = (n0 & 31u) | ((n1 & 31u) << 5) | ((n2 & 31u) << 10) | ((n3 & 31u) << 15);
-          pend[q] = true;
+          pb[q] = (n0 & 31u) | ((n1 & 31u) << 8) | ((n2 & 31u) << 16) | ((n3 & 31u) << 24);
         }
-        if (!__any_sync(kFull, act[0] | act[1] | act[2] | act[3])) break;
+      };
+      auto consume = [&](const uint32_t (&pw)[G][4], const uint32_t (&pb)[G]) {
+#pragma unroll
+        for (int q = 0; q < G; q++) {
+          const uint32_t hit = (pw[q][0] >> (pb[q] & 31u)) & (pw[q][1] >> ((pb[q] >> 8) & 31u)) &
+                               (pw[q][2] >> ((pb[q] >> 16) & 31u)) & (pw[q][3] >> (pb[q] >> 24)) & 1u;
+          presq[q] += hit;
+          missq[q] += hit ^ 1u;
+        }
+      };
+      // a candidate that has missed more samples than the threshold allows cannot qualify (its support stays below
+      // ceil(thrE) whatever the remaining samples say): once no lane holds a live one the group is settled
+      auto live = [&]() {
+        bool a = false;
+#pragma unroll
+        for (int q = 0; q < G; q++) a |= (L >= 2 || (L == 1 && q == 0)) && missq[q] <= allowed;
+        return __any_sync(kFull, a);
+      };
+      // the sampled rolls only (kk % jump == 0, :1294-1310): kk = 0, jump, 2 jump .. < k - 1
+      uint32_t kk = 0;
+      issue(kk, pwA, pbA);
+      kk += w.jump;
+      for (;;) {
+        const bool moreB = kk + 1 < k;
+        if (moreB) issue(kk, pwB, pbB);
+        kk += w.jump;
+        consume(pwA, pbA);
+        if (!moreB || !live()) break;
+        const bool moreA = kk + 1 < k;
+        if (moreA) issue(kk, pwA, pbA);
+        kk += w.jump;
+        consume(pwB, pbB);
+        if (!moreA || !live()) break;
       }
 #pragma unroll
       for (int q = 0; q < G; q++) {
-        if (pend[q]) {
-          const uint32_t pb = pbits[q];
-          if (((pw[q][0] >> (pb & 31u)) & (pw[q][1] >> ((pb >> 5) & 31u)) & (pw[q][2] >> ((pb >> 10) & 31u)) &
-               (pw[q][3] >> ((pb >> 15) & 31u)) & 1u) != 0u) presq[q]++;
-        }
         const bool exists = L >= 2 || (L == 1 && q == 0);
         const uint32_t i = start + pre * 4u + uint32_t(q); // position in multi_possible_bases[first] (:198-343)
-        if (exists && i < ntry && float(presq[q]) >= w.thrE && (w.mode == 0 || presq[q] > 0)) { // :1333-1337, :1400
+        if (exists && missq[q] <= allowed && i < ntry && float(presq[q]) >= w.thrE && (w.mode == 0 || presq[q] > 0)) { // :1333-1337, :1400
           const uint32_t order = 2 * i;
           const uint32_t key = (presq[q] << 12) | (order + 1);
           best_key = max(best_key, key);
           first_key = min(first_key, order);
         }
       }
-    }
-  }
-  // deletions num_deletions .. max_del, one per visited insertion index (:1359-1396)
-  uint32_t ndel = 0;
-  if (num_deletions <= w.max_del) ndel = min(ntry, w.max_del - num_deletions + 1);
-  if (w.lane < ndel) {
-    const uint32_t nd = num_deletions + w.lane;
-    HashState t = w.hs;
-    uint32_t present = 0;
-    if (nd - 1 < an) { // the character that follows the deleted run must exist
-      ws_changelast(w, t, draft_char, ahead_at(w, nd - 1)); // :1190-1197
-      if (bf_contains(w, t)) present++;                     // :1201-1203
-      for (uint32_t kk = 1; kk + 2 <= k; kk++) {            // :1204-1220
-        const uint32_t ai = nd - 1 + kk;
-        if (ai >= an) break; // roll() fails: end of contig
-        ws_roll(w, t, ring_at(w, kk - 1), ahead_at(w, ai));
-        if (((w.samp >> kk) & 1ull) && bf_contains(w, t)) present++;
-      }
-    }
-    if (float(present) >= w.thrD && present > 0) { // :1226-1233 (returns 0 when rejected)
-      const uint32_t order = 2 * w.lane + 1;
-      const uint32_t key = (present << 12) | (order + 1);
-      best_key = max(best_key, key);
-      first_key = min(first_key, order);
     }
   }
   num_deletions += ndel;
@@ -892,6 +934,8 @@ __device__ __forceinline__ void edit_round(WS& w)
       tF[e] = kk >= j ? srol(df, kk - j) : 0ull;
       tR[e] = kk >= j ? sror(dr, kk - j + 1u) : 0ull;
     }
+    tF[kInsZeroRow + lane] = 0ull; // the row an inserted A points at
+    tR[kInsZeroRow + lane] = 0ull;
   }
   w.samp = 0;
   for (uint32_t kk = 0; kk < k; kk += w.jump) w.samp |= 1ull << kk;
@@ -1113,7 +1157,7 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
   __shared__ uint64_t seedt_sh[kEditWarps][32];
   __shared__ uint64_t stage_sh[kEditWarps][192];
   __shared__ uint64_t com_sh[kEditWarps][2 * 5 * 32];
-  __shared__ uint64_t ins_sh[kEditWarps][2][4 * 3 * 32];
+  __shared__ uint64_t ins_sh[kEditWarps][2][kInsZeroRow + 32];
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
     const uint32_t lc = i | 0x20u;
     code_sh[i] = lc == 'a' ? 1 : lc == 'c' ? 2 : lc == 'g' ? 3 : lc == 't' ? 4 : 0;
