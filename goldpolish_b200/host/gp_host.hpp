@@ -23,6 +23,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <unordered_set>
 #include <thread>
@@ -261,10 +262,24 @@ private:
 // ---------------------------------------------------------------------------------------
 // Mappings: target id -> mapped read ids, first-seen order, de-duplicated
 // ---------------------------------------------------------------------------------------
+// Same result as AllMappings (src/mappings.cpp:15-330), loaded by all host cores instead of one
+// stream-parsing thread:
+//   1. the file is mapped and cut at line ends into one slice per thread; every thread tokenises its slice into
+//      (read, target, minimizers) records that point into the map (no copies);
+//   2. the reference's carry-over -- a line with too few columns keeps the ids of the line before it (:146-160,
+//      :199-213), ntLink tokens are triples whatever the line structure (:83-108) -- is resolved by one short sequential
+//      pass over the slices that need it (none, in a well-formed file);
+//   3. targets are dealt to the threads by hash; every thread walks ALL records in file order and keeps those of its
+//      own targets, so "first seen" is the file's order and no map is shared; it then applies the minimizer filter
+//      (:230-320) to its targets and turns the survivors into strings.
+// threads = 0: GP_HOST_THREADS or all cores.
 class Mappings {
 public:
+  using Map = std::unordered_map<std::string, std::vector<std::string>>;
+
   // src/mappings.cpp:15-35: type by file suffix; the minimizer filter only for ntLink triples
-  Mappings(const std::string& path, const SeqIndex& targets, unsigned mx_min, unsigned mx_max, double mx_max_per_10kbp)
+  Mappings(const std::string& path, const SeqIndex& targets, unsigned mx_min, unsigned mx_max, double mx_max_per_10kbp,
+           unsigned threads = 0)
   {
     // The reference reads mappings through btllib::DataSource, which pipes .bam through samtools and compressed
     // files through their decompressors (src/mappings.cpp:136-139); this reader takes plain text only, so those
@@ -272,78 +287,66 @@ public:
     for (const char* suf : { ".bam", ".gz", ".bz2", ".xz", ".zst", ".zip", ".lrz" })
       if (endswith(path, suf)) die("mappings file " + path + ": binary/compressed mappings are not supported here; "
                                    "convert first (e.g. `samtools view -h` / `zcat`) and pass the text file");
-    if (endswith(path, ".sam")) load_lines(path, targets, 3);
-    else if (endswith(path, ".paf")) load_lines(path, targets, 6);
-    else {
-      load_ntlink(path, targets, mx_min);
-      filter(mx_max_per_10kbp, mx_min, mx_max, targets);
+    const int target_col = endswith(path, ".sam") ? 3 : endswith(path, ".paf") ? 6 : 0; // 0: ntLink triples
+    if (target_col == 0) {
+      if (mx_max_per_10kbp <= 0) die("max_mapped_seqs_per_target_10kbp is not positive.");
+      if (mx_min >= mx_max) die("mx_threshold_min is not smaller than mx_threshold_max.");
     }
-    seen.clear();
-    mx.clear();
+    if (threads == 0) {
+      if (const char* e = std::getenv("GP_HOST_THREADS")) threads = unsigned(std::max(0, std::atoi(e)));
+      if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    }
+    load(path, targets, target_col, mx_min, mx_max, mx_max_per_10kbp, threads);
   }
 
   const std::vector<std::string>& get(const std::string& target) const
   {
     static const std::vector<std::string> empty;
-    const auto it = maps.find(target);
-    return it == maps.end() ? empty : it->second;
+    const Map& m = shards[std::hash<std::string>{}(target) % shards.size()];
+    const auto it = m.find(target);
+    return it == m.end() ? empty : it->second;
   }
-  const std::unordered_map<std::string, std::vector<std::string>>& all() const { return maps; }
+  // every (target, reads) pair, in no particular order
+  template <class Fn> void for_each(Fn&& fn) const
+  {
+    for (const Map& m : shards)
+      for (const auto& kv : m) fn(kv.first, kv.second);
+  }
+  size_t n_targets() const
+  {
+    size_t n = 0;
+    for (const Map& m : shards) n += m.size();
+    return n;
+  }
 
 private:
-  void add(const std::string& read, const std::string& target, const SeqIndex& targets, unsigned m)
-  { // load_mapping, src/mappings.cpp:37-72
-    if (!targets.exists(target)) return;
-    auto& s = seen[target];
-    if (s.find(read) != s.end()) return;
-    s.insert(read);
-    maps[target].push_back(read);
-    mx[target].push_back(m);
-  }
-
-  void load_ntlink(const std::string& path, const SeqIndex& targets, unsigned mx_min)
-  { // :74-110
-    std::ifstream f(path);
-    if (!f.good()) die("cannot open " + path);
-    std::string tok, read, target;
-    unsigned long i = 0;
-    while (bool(f >> tok)) {
-      switch (i % 3) {
-      case 0: read = tok; break;
-      case 1: target = tok; break;
-      default: {
-        const unsigned long m = std::stoul(tok);
-        if (m >= mx_min) add(read, target, targets, unsigned(m));
-      }
-      }
-      i++;
+  using sv = std::string_view;
+  struct Rec {
+    sv read, target;
+    unsigned long mx = 0;
+    bool has_read = false, has_target = false;
+  };
+  struct Slice {
+    std::vector<Rec> recs;     // line formats; ntLink when the slice holds whole triples
+    std::vector<sv> toks;      // ntLink
+    bool incomplete = false;   // some record lacks an id of its own
+  };
+  static bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); } // std::isspace, "C" locale
+  static unsigned long parse_mx(sv t)
+  { // std::stoul (:95); digits-only tokens take the short way
+    unsigned long v = 0;
+    bool plain = !t.empty() && t.size() < 19;
+    for (const char c : t) {
+      if (c < '0' || c > '9') { plain = false; break; }
+      v = v * 10 + unsigned(c - '0');
+    }
+    if (plain) return v;
+    try {
+      return std::stoul(std::string(t));
+    } catch (const std::exception&) {
+      die("mappings: '" + std::string(t) + "' is not a minimizer count"); // (the reference dies of the uncaught exception)
     }
   }
-
-  // SAM (target column 3) / PAF (target column 6): query column 1; '@' lines skipped; a short
-  // line keeps the ids of the previous one, as the reference's loop does (:112-215)
-  void load_lines(const std::string& path, const SeqIndex& targets, int target_col)
-  {
-    FILE* f = std::fopen(path.c_str(), "r");
-    if (!f) die("cannot open " + path);
-    char* line = nullptr;
-    size_t n = 0;
-    std::string tok, read, target;
-    while (getline(&line, &n, f) > 0) {
-      if (line[0] == '@') continue;
-      std::stringstream ss(line);
-      int col = 1;
-      while (bool(ss >> tok)) {
-        if (col == 1) read = tok;
-        else if (col == target_col) target = tok;
-        col++;
-      }
-      add(read, target, targets, 0);
-    }
-    std::free(line);
-    std::fclose(f);
-  }
-
   static unsigned count_ge(const std::vector<unsigned>& v, unsigned thr)
   {
     unsigned c = 0;
@@ -351,37 +354,160 @@ private:
     return c;
   }
 
-  void filter(double max_per_10kbp, unsigned mx_min, unsigned mx_max, const SeqIndex& targets)
-  { // :230-320
-    if (max_per_10kbp <= 0) die("max_mapped_seqs_per_target_10kbp is not positive.");
-    if (mx_min >= mx_max) die("mx_threshold_min is not smaller than mx_threshold_max.");
-    for (auto& kv : maps) {
-      auto& reads = kv.second;
-      if (reads.empty()) continue;
-      const auto& m = mx.at(kv.first);
-      if (!targets.exists(kv.first)) continue;
-      const int max_reads = int(std::ceil(double(targets.at(kv.first).len) * max_per_10kbp / 10000.0));
-      if (max_reads <= 0) die("max_mapped_seqs <= 0.");
-      int lo = int(mx_min), hi = int(mx_max), thr;
-      if (int(reads.size()) <= max_reads) thr = lo;
-      else if (int(count_ge(m, unsigned(hi))) > max_reads) thr = hi;
-      else {
-        while (hi - lo > 1) {
-          const int mid = (hi + lo) / 2;
-          if (int(count_ge(m, unsigned(mid))) > max_reads) lo = mid; else hi = mid;
-        }
-        thr = hi;
-      }
-      std::vector<std::string> kept;
-      for (size_t i = 0; i < reads.size(); i++)
-        if (int(m[i]) >= thr) kept.push_back(reads[i]);
-      reads.swap(kept);
+  void load(const std::string& path, const SeqIndex& targets, int target_col, unsigned mx_min, unsigned mx_max,
+            double max_per_10kbp, unsigned threads)
+  {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) die("cannot open " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) die("cannot stat " + path);
+    const size_t N = size_t(st.st_size);
+    const char* d = nullptr;
+    if (N) {
+      d = static_cast<const char*>(mmap(nullptr, N, PROT_READ, MAP_PRIVATE, fd, 0));
+      if (d == MAP_FAILED) die("cannot map " + path);
+      madvise(const_cast<char*>(d), N, MADV_SEQUENTIAL);
     }
+    const size_t T = std::max<size_t>(1, std::min<size_t>(threads, N / (1u << 20) + 1));
+    shards.assign(T, Map());
+    auto parallel = [&](auto&& fn) {
+      std::vector<std::thread> th;
+      for (size_t t = 1; t < T; t++) th.emplace_back(fn, t);
+      fn(size_t(0));
+      for (auto& x : th) x.join();
+    };
+    // 1. slices start at line starts
+    std::vector<size_t> cut(T + 1, N);
+    cut[0] = 0;
+    for (size_t t = 1; t < T; t++) {
+      size_t pos = std::max(cut[t - 1], N / T * t);
+      if (pos > 0 && pos < N && d[pos - 1] != '\n') {
+        const char* q = static_cast<const char*>(memchr(d + pos, '\n', N - pos));
+        pos = q ? size_t(q - d) + 1 : N;
+      }
+      cut[t] = std::min(pos, N);
+    }
+    std::vector<Slice> sl(T);
+    parallel([&](size_t t) {
+      Slice& S = sl[t];
+      size_t pos = cut[t];
+      const size_t end = cut[t + 1];
+      if (target_col == 0) { // whitespace-separated tokens
+        while (pos < end) {
+          while (pos < end && is_space(d[pos])) pos++;
+          const size_t b = pos;
+          while (pos < end && !is_space(d[pos])) pos++;
+          if (pos > b) S.toks.emplace_back(d + b, pos - b);
+        }
+        return;
+      }
+      while (pos < end) { // one record per line that does not start with '@'
+        const char* q = static_cast<const char*>(memchr(d + pos, '\n', end - pos));
+        const size_t le = q ? size_t(q - d) : end;
+        if (d[pos] != '@') {
+          Rec r;
+          int col = 1;
+          size_t p = pos;
+          while (p < le && (col <= target_col)) {
+            while (p < le && is_space(d[p])) p++;
+            const size_t b = p;
+            while (p < le && !is_space(d[p])) p++;
+            if (p == b) break;
+            if (col == 1) { r.read = sv(d + b, p - b); r.has_read = true; }
+            else if (col == target_col) { r.target = sv(d + b, p - b); r.has_target = true; }
+            col++;
+          }
+          if (!r.has_read || !r.has_target) S.incomplete = true;
+          S.recs.push_back(r);
+        }
+        pos = le + 1;
+      }
+    });
+    // 2. carry-over
+    if (target_col == 0) {
+      bool whole = true;
+      for (const Slice& S : sl) whole = whole && S.toks.size() % 3 == 0;
+      if (!whole) { // triples straddle lines AND slices: regroup the token stream as one
+        for (size_t t = 1; t < T; t++) {
+          sl[0].toks.insert(sl[0].toks.end(), sl[t].toks.begin(), sl[t].toks.end());
+          std::vector<sv>().swap(sl[t].toks);
+        }
+      }
+      parallel([&](size_t t) {
+        Slice& S = sl[t];
+        S.recs.reserve(S.toks.size() / 3);
+        for (size_t i = 0; i + 2 < S.toks.size(); i += 3) { // (a trailing partial triple never reaches `case 2`)
+          Rec r;
+          r.read = S.toks[i]; r.target = S.toks[i + 1]; r.has_read = r.has_target = true;
+          r.mx = parse_mx(S.toks[i + 2]);
+          if (r.mx >= mx_min) S.recs.push_back(r); // :96
+        }
+        std::vector<sv>().swap(S.toks);
+      });
+    } else {
+      sv read, target; // ids of the line before (empty strings before the first line, :144, :197)
+      for (Slice& S : sl) {
+        if (S.incomplete)
+          for (Rec& r : S.recs) {
+            if (!r.has_read) r.read = read;
+            if (!r.has_target) r.target = target;
+            read = r.read; target = r.target;
+          }
+        else if (!S.recs.empty()) { read = S.recs.back().read; target = S.recs.back().target; }
+      }
+    }
+    // 3. one shard of targets per thread
+    parallel([&](size_t me) {
+      struct Entry {
+        bool known = false;
+        std::vector<sv> reads;
+        std::unordered_set<sv> seen;
+        std::vector<unsigned> mx;
+      };
+      std::unordered_map<sv, Entry> mine;
+      const std::hash<sv> H;
+      for (const Slice& S : sl)
+        for (const Rec& r : S.recs) {
+          if (T > 1 && H(r.target) % T != me) continue;
+          auto it = mine.find(r.target);
+          if (it == mine.end()) { // load_mapping, :37-72: targets that the index does not know are ignored
+            it = mine.emplace(r.target, Entry()).first;
+            it->second.known = targets.exists(std::string(r.target));
+          }
+          Entry& e = it->second;
+          if (!e.known || !e.seen.insert(r.read).second) continue;
+          e.reads.push_back(r.read);
+          e.mx.push_back(unsigned(r.mx));
+        }
+      Map& out = shards[me];
+      for (auto& kv : mine) {
+        Entry& e = kv.second;
+        if (!e.known || e.reads.empty()) continue;
+        int thr = 0;
+        if (target_col == 0) { // filter, :230-320
+          const int max_reads = int(std::ceil(double(targets.at(std::string(kv.first)).len) * max_per_10kbp / 10000.0));
+          if (max_reads <= 0) die("max_mapped_seqs <= 0.");
+          int lo = int(mx_min), hi = int(mx_max);
+          if (int(e.reads.size()) <= max_reads) thr = lo;
+          else if (int(count_ge(e.mx, unsigned(hi))) > max_reads) thr = hi;
+          else {
+            while (hi - lo > 1) {
+              const int mid = (hi + lo) / 2;
+              if (int(count_ge(e.mx, unsigned(mid))) > max_reads) lo = mid; else hi = mid;
+            }
+            thr = hi;
+          }
+        }
+        std::vector<std::string>& kept = out[std::string(kv.first)];
+        for (size_t i = 0; i < e.reads.size(); i++)
+          if (target_col != 0 || int(e.mx[i]) >= thr) kept.emplace_back(e.reads[i]);
+      }
+    });
+    if (N) munmap(const_cast<char*>(d), N);
+    close(fd);
   }
 
-  std::unordered_map<std::string, std::vector<std::string>> maps;
-  std::unordered_map<std::string, std::unordered_set<std::string>> seen;
-  std::unordered_map<std::string, std::vector<unsigned>> mx;
+  std::vector<Map> shards; // target -> reads; a target lives in shard hash(target) % shards.size()
 };
 
 // ---------------------------------------------------------------------------------------

@@ -73,7 +73,22 @@ struct Request {
   std::vector<FastaRecord> recs;
   std::vector<std::string> polished;   // one per record ("" + dropped flag when the reference would not emit it)
   std::vector<uint8_t> dropped;
+  uint64_t input_size = 0;             // bytes of <batch.fa> (the guard compares file sizes, scripts/goldpolish-ntedit:31-37)
+  std::string body;                    // what goes to <out.fa> ...
+  bool keep_input = false;             // ... unless the guard rejected it: then <out.fa> is a copy of <batch.fa>
+  // "@prep <k> <prepd.fa>" after "@polish": also leave what `goldpolish-mask -s -k<k> <out.fa>` would print
+  // (scripts/goldpolish-make:65-66) in <prepd.fa>, masked on the device (gp_prep) while the records are at hand
+  unsigned prep_k = 0;
+  std::string prep_path, prep_body;
 };
+
+// ">id[ comment]\n" + sequence + "\n", as ntEdit (ntedit.cpp:1853-1856) and btllib::SeqWriter write FASTA
+void append_record(std::string& body, const FastaRecord& rec, const char* seq, size_t len)
+{
+  body += ">" + rec.name + (rec.comment.empty() ? "" : " " + rec.comment) + "\n";
+  body.append(seq, len);
+  body += "\n";
+}
 
 // One GPU: a context, the read store, a queue of pending requests and the thread that builds them.
 struct Device {
@@ -87,6 +102,54 @@ struct Device {
   uint64_t batches_served = 0;
   bool stopping = false;
   std::thread thread;
+
+  // <out.fa> of every polished request (k chain + the 0.75 guard), and <prepd.fa> of those that asked for it: the
+  // records that <out.fa> holds, masked by ONE gp_prep call for all of them
+  void finish_polished(std::vector<std::shared_ptr<Request>>& todo)
+  {
+    std::string mseqs;
+    std::vector<uint64_t> moff(1, 0);
+    struct Ref { Request* r; const FastaRecord* rec; };
+    std::vector<Ref> mrecs;
+    std::vector<FastaRecord> reread; // (records of guard-rejected batches are masked as the input file holds them)
+    for (auto& rp : todo) {
+      Request& r = *rp;
+      if (!r.polish) continue;
+      for (size_t i = 0; i < r.recs.size(); i++)
+        if (!r.dropped[i]) append_record(r.body, r.recs[i], r.polished[i].data(), r.polished[i].size()); // ntedit.cpp:1850
+      const bool keep_input = r.keep_input = gp_guard_rejects(r.input_size, r.body.size()) != 0; // scripts/goldpolish-ntedit:31-37
+      if (r.prep_k == 0) continue;
+      for (size_t i = 0; i < r.recs.size(); i++) {
+        if (!keep_input && r.dropped[i]) continue;
+        const std::string& seq = keep_input ? r.recs[i].seq : r.polished[i];
+        mseqs += seq;
+        moff.push_back(mseqs.size());
+        mrecs.push_back(Ref{ &r, &r.recs[i] });
+      }
+    }
+    if (mrecs.empty()) return;
+    // all requests of a call share one mask width in practice (the first k value); group by k to be exact
+    std::vector<unsigned> widths;
+    for (const auto& m : mrecs)
+      if (std::find(widths.begin(), widths.end(), m.r->prep_k) == widths.end()) widths.push_back(m.r->prep_k);
+    for (const unsigned kk : widths) {
+      std::string seqs;
+      std::vector<uint64_t> off(1, 0);
+      std::vector<size_t> who;
+      for (size_t i = 0; i < mrecs.size(); i++)
+        if (mrecs[i].r->prep_k == kk) {
+          seqs.append(mseqs, moff[i], moff[i + 1] - moff[i]);
+          off.push_back(seqs.size());
+          who.push_back(i);
+        }
+      std::vector<char> out(seqs.size() + who.size() + 16);
+      std::vector<uint64_t> ooff(who.size() + 1, 0);
+      check_gp(ctx, gp_prep(ctx, uint32_t(who.size()), seqs.data(), off.data(), 1, kk, 0, out.data(), out.size(), ooff.data()),
+               "gp_prep");
+      for (size_t j = 0; j < who.size(); j++)
+        append_record(mrecs[who[j]].r->prep_body, *mrecs[who[j]].rec, out.data() + ooff[j], size_t(ooff[j + 1] - ooff[j]));
+    }
+  }
 
   // builds every request that is pending in one call.  The payloads land in page-locked memory that the build
   // kernel fills filter by filter as they become final (gp_build_output_host): no bulk copy after the build, and
@@ -155,6 +218,7 @@ struct Device {
               todo[i]->polished.emplace_back(pout.data() + poff[c], size_t(poff[c + 1] - poff[c]));
               todo[i]->dropped.push_back(dropped[c]);
             }
+        finish_polished(todo);
       }
       {
         std::lock_guard<std::mutex> lk(mu);
@@ -244,13 +308,14 @@ int main(int argc, char** argv)
     std::vector<const std::string*> order;
     std::vector<uint32_t> lens;
     uint64_t total = 0;
-    for (const auto& kv : maps.all())
-      for (const auto& id : kv.second)
+    maps.for_each([&](const std::string&, const std::vector<std::string>& ids) {
+      for (const auto& id : ids)
         if (read_slot.emplace(id, uint32_t(order.size())).second) {
           order.push_back(&id);
           lens.push_back(uint32_t(reads.at(id).len));
           total += lens.back();
         }
+    });
     info("Uploading " + std::to_string(order.size()) + " mapped reads (" + std::to_string(total) + " bases) to " +
          std::to_string(devs.size()) + " device(s)");
     for (auto& d : devs) check_gp(d->ctx, gp_reads_begin(d->ctx, order.size(), lens.data()), "gp_reads_begin");
@@ -291,6 +356,12 @@ int main(int argc, char** argv)
           req->polish = true;
           continue;
         }
+        if (id == "@prep") {
+          long kk = 0;
+          if (!(in >> kk >> req->prep_path) || kk < 1 || kk > 64) die("malformed @prep request for batch " + batch);
+          req->prep_k = unsigned(kk);
+          continue;
+        }
         const uint64_t tlen = targets.at(id).len;
         const auto& mapped = maps.get(id);
         if (mapped.empty()) continue;
@@ -301,11 +372,11 @@ int main(int argc, char** argv)
         }
       }
     }
-    uint64_t input_size = 0;
+    if (req->prep_k && !req->polish) die("@prep without @polish for batch " + batch);
     if (req->polish) {
       struct stat st;
       if (stat(req->seqs_path.c_str(), &st) != 0) die("cannot stat " + req->seqs_path);
-      input_size = uint64_t(st.st_size);
+      req->input_size = uint64_t(st.st_size);
       req->recs = read_fasta(req->seqs_path);
     }
     // the device with the least work pending
@@ -328,19 +399,19 @@ int main(int argc, char** argv)
       bf_format::save(batch + "-k" + std::to_string(ks[i]) + ".bf", req->payload.data() + i * GP_BF_BYTES, GP_BF_BYTES,
                       GP_HASH_NUM, ks[i]);
     if (req->polish) { // after the .bf files: `make` must not find the polished file older than its prerequisites
-      std::string body;
-      for (size_t i = 0; i < req->recs.size(); i++) {
-        if (req->dropped[i]) continue; // ntedit.cpp:1850
-        body += ">" + req->recs[i].name + (req->recs[i].comment.empty() ? "" : " " + req->recs[i].comment) + "\n";
-        body += req->polished[i];
-        body += "\n";
+      {
+        std::ofstream o(req->out_path, std::ios::binary);
+        if (!o.good()) die("cannot write " + req->out_path);
+        if (req->keep_input) { // scripts/goldpolish-ntedit:31-37
+          std::ifstream in(req->seqs_path, std::ios::binary);
+          o << in.rdbuf();
+        } else o << req->body;
       }
-      std::ofstream o(req->out_path, std::ios::binary);
-      if (!o.good()) die("cannot write " + req->out_path);
-      if (gp_guard_rejects(input_size, body.size())) { // scripts/goldpolish-ntedit:31-37: keep the input
-        std::ifstream in(req->seqs_path, std::ios::binary);
-        o << in.rdbuf();
-      } else o << body;
+      if (req->prep_k) { // after <out.fa>, its prerequisite in goldpolish-make's `%.prepd.fa: %.fa`
+        std::ofstream o(req->prep_path, std::ios::binary);
+        if (!o.good()) die("cannot write " + req->prep_path);
+        o << req->prep_body;
+      }
     }
     confirm_pipe(ready_pipe);
     std::remove(ids_pipe.c_str());

@@ -154,4 +154,35 @@ ref_serve_batches(const char* target_fa,
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// What the reference's own AllMappings (src/mappings.cpp) holds after loading `mappings_path`: one line per target of
+// the index that has mappings, sorted by id, "<target>\t<read> <read> ...\n" (gp-host-check prints the same from
+// goldpolish_b200's loader).  Returns 0, or < 0 when the output cannot be written.
+int
+ref_mappings_dump(const char* target_fa, const char* target_index, const char* mappings_path, double mx_max, const char* out_path)
+{
+  SeqIndex target_seqs_index(target_index, target_fa);
+  AllMappings all_mappings(mappings_path, target_seqs_index, MX_THRESHOLD_MIN, MX_THRESHOLD_MAX, mx_max);
+  std::vector<std::string> ids;
+  {
+    std::ifstream ifs(target_index);
+    std::string tok;
+    unsigned long i = 0;
+    while (bool(ifs >> tok)) {
+      if (i++ % 4 == 0) ids.push_back(tok);
+    }
+  }
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  std::ofstream out(out_path);
+  if (!out.good()) return -1;
+  for (const auto& id : ids) {
+    const auto& v = all_mappings.get_mappings(id);
+    if (v.empty()) continue;
+    out << id << '\t';
+    for (size_t j = 0; j < v.size(); j++) out << (j ? " " : "") << v[j];
+    out << '\n';
+  }
+  return 0;
+}
+
 } // extern "C"

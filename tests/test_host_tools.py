@@ -312,4 +312,14 @@ def test_polish_batch_dropin_fused_with_the_server():
                 t.join(timeout=60)
                 assert got_done and got_done[0].strip() == "1"
                 assert open(os.path.join(fused, "batch.ntedited.fa")).read() == expected, b
+                # "@prep": what `goldpolish-mask -s -k32 batch.ntedited.fa` prints (scripts/goldpolish-make:65-66), by the
+                # restatement that the reference script's own vectors pin (tests/test_mask.py) and by our mask tool
+                from oracle import mask_oracle as mo
+                lines = expected.split("\n")
+                want = "".join(h + "\n" + mo.mask(q, 32) + "\n" for h, q in zip(lines[0::2], lines[1::2]) if h)
+                prepd = os.path.join(fused, "batch.ntedited.prepd.fa")
+                assert open(prepd).read() == want, b
+                assert subprocess.check_output([os.path.join(BIN, "goldpolish-mask"), "-s", "-k32", "batch.ntedited.fa"],
+                                               cwd=fused, env=ENV).decode() == want, b
+                assert os.stat(prepd).st_mtime_ns >= os.stat(os.path.join(fused, "batch.ntedited.fa")).st_mtime_ns
                 assert not any(os.path.exists(os.path.join(bdir, f"{name}-k{k}.bf")) for k in KS)
