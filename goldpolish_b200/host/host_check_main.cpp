@@ -1,5 +1,5 @@
 // gp-host-check: prints what the host side of the drop-ins decided, without touching a GPU -- for parity tests of the
-// feeder logic against the reference's own classes (oracle/ref_harness_bfs.cpp dumps the same text from AllMappings).
+// feeder logic against the reference's own classes (the test harness dumps the same text from its AllMappings).
 //   gp-host-check mappings <targets.fa> <targets.index> <mappings> <mx_max_per_10kbp> [threads]
 //       one line per target of the index that has mappings, sorted by id: "<target>\t<read> <read> ...\n"
 //       (src/mappings.cpp:15-330 with MX_THRESHOLD_MIN/MAX of src/goldpolish_targeted_bfs.cpp:34-35)
