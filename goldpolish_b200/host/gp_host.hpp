@@ -55,6 +55,91 @@ inline bool endswith(const std::string& s, const std::string& suf)
 }
 
 // ---------------------------------------------------------------------------------------
+// Text files read by all host cores: a read-only map of the file, cut at line ends into one slice
+// per thread (at least 1 MiB of text each)
+// ---------------------------------------------------------------------------------------
+inline unsigned host_threads(unsigned threads)
+{ // 0: GP_HOST_THREADS, else every core
+  if (threads == 0)
+    if (const char* e = std::getenv("GP_HOST_THREADS")) threads = unsigned(std::max(0, std::atoi(e)));
+  return threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+}
+inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); } // std::isspace in the "C" locale
+
+struct SlicedFile {
+  const char* d = nullptr;
+  size_t N = 0, T = 1;
+  std::vector<size_t> cut; // slice t = [cut[t], cut[t + 1]); every slice starts at a line start
+  int fd = -1;
+
+  SlicedFile(const std::string& path, unsigned threads)
+  {
+    fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) die("cannot open " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) die("cannot stat " + path);
+    N = size_t(st.st_size);
+    if (N) {
+      d = static_cast<const char*>(mmap(nullptr, N, PROT_READ, MAP_PRIVATE, fd, 0));
+      if (d == MAP_FAILED) die("cannot map " + path);
+      madvise(const_cast<char*>(d), N, MADV_SEQUENTIAL);
+    }
+    T = std::max<size_t>(1, std::min<size_t>(host_threads(threads), N / (1u << 20) + 1));
+    cut.assign(T + 1, N);
+    cut[0] = 0;
+    for (size_t t = 1; t < T; t++) {
+      size_t pos = std::max(cut[t - 1], N / T * t);
+      if (pos > 0 && pos < N && d[pos - 1] != '\n') {
+        const char* q = static_cast<const char*>(memchr(d + pos, '\n', N - pos));
+        pos = q ? size_t(q - d) + 1 : N;
+      }
+      cut[t] = std::min(pos, N);
+    }
+  }
+  SlicedFile(const SlicedFile&) = delete;
+  SlicedFile& operator=(const SlicedFile&) = delete;
+  ~SlicedFile()
+  {
+    if (N) munmap(const_cast<char*>(d), N);
+    if (fd >= 0) close(fd);
+  }
+  // fn(t) for every slice, one thread each
+  template <class Fn> void parallel(Fn&& fn) const
+  {
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < T; t++) th.emplace_back(fn, t);
+    fn(size_t(0));
+    for (auto& x : th) x.join();
+  }
+  // whitespace-separated tokens of every slice (`stream >> token`), as views into the map.  Formats whose records are
+  // `group` tokens whatever the line structure (the SeqIndex file: 4, ntLink mappings: 3) need every slice to hold
+  // whole records: if one does not, all tokens are handed back as ONE slice
+  std::vector<std::vector<std::string_view>> tokens(size_t group) const
+  {
+    std::vector<std::vector<std::string_view>> out(T);
+    parallel([&](size_t t) {
+      size_t pos = cut[t];
+      const size_t end = cut[t + 1];
+      auto& v = out[t];
+      while (pos < end) {
+        while (pos < end && is_space(d[pos])) pos++;
+        const size_t b = pos;
+        while (pos < end && !is_space(d[pos])) pos++;
+        if (pos > b) v.emplace_back(d + b, pos - b);
+      }
+    });
+    bool whole = true;
+    for (const auto& v : out) whole = whole && v.size() % group == 0;
+    if (!whole)
+      for (size_t t = 1; t < T; t++) {
+        out[0].insert(out[0].end(), out[t].begin(), out[t].end());
+        std::vector<std::string_view>().swap(out[t]);
+      }
+    return out;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
 // SeqIndex: id -> (byte offset of the sequence line, length, average phred)
 // ---------------------------------------------------------------------------------------
 struct SeqRecord {
@@ -175,7 +260,7 @@ public:
     });
     size_t total = 0;
     for (auto& v : out) total += v.size();
-    ix.recs.reserve(total);
+    ix.shards[0].reserve(total);
     ix.order.reserve(total);
     for (auto& v : out)
       for (auto& r : v) ix.add(r.id, r.start, r.len, r.phred);
@@ -189,41 +274,70 @@ public:
   {
     std::ofstream o(path);
     for (const auto& id : order) {
-      const auto& r = recs.at(id);
+      const SeqRecord& r = at(id);
       o << id << '\t' << r.start << '\t' << r.len << '\t' << r.phred << '\n';
     }
   }
 
-  // whitespace separated tokens, four per record (src/seqindex.cpp:86-125)
-  static SeqIndex load(const std::string& index_path, const std::string& seqs_path)
+  // whitespace separated tokens, four per record (src/seqindex.cpp:86-125); the first duplicate id wins.  Loaded by
+  // all host cores: tokens per slice of the file, then the ids are dealt to the threads by hash and every thread fills
+  // its own shard of the map, walking the records in file order
+  static SeqIndex load(const std::string& index_path, const std::string& seqs_path, unsigned threads = 0)
   {
     SeqIndex ix;
     ix.seqs_path = seqs_path;
-    std::ifstream f(index_path);
-    if (!f.good()) die("cannot open " + index_path);
-    std::string tok, id;
-    uint64_t start = 0, len = 0;
-    unsigned long i = 0;
-    while (bool(f >> tok)) {
-      switch (i % 4) {
-      case 0: id = tok; break;
-      case 1: start = std::stoull(tok); break;
-      case 2: len = std::stoull(tok); break;
-      default: ix.add(id, start, len, std::stod(tok)); break;
-      }
-      i++;
-    }
+    const SlicedFile f(index_path, threads);
+    const auto toks = f.tokens(4);
+    const size_t T = f.T;
+    struct Rec { std::string_view id; uint64_t start, len; double phred; };
+    std::vector<std::vector<Rec>> recs(T);
+    std::vector<std::vector<uint8_t>> first(T);
+    f.parallel([&](size_t t) {
+      const auto& v = toks[t];
+      recs[t].reserve(v.size() / 4);
+      for (size_t i = 0; i + 3 < v.size(); i += 4) // (a trailing partial record never reaches the fourth token)
+        recs[t].push_back(Rec{ v[i], to_u64(v[i + 1]), to_u64(v[i + 2]), to_double(v[i + 3]) });
+      first[t].assign(recs[t].size(), 0);
+    });
+    ix.shards.assign(T, Shard());
+    f.parallel([&](size_t me) {
+      Shard& mine = ix.shards[me];
+      const std::hash<std::string_view> H;
+      for (size_t t = 0; t < T; t++)
+        for (size_t i = 0; i < recs[t].size(); i++) {
+          const Rec& r = recs[t][i];
+          if (T > 1 && H(r.id) % T != me) continue;
+          SeqRecord sr;
+          sr.start = r.start; sr.len = r.len; sr.phred = r.phred;
+          if (mine.emplace(std::string(r.id), sr).second) first[t][i] = 1;
+        }
+    });
+    std::vector<std::vector<std::string>> ord(T);
+    f.parallel([&](size_t t) {
+      for (size_t i = 0; i < recs[t].size(); i++)
+        if (first[t][i]) ord[t].emplace_back(recs[t][i].id);
+    });
+    size_t total = 0;
+    for (const auto& v : ord) total += v.size();
+    ix.order.reserve(total);
+    for (auto& v : ord)
+      for (auto& id : v) ix.order.push_back(std::move(id));
     return ix;
   }
 
-  bool exists(const std::string& id) const { return recs.find(id) != recs.end(); }
+  bool exists(const std::string& id) const { return find(id) != nullptr; }
   const SeqRecord& at(const std::string& id) const
   {
-    const auto it = recs.find(id);
-    if (it == recs.end()) die("sequence id not in index: " + id); // unordered_map::at would throw
-    return it->second;
+    const SeqRecord* r = find(id);
+    if (!r) die("sequence id not in index: " + id); // unordered_map::at would throw
+    return *r;
   }
-  size_t size() const { return recs.size(); }
+  size_t size() const
+  {
+    size_t n = 0;
+    for (const Shard& m : shards) n += m.size();
+    return n;
+  }
 
   // whole sequence line, as SeqIndex::get_seq<1> returns it (src/seqindex.hpp:59-102)
   void read_seq(const std::string& id, std::string& out) const
@@ -247,15 +361,47 @@ public:
   std::vector<std::string> order; // insertion order (save() of the reference iterates a hash map)
 
 private:
+  using Shard = std::unordered_map<std::string, SeqRecord>;
+  const SeqRecord* find(const std::string& id) const
+  {
+    const Shard& m = shards[shards.size() > 1 ? std::hash<std::string>{}(id) % shards.size() : 0];
+    const auto it = m.find(id);
+    return it == m.end() ? nullptr : &it->second;
+  }
   void add(const std::string& id, uint64_t start, uint64_t len, double phred)
   {
-    if (recs.find(id) != recs.end()) return;
+    Shard& m = shards[shards.size() > 1 ? std::hash<std::string>{}(id) % shards.size() : 0];
+    if (m.find(id) != m.end()) return;
     SeqRecord r;
     r.start = start; r.len = len; r.phred = phred;
-    recs.emplace(id, r);
+    m.emplace(id, r);
     order.push_back(id);
   }
-  std::unordered_map<std::string, SeqRecord> recs;
+  // std::stoull / std::stod of the reference (:105-113); plain digit strings take the short way
+  static uint64_t to_u64(std::string_view t)
+  {
+    uint64_t v = 0;
+    bool plain = !t.empty() && t.size() < 19;
+    for (const char c : t) {
+      if (c < '0' || c > '9') { plain = false; break; }
+      v = v * 10 + unsigned(c - '0');
+    }
+    if (plain) return v;
+    try {
+      return std::stoull(std::string(t));
+    } catch (const std::exception&) {
+      die("index: '" + std::string(t) + "' is not a number");
+    }
+  }
+  static double to_double(std::string_view t)
+  {
+    try {
+      return std::stod(std::string(t));
+    } catch (const std::exception&) {
+      die("index: '" + std::string(t) + "' is not a number");
+    }
+  }
+  std::vector<Shard> shards = std::vector<Shard>(1); // an id lives in shard hash(id) % shards.size()
   mutable int fd = -1;
 };
 
@@ -264,8 +410,8 @@ private:
 // ---------------------------------------------------------------------------------------
 // Same result as AllMappings (src/mappings.cpp:15-330), loaded by all host cores instead of one
 // stream-parsing thread:
-//   1. the file is mapped and cut at line ends into one slice per thread; every thread tokenises its slice into
-//      (read, target, minimizers) records that point into the map (no copies);
+//   1. the file is mapped and cut at line ends into one slice per thread (SlicedFile); every thread tokenises its slice
+//      into (read, target, minimizers) records that point into the map (no copies);
 //   2. the reference's carry-over -- a line with too few columns keeps the ids of the line before it (:146-160,
 //      :199-213), ntLink tokens are triples whatever the line structure (:83-108) -- is resolved by one short sequential
 //      pass over the slices that need it (none, in a well-formed file);
@@ -291,10 +437,6 @@ public:
     if (target_col == 0) {
       if (mx_max_per_10kbp <= 0) die("max_mapped_seqs_per_target_10kbp is not positive.");
       if (mx_min >= mx_max) die("mx_threshold_min is not smaller than mx_threshold_max.");
-    }
-    if (threads == 0) {
-      if (const char* e = std::getenv("GP_HOST_THREADS")) threads = unsigned(std::max(0, std::atoi(e)));
-      if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
     }
     load(path, targets, target_col, mx_min, mx_max, mx_max_per_10kbp, threads);
   }
@@ -327,11 +469,9 @@ private:
     bool has_read = false, has_target = false;
   };
   struct Slice {
-    std::vector<Rec> recs;     // line formats; ntLink when the slice holds whole triples
-    std::vector<sv> toks;      // ntLink
+    std::vector<Rec> recs;
     bool incomplete = false;   // some record lacks an id of its own
   };
-  static bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); } // std::isspace, "C" locale
   static unsigned long parse_mx(sv t)
   { // std::stoul (:95); digits-only tokens take the short way
     unsigned long v = 0;
@@ -357,94 +497,52 @@ private:
   void load(const std::string& path, const SeqIndex& targets, int target_col, unsigned mx_min, unsigned mx_max,
             double max_per_10kbp, unsigned threads)
   {
-    const int fd = open(path.c_str(), O_RDONLY);
-    if (fd < 0) die("cannot open " + path);
-    struct stat st;
-    if (fstat(fd, &st) != 0) die("cannot stat " + path);
-    const size_t N = size_t(st.st_size);
-    const char* d = nullptr;
-    if (N) {
-      d = static_cast<const char*>(mmap(nullptr, N, PROT_READ, MAP_PRIVATE, fd, 0));
-      if (d == MAP_FAILED) die("cannot map " + path);
-      madvise(const_cast<char*>(d), N, MADV_SEQUENTIAL);
-    }
-    const size_t T = std::max<size_t>(1, std::min<size_t>(threads, N / (1u << 20) + 1));
+    const SlicedFile f(path, threads);
+    const char* d = f.d;
+    const size_t T = f.T;
     shards.assign(T, Map());
-    auto parallel = [&](auto&& fn) {
-      std::vector<std::thread> th;
-      for (size_t t = 1; t < T; t++) th.emplace_back(fn, t);
-      fn(size_t(0));
-      for (auto& x : th) x.join();
-    };
-    // 1. slices start at line starts
-    std::vector<size_t> cut(T + 1, N);
-    cut[0] = 0;
-    for (size_t t = 1; t < T; t++) {
-      size_t pos = std::max(cut[t - 1], N / T * t);
-      if (pos > 0 && pos < N && d[pos - 1] != '\n') {
-        const char* q = static_cast<const char*>(memchr(d + pos, '\n', N - pos));
-        pos = q ? size_t(q - d) + 1 : N;
-      }
-      cut[t] = std::min(pos, N);
-    }
+    auto parallel = [&](auto&& fn) { f.parallel(fn); };
+    // 1. + 2. records per slice, carry-over resolved
     std::vector<Slice> sl(T);
-    parallel([&](size_t t) {
-      Slice& S = sl[t];
-      size_t pos = cut[t];
-      const size_t end = cut[t + 1];
-      if (target_col == 0) { // whitespace-separated tokens
-        while (pos < end) {
-          while (pos < end && is_space(d[pos])) pos++;
-          const size_t b = pos;
-          while (pos < end && !is_space(d[pos])) pos++;
-          if (pos > b) S.toks.emplace_back(d + b, pos - b);
-        }
-        return;
-      }
-      while (pos < end) { // one record per line that does not start with '@'
-        const char* q = static_cast<const char*>(memchr(d + pos, '\n', end - pos));
-        const size_t le = q ? size_t(q - d) : end;
-        if (d[pos] != '@') {
-          Rec r;
-          int col = 1;
-          size_t p = pos;
-          while (p < le && (col <= target_col)) {
-            while (p < le && is_space(d[p])) p++;
-            const size_t b = p;
-            while (p < le && !is_space(d[p])) p++;
-            if (p == b) break;
-            if (col == 1) { r.read = sv(d + b, p - b); r.has_read = true; }
-            else if (col == target_col) { r.target = sv(d + b, p - b); r.has_target = true; }
-            col++;
-          }
-          if (!r.has_read || !r.has_target) S.incomplete = true;
-          S.recs.push_back(r);
-        }
-        pos = le + 1;
-      }
-    });
-    // 2. carry-over
     if (target_col == 0) {
-      bool whole = true;
-      for (const Slice& S : sl) whole = whole && S.toks.size() % 3 == 0;
-      if (!whole) { // triples straddle lines AND slices: regroup the token stream as one
-        for (size_t t = 1; t < T; t++) {
-          sl[0].toks.insert(sl[0].toks.end(), sl[t].toks.begin(), sl[t].toks.end());
-          std::vector<sv>().swap(sl[t].toks);
-        }
-      }
+      const auto toks = f.tokens(3);
       parallel([&](size_t t) {
-        Slice& S = sl[t];
-        S.recs.reserve(S.toks.size() / 3);
-        for (size_t i = 0; i + 2 < S.toks.size(); i += 3) { // (a trailing partial triple never reaches `case 2`)
+        const auto& v = toks[t];
+        sl[t].recs.reserve(v.size() / 3);
+        for (size_t i = 0; i + 2 < v.size(); i += 3) { // (a trailing partial triple never reaches `case 2`)
           Rec r;
-          r.read = S.toks[i]; r.target = S.toks[i + 1]; r.has_read = r.has_target = true;
-          r.mx = parse_mx(S.toks[i + 2]);
-          if (r.mx >= mx_min) S.recs.push_back(r); // :96
+          r.read = v[i]; r.target = v[i + 1]; r.has_read = r.has_target = true;
+          r.mx = parse_mx(v[i + 2]);
+          if (r.mx >= mx_min) sl[t].recs.push_back(r); // :96
         }
-        std::vector<sv>().swap(S.toks);
       });
     } else {
+      parallel([&](size_t t) {
+        Slice& S = sl[t];
+        size_t pos = f.cut[t];
+        const size_t end = f.cut[t + 1];
+        while (pos < end) { // one record per line that does not start with '@'
+          const char* q = static_cast<const char*>(memchr(d + pos, '\n', end - pos));
+          const size_t le = q ? size_t(q - d) : end;
+          if (d[pos] != '@') {
+            Rec r;
+            int col = 1;
+            size_t p = pos;
+            while (p < le && col <= target_col) {
+              while (p < le && is_space(d[p])) p++;
+              const size_t b = p;
+              while (p < le && !is_space(d[p])) p++;
+              if (p == b) break;
+              if (col == 1) { r.read = sv(d + b, p - b); r.has_read = true; }
+              else if (col == target_col) { r.target = sv(d + b, p - b); r.has_target = true; }
+              col++;
+            }
+            if (!r.has_read || !r.has_target) S.incomplete = true;
+            S.recs.push_back(r);
+          }
+          pos = le + 1;
+        }
+      });
       sv read, target; // ids of the line before (empty strings before the first line, :144, :197)
       for (Slice& S : sl) {
         if (S.incomplete)
@@ -503,8 +601,6 @@ private:
           if (target_col != 0 || int(e.mx[i]) >= thr) kept.emplace_back(e.reads[i]);
       }
     });
-    if (N) munmap(const_cast<char*>(d), N);
-    close(fd);
   }
 
   std::vector<Map> shards; // target -> reads; a target lives in shard hash(target) % shards.size()

@@ -14,8 +14,8 @@ import test_mappings_loader as t  # noqa: E402
 
 with tempfile.TemporaryDirectory() as w:
     out = {}
-    for name, (path, mx_max) in t.make_cases(w).items():
-        dump = t.reference(w, path, mx_max)
+    for name, (path, mx_max, *index) in t.make_cases(w).items():
+        dump = t.reference(w, path, mx_max, *index)
         assert dump is not None, "build oracle/_ref first (make -C oracle ref)"
         out[name] = {"file": path, "mx_max_per_10kbp": mx_max, "targets": dump.count(b"\n"),
                      "mapped_reads": sum(len(line.split(b"\t")[1].split()) for line in dump.splitlines()),

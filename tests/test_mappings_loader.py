@@ -74,15 +74,32 @@ def make_cases(w):
     with open(os.path.join(w, "empty.paf"), "w"):
         pass
     cases["paf_empty"] = ("empty.paf", 150.0)
+    # an index (src/seqindex.cpp:86-125: four tokens per record, whatever the lines) with duplicate ids -- the first
+    # one wins, and its length decides how many reads the minimizer filter keeps -- ragged spacing, > 1 MiB
+    recs = []
+    for i in range(n_t):
+        recs.append((f"ctg{i}", 10 + i, int(tl[i]), 0.0))
+        if i % 3 == 0:
+            recs.append((f"ctg{i}", 7, int(tl[i]) * 4, 1.5))      # later duplicate: ignored
+    recs += [(f"pad{i}", i, 1000 + i, 12.25) for i in range(60000)]
+    seps = [" ", "\t", "\n", "\t\t", " \n"]
+    with open(os.path.join(w, "dup.index"), "w") as f:
+        k = 0
+        for rec in recs:
+            for tok in rec:
+                f.write(str(tok) + (seps[k % len(seps)] if k % 11 == 0 else "\t" if tok is not rec[-1] else "\n"))
+                k += 1
+    cases["ntlink_dup_index"] = ("big.tsv", 20.0, "dup.index")
     return cases
 
 
-def ours(w, path, mx_max, threads):
+def ours(w, path, mx_max, threads, index="draft.fa.index"):
     return subprocess.check_output([os.path.join(BIN, "gp-host-check"), "mappings", os.path.join(w, "draft.fa"),
-                                    os.path.join(w, "draft.fa.index"), os.path.join(w, path), str(mx_max), str(threads)], env=ENV)
+                                    os.path.join(w, index), os.path.join(w, path), str(mx_max), str(threads)],
+                                   env=dict(ENV, GP_HOST_THREADS=str(threads)))
 
 
-def reference(w, path, mx_max):
+def reference(w, path, mx_max, index="draft.fa.index"):
     """The reference's own AllMappings, or None when oracle/_ref is not built."""
     so = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
     if not os.path.exists(so):
@@ -91,7 +108,7 @@ def reference(w, path, mx_max):
     lib.ref_mappings_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_char_p]
     lib.ref_mappings_dump.restype = C.c_int
     out = os.path.join(w, "ref_dump.txt")
-    assert lib.ref_mappings_dump(os.path.join(w, "draft.fa").encode(), os.path.join(w, "draft.fa.index").encode(),
+    assert lib.ref_mappings_dump(os.path.join(w, "draft.fa").encode(), os.path.join(w, index).encode(),
                                  os.path.join(w, path).encode(), mx_max, out.encode()) == 0
     return open(out, "rb").read()
 
@@ -99,10 +116,10 @@ def reference(w, path, mx_max):
 def test_loader_matches_the_reference_mappings(tmp_path):
     w = str(tmp_path)
     golden = json.load(open(GOLDEN))
-    for name, (path, mx_max) in make_cases(w).items():
-        want = reference(w, path, mx_max)
+    for name, (path, mx_max, *index) in make_cases(w).items():
+        want = reference(w, path, mx_max, *index)
         for threads in (1, 3, 8):
-            got = ours(w, path, mx_max, threads)
+            got = ours(w, path, mx_max, threads, *index)
             if want is not None:
                 assert got == want, (name, threads)
             assert hashlib.sha256(got).hexdigest() == golden[name]["sha256"], (name, threads)
