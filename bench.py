@@ -521,7 +521,8 @@ def ours(args, rank, world, local_rank):
                 # + 1 mask bit per base; three orders of magnitude below the copy peak -- the kernel lives on random
                 # 32-byte-sector touches, not on this stream
                 "hashing_stream_gbs": hashing_gbs, "hashing_stream_frac_of_hbm_copy_peak": hashing_gbs / float(peaks["hbm_gbs"]),
-                "overlap": "edit kernel runs beside the build kernel (its span includes waiting for filters)" if not args.separate
+                "overlap": (f"edit kernel runs beside the build kernel on {st2['edit_sms']} SMs of its own (its span includes waiting for filters)"
+                            if st2.get("edit_sms") else "edit kernel runs beside the build kernel, sharing its SMs (its span includes waiting for filters)") if not args.separate
                            else "none (--separate)"}
         if args.roof:
             # measured random-access roofs (sector touches / s), same access shapes as the kernels:
@@ -620,7 +621,7 @@ def ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "parity": parity,
             "stats": {k: st2[k] for k in ("kmer_ops", "serial_kmers", "triggers", "edits", "masked", "rollbacks",
-                                          "build_ms", "polish_ms", "pack_ms", "build_kernel_ms", "edit_kernel_ms", "polish_reruns")},
+                                          "build_ms", "polish_ms", "pack_ms", "build_kernel_ms", "edit_kernel_ms", "polish_reruns", "edit_sms")},
         }
         emit(line)
         if parity is not None and (parity["bf_equal"] is False or not parity["fasta_equal"]):

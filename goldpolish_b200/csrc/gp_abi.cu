@@ -77,7 +77,8 @@ struct gp_ctx {
   std::vector<uint32_t> wave_first, wave_count, wave_order_off;
   DevBuf d_batch_entry_off, d_entries, d_bf_pool, d_cbf_pool, d_stream_order, d_next, d_counters;
   // level-synchronous build
-  DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel, d_cta_times;
+  DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel, d_cta_times, d_sm_table;
+  uint32_t edit_sms = 0;   // SMs that the last overlapped pass gave to the edit kernel (0: the two kernels shared every SM)
   uint32_t level_grid = 0; // CTAs of the last level-synchronous launch
   uint64_t anchor_stride = 0;
   uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_time_bits = 26, level_arrays = 2;
@@ -618,7 +619,7 @@ static int upload_bf_slots(gp_ctx* ctx, cudaStream_t s, bool build_order)
 
 // level-synchronous build of wave wv on stream s (build_stream_tab first); batch_done / ctas_per_sm are
 // gp_pipeline_run's (NULL, 0 otherwise)
-static int build_launch_levels_wave(gp_ctx* ctx, cudaStream_t s, size_t wv, uint32_t* batch_done, int ctas_per_sm)
+static int build_launch_levels_wave(gp_ctx* ctx, cudaStream_t s, size_t wv, uint32_t* batch_done, int ctas_per_sm, uint32_t reserve_sms = 0)
 {
   const gp_config& c = ctx->cfg;
   {
@@ -702,6 +703,14 @@ static int build_launch_levels_wave(gp_ctx* ctx, cudaStream_t s, size_t wv, uint
       GP_CUDA(ctx, ctx->d_cta_times.ensure(size_t(ctx->sm_count) * 4 * 32 * 8));
       GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cta_times.p, 0, size_t(ctx->sm_count) * 4 * 32 * 8, s));
       p.cta_times = ctx->d_cta_times.as<unsigned long long>();
+    }
+    if (reserve_sms) { // the launch fills every SM; the kernel hands `reserve_sms` of them back (see there)
+      const size_t bytes = (1 + 2 * 4096) * 4; // (%nsmid is far below 4096)
+      GP_CUDA(ctx, ctx->d_sm_table.ensure(bytes));
+      GP_CUDA(ctx, cudaMemsetAsync(ctx->d_sm_table.p, 0, bytes, s));
+      p.reserve_sms = reserve_sms;
+      p.ctas_per_sm = uint32_t(gp::levels_ctas_per_sm(ctas_per_sm));
+      p.sm_table = ctx->d_sm_table.as<uint32_t>();
     }
     ctx->level_grid = uint32_t(gp::levels_max_grid(ctx->sm_count, ctas_per_sm));
     GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s, ctas_per_sm));
@@ -1037,7 +1046,7 @@ static int polish_prepare(gp_ctx* ctx)
 
 // the edit kernel on stream es (the context's stream unless pipelined: then `order`, `batch_done` and
 // alongside are gp_pipeline_run's)
-static int polish_edit(gp_ctx* ctx, cudaStream_t es, const uint32_t* order, uint32_t n_order, const uint32_t* batch_done, bool alongside)
+static int polish_edit(gp_ctx* ctx, cudaStream_t es, const uint32_t* order, uint32_t n_order, const uint32_t* batch_done, int alongside)
 {
   const gp_config& c = ctx->cfg;
   const uint32_t n = order ? n_order : ctx->n_contigs; // slots of `order` this launch works through
@@ -1240,17 +1249,40 @@ int gp_pipeline_run(gp_ctx* ctx)
   // serialization, so it becomes resident next to the running build, takes the wave's contigs in build order and
   // waits for each one's filters.  No event may sit between the two launches; their durations come from device
   // timers.  The next wave's pool clear waits (stream order) for this wave's edit kernel.
+  // How the two kernels share the GPU.  Default: the edit kernel gets SMs of its own -- the build launch fills every SM
+  // (3 CTAs) and hands E of them back, the edit kernel's whole-SM CTAs land there (and on every SM once the build is
+  // through).  E from the work staged: edit ~0.8 us of one warp per draft base and k chain when the warp has a
+  // scheduler to itself, build ~9.6 G k-mer ops/s, 12 edit warps per SM at about a third of that speed each (three to
+  // a scheduler, L2 busy with the build) -- measured: with less, polishing falls behind the build and the step ends
+  // in a tail; every SM given away costs the build a little more than its 1/148.  GP_EDIT_SMS=n fixes E; 0 is the older
+  // scheme (every SM: 2 build CTAs + one 3-warp edit CTA), which costs the build more than it looks: an edit warp slows
+  // its SM's part of EVERY barrier interval, and the grid barrier waits for the slowest SM.
+  uint32_t edit_sms = 0;
+  if (overlap) {
+    uint64_t draft = 0, steps = 0;
+    for (uint32_t i = 0; i < n; i++) draft += ctx->h_len[i];
+    for (uint32_t ki = 0; ki < c.nk; ki++) steps += ctx->h_pre[size_t(ki) * (ctx->n_entries + 1) + ctx->n_entries];
+    const double edit_s = double(draft) * 0.8e-6, build_s = std::max(1e-6, double(steps) * 32.0 / 9.6e9);
+    edit_sms = uint32_t(std::ceil(4.5 * edit_s / build_s / 12.0));
+    edit_sms = std::min(std::max(edit_sms, 2u), 24u);
+    if (const char* e = std::getenv("GP_EDIT_SMS")) edit_sms = uint32_t(std::max(0, std::atoi(e)));
+    if (std::getenv("GP_LEVEL_CTAS") || int(edit_sms) * 2 > ctx->sm_count) edit_sms = 0; // (experiments with other grids)
+  }
+  ctx->edit_sms = edit_sms;
+  ctx->stats.edit_sms = edit_sms;
+  int shared_ctas = 2; // build CTAs per SM when the edit kernel shares the SMs
+  if (const char* e = std::getenv("GP_EXP_PIPE_CTAS")) shared_ctas = std::max(1, std::atoi(e)); // (experiments)
   uint32_t launches = 0, edit_launches = 0;
   uint32_t* bd = overlap ? ctx->d_batch_done.as<uint32_t>() : nullptr;
   for (size_t wv = 0; wv < ctx->wave_first.size(); wv++) {
     if (!ctx->bf_all_resident) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_bf_pool.p, 0, uint64_t(ctx->wave_count[wv]) * per_bf, s));
-    if (algo == 2) { if (int rc = build_launch_levels_wave(ctx, s, wv, bd, overlap ? 2 : 0)) return rc; }
+    if (algo == 2) { if (int rc = build_launch_levels_wave(ctx, s, wv, bd, overlap && !edit_sms ? shared_ctas : 0, edit_sms)) return rc; }
     else if (int rc = build_launch_inorder_wave(ctx, s, wv)) return rc;
     launches++;
     const uint32_t c0 = ctx->h_wave_contig_off[wv], c1 = ctx->h_wave_contig_off[wv + 1];
     if (c1 > c0) {
       if (wv) GP_CUDA(ctx, cudaMemsetAsync(ctx->d_pnext.p, 0, 4, s));
-      if (int rc = polish_edit(ctx, s, ctx->d_order_pipe.as<uint32_t>() + c0, c1 - c0, bd, overlap)) return rc;
+      if (int rc = polish_edit(ctx, s, ctx->d_order_pipe.as<uint32_t>() + c0, c1 - c0, bd, overlap ? (edit_sms ? 2 : 1) : 0)) return rc;
       edit_launches++;
     }
     if (int rc = wave_payloads_out(ctx, s, wv, algo == 2 && ctx->bf_host_dev)) return rc;

@@ -462,23 +462,57 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   __shared__ unsigned long long cal_ns, cal_steps;      // round-0 work of this CTA's first warp since its last speed publication
   __shared__ unsigned long long red_sh[3][kLevelWarps];
   __shared__ unsigned long long diag[kLevelDiag];       // interval-time diagnostics of this CTA (thread 0)
+  __shared__ uint32_t bid_sh;
   if (p.batch_done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the edit kernel may join us now
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(p.counters + 20, globaltimer_ns()); // (several waves: the first start)
+  // Which CTA am I, of how many?  Normally blockIdx.x of gridDim.x.  With p.reserve_sms (gp_pipeline_run) the launch
+  // fills EVERY SM with p.ctas_per_sm CTAs and then gives the last `reserve_sms` SMs to arrive back: their CTAs leave
+  // at once, and the edit kernel launched behind us -- CTAs that need a whole SM -- lands exactly there.  The two
+  // kernels then share L2 but no SM: an edit warp beside build warps slowed its SM's share of EVERY barrier interval,
+  // i.e. the whole grid.  SM ids are not contiguous (%smid), so the SMs are numbered in order of arrival: the first CTA
+  // on an SM draws the SM's rank, the others wait for it (all CTAs are resident: cooperative launch).
+  uint32_t bid = blockIdx.x, nb = gridDim.x;
+  if (p.reserve_sms) {
+    if (threadIdx.x == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      uint32_t* arrivals = p.sm_table + 1u + 2u * smid;
+      uint32_t* rank_p1 = arrivals + 1;
+      const uint32_t slot = atomicAdd(arrivals, 1u);
+      uint32_t rank;
+      if (slot == 0u) {
+        rank = atomicAdd(p.sm_table, 1u);
+        atomicExch(rank_p1, rank + 1u);
+      } else {
+        while ((rank = *reinterpret_cast<volatile uint32_t*>(rank_p1)) == 0u) { }
+        rank -= 1u;
+      }
+      const uint32_t keep = gridDim.x / p.ctas_per_sm - p.reserve_sms; // SMs that build
+      // the CTAs of one SM are `keep` apart, as blockIdx.x puts them: neighbouring CTAs hold neighbouring pieces of
+      // every time slab (the same reads), and an SM whose three CTAs were neighbours carried three times the
+      // unevenness of survivors into every barrier interval (measured: +7 % on the whole build)
+      bid_sh = rank < keep && slot < p.ctas_per_sm ? slot * keep + rank : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    bid = bid_sh;
+    nb = (gridDim.x / p.ctas_per_sm - p.reserve_sms) * p.ctas_per_sm;
+    if (bid == 0xFFFFFFFFu) return; // (has taken part in nothing)
+  }
+  if (bid == 0 && threadIdx.x == 0) atomicMin(p.counters + 20, globaltimer_ns()); // (several waves: the first start)
   fill_hash_tables(tf, tr);
   LevelCtx c;
   c.tf = tf; c.tr = tr;
   c.lane = threadIdx.x & 31u;
-  c.gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  c.gwarp = (bid * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (nb * blockDim.x) >> 5;
   const uint32_t wib = threadIdx.x >> 5;
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t gtid = bid * blockDim.x + threadIdx.x, gthreads = nb * blockDim.x;
   const uint32_t tb = p.time_bits, vmask = (1u << tb) - 1u, maxtag = (1u << (32u - tb)) - 1u;
   const bool planner = threadIdx.x == 32u; // a thread that neither polls nor arrives: planning stays off the barrier's critical path
   unsigned long long ops = 0, list_seen = 0;
   if (threadIdx.x == 0) { cal_ns = 0; cal_steps = 0; }
   if (threadIdx.x < kLevelDiag) diag[threadIdx.x] = 0;
   if (threadIdx.x <= uint32_t(kLevelWarps)) // equal shares until speeds have been measured
-    cum_sh[0][threadIdx.x] = cum_sh[1][threadIdx.x] = (uint64_t(blockIdx.x * kLevelWarps + threadIdx.x) << 32) / nwarps;
+    cum_sh[0][threadIdx.x] = cum_sh[1][threadIdx.x] = (uint64_t(bid * kLevelWarps + threadIdx.x) << 32) / nwarps;
 
   // ---- scheduling (planner thread only; every CTA computes the same sequence from uniform data) ----
   auto new_tag = [&]() { sch.epoch++; return (maxtag - sch.epoch) << tb; };
@@ -494,7 +528,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       if (sid + 1u < p.n_streams) sch.nx_info = __ldg(p.stream_tab + sid + 1u);
       const uint32_t ki = sid % p.nk, batch = info.z;
       if (info.x == 0) { // nothing to insert: the (zeroed) filter is final
-        if (p.batch_done && blockIdx.x == 0) { atomicAdd(p.batch_done + batch, 1u); atomicAdd(p.batch_done + p.n_batches_total, 1u); }
+        if (p.batch_done && bid == 0) { atomicAdd(p.batch_done + batch, 1u); atomicAdd(p.batch_done + p.n_batches_total, 1u); }
         continue;
       }
       const uint32_t lmax = info.y; // largest thr of the stream (kmer_threshold - 2 + k index, utils.cpp:108,121)
@@ -613,10 +647,15 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
     unsigned long long t_a = 0, t_b = 0;
     if (threadIdx.x == 0) {
       t_a = globaltimer_ns();
-      while (ld_relaxed_u64(p.bars) < target) { }
+      uint32_t polls = 0;
+      while (ld_relaxed_u64(p.bars) < target) {
+        // an interval is microseconds; 10 s at a barrier means CTAs are missing (the launch did not fill the SMs the way
+        // reserve_sms counts on, or somebody died): fail the launch rather than hang the device
+        if ((++polls & 0xFFFFu) == 0u && globaltimer_ns() - t_a > 10000000000ull) asm volatile("trap;");
+      }
       __threadfence();
       t_b = globaltimer_ns();
-      target += gridDim.x;
+      target += nb;
     }
     __syncthreads(); // the previous interval is complete everywhere
     for (uint32_t i = 0; i < P.done_n; i++) filter_final(p, P.done_b[i], P.done_ki[i], P.done_slot[i], gtid, gthreads);
@@ -626,15 +665,15 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       // every CTA published the rate of its round-0 passes (steps per time) a few streams ago: the shares of the stream
       // that begins are proportional to them.  Integer sums, so that every CTA derives the very same boundaries.
       unsigned long long tot = 0;
-      for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot += __ldcg(p.speed + i);
+      for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) tot += __ldcg(p.speed + i);
       tot = block_sum(tot, red_sh[0]);
-      const unsigned long long mean = max(1ull, tot / gridDim.x), lo = max(1ull, mean * 7ull / 10ull), hi = mean * 14ull / 10ull + 1ull;
+      const unsigned long long mean = max(1ull, tot / nb), lo = max(1ull, mean * 7ull / 10ull), hi = mean * 14ull / 10ull + 1ull;
       unsigned long long all = 0, before = 0, mine = 0;
-      for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
         const unsigned long long v = min(max((unsigned long long)__ldcg(p.speed + i), lo), hi);
         all += v;
-        if (i < blockIdx.x) before += v;
-        if (i == blockIdx.x) mine = v;
+        if (i < bid) before += v;
+        if (i == bid) mine = v;
       }
       all = block_sum(all, red_sh[0]); before = block_sum(before, red_sh[1]); mine = block_sum(mine, red_sh[2]);
       if (threadIdx.x <= uint32_t(kLevelWarps))
@@ -706,7 +745,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
     if (threadIdx.x == 0) {
       const unsigned long long t_c = globaltimer_ns();
       if (main_kind == MK_R0 && P.publish && P.last_part && p.weighted) { // this CTA's round-0 rate, for the weighted shares
-        p.speed[blockIdx.x] = uint32_t(min(max(cal_steps * 4000000ull / max(cal_ns, 1ull), 1ull), 262143ull));
+        p.speed[bid] = uint32_t(min(max(cal_steps * 4000000ull / max(cal_ns, 1ull), 1ull), 262143ull));
         cal_ns = 0; cal_steps = 0;
       }
       __threadfence();
@@ -724,10 +763,10 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   for (int o = 16; o > 0; o >>= 1) ops += __shfl_xor_sync(0xffffffffu, ops, o);
   if (c.lane == 0 && ops) atomicAdd(p.counters + 0, ops);
   if (c.lane == 0 && list_seen) atomicAdd(p.counters + 17, list_seen);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(p.counters + 21, globaltimer_ns());
-  if (blockIdx.x == p.report_cta && threadIdx.x == 0)
+  if (bid == 0 && threadIdx.x == 0) atomicMax(p.counters + 21, globaltimer_ns());
+  if (bid == p.report_cta && threadIdx.x == 0)
     for (uint32_t i = 0; i < kLevelDiag; i++) p.counters[kLevelDiagAt + i] += diag[i]; // several waves add up
-  if (p.cta_times && threadIdx.x < kLevelDiag) p.cta_times[blockIdx.x * 32u + threadIdx.x] = diag[threadIdx.x];
+  if (p.cta_times && threadIdx.x < kLevelDiag) p.cta_times[bid * 32u + threadIdx.x] = diag[threadIdx.x];
 }
 
 // ---- known-answer support: the hashes exactly as the build kernels compute them ----
@@ -767,7 +806,7 @@ void launch_debug_nthash(const uint64_t* pk, const uint32_t* nm, uint64_t wbase,
   debug_nthash_kernel<<<8, kLevelWarps * 32, 0, s>>>(pk, nm, wbase, len, k, h, valid);
 }
 
-int levels_max_grid(int sm_count, int ctas_per_sm)
+int levels_ctas_per_sm(int ctas_per_sm)
 {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, build_filters_levels_kernel, kLevelWarps * 32, 0);
@@ -775,8 +814,10 @@ int levels_max_grid(int sm_count, int ctas_per_sm)
   if (per_sm > 4) per_sm = 4;
   if (ctas_per_sm > 0) per_sm = std::min(per_sm, ctas_per_sm);
   if (const char* e = std::getenv("GP_LEVEL_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e))); // experiments
-  return sm_count * per_sm;
+  return per_sm;
 }
+
+int levels_max_grid(int sm_count, int ctas_per_sm) { return sm_count * levels_ctas_per_sm(ctas_per_sm); }
 
 void preload_levels()
 {

@@ -23,6 +23,8 @@
 #include "gp_common.cuh"
 #include "gp_kernels.cuh"
 
+#include <cstdlib>
+
 namespace gp {
 
 constexpr int kEditWarps = 4;
@@ -51,6 +53,7 @@ struct WS {
   // the stream around the window: vb[i & 255] = character with absolute stream index i;
   // [hp, hp+k) is the window, [hp+k, ve) the characters ahead of the tail cursor
   unsigned char* vb;
+  unsigned char* kmer;       // 32 bytes: the window a re-seed starts from (make_edit)
   // candidate-search tables (shared memory): per-round seed tables and per-call staging
   const unsigned char* code; // byte -> 0 none, 1 A, 2 C, 3 G, 4 T (either case)
   uint64_t* seedt;           // [0..4] F, [8..12] F rotated by k, [16..23] R (by c & 7), [24..31] R rotated by k
@@ -787,8 +790,7 @@ __device__ __forceinline__ void make_edit(WS& w, uint32_t draft_char, const Best
   }
   uint32_t new_last = 0;   // character now sitting at the tail of the window
   bool stream_changed = false, reseeded = false, found = false;
-  __shared__ unsigned char kmer_sh[kEditWarps][32];
-  unsigned char* kmer = kmer_sh[(threadIdx.x >> 5)];
+  unsigned char* kmer = w.kmer;
   if (w.lane == 0) {
     Rope r = { w.nd, w.nn, w.ncap, w.seq, w.len, 0 };
     uint32_t t_idx = w.t.idx, t_seq = w.t.pos, h_idx = w.h.idx, h_seq = w.h.pos;
@@ -1150,14 +1152,15 @@ __device__ __forceinline__ uint32_t emit_rope(const WS& w, char* dst, uint32_t c
   return o;
 }
 
-__global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
+// Shared memory of one edit warp (dynamic: a CTA is kEditWarps warps, or kEditSmWarps when it owns its SM)
+constexpr uint32_t kWarpSmemWords = 2u * (kInsZeroRow + 32u) + 2u * 5u * 32u + 192u + 32u;  // ins F/R, common chains, stage, seeds
+constexpr uint32_t kWarpSmemBytes = kWarpSmemWords * 8u + kVBuf + 32u;                       // + stream ring + re-seed window
+constexpr int kEditSmWarps = 12; // 12 x 32 x 168 registers: the whole register file of an SM
+
+__global__ void __launch_bounds__(kEditSmWarps * 32, 1) edit_kernel(EditParams p)
 {
-  __shared__ unsigned char vb_sh[kEditWarps][kVBuf];
+  extern __shared__ __align__(16) uint64_t edit_dyn[];
   __shared__ unsigned char code_sh[256];
-  __shared__ uint64_t seedt_sh[kEditWarps][32];
-  __shared__ uint64_t stage_sh[kEditWarps][192];
-  __shared__ uint64_t com_sh[kEditWarps][2 * 5 * 32];
-  __shared__ uint64_t ins_sh[kEditWarps][2][kInsZeroRow + 32];
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
     const uint32_t lc = i | 0x20u;
     code_sh[i] = lc == 'a' ? 1 : lc == 'c' ? 2 : lc == 'g' ? 3 : lc == 't' ? 4 : 0;
@@ -1209,13 +1212,17 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
     bool dropped = false;
     WS w;
     w.lane = lane;
-    w.vb = vb_sh[warp];
+    {
+      uint64_t* base = edit_dyn + size_t(warp) * (kWarpSmemBytes / 8u);
+      w.insF = base;
+      w.insR = base + (kInsZeroRow + 32u);
+      w.com = base + 2u * (kInsZeroRow + 32u);
+      w.stage = w.com + 2u * 5u * 32u;
+      w.seedt = w.stage + 192u;
+      w.vb = reinterpret_cast<unsigned char*>(w.seedt + 32u);
+      w.kmer = w.vb + kVBuf;
+    }
     w.code = code_sh;
-    w.seedt = seedt_sh[warp];
-    w.stage = stage_sh[warp];
-    w.com = com_sh[warp];
-    w.insF = ins_sh[warp][0];
-    w.insR = ins_sh[warp][1];
     w.nd = p.nodes + p.node_off[ci];
     w.ncap = uint32_t(p.node_off[ci + 1] - p.node_off[ci]);
     w.max_ins = p.max_insertions; w.max_del = p.max_deletions; w.jump = p.jump;
@@ -1263,8 +1270,12 @@ __global__ void __launch_bounds__(kEditWarps * 32, 3) edit_kernel(EditParams p)
 
 // alongside_build (gp_pipeline_run): launched right behind the level-synchronous build kernel in the same
 // stream with programmatic stream serialization -- it starts once every build CTA has signalled
-// launch_dependents, i.e. when the build is resident, and fills what that leaves free: one 3-warp CTA per SM
-// (per scheduler: 2 build CTAs x 2 warps x 80 registers + one edit warp x 168 registers <= 16384).
+// launch_dependents, i.e. when the build is resident.  Two shapes:
+//   alongside_build = 1  one 3-warp CTA per SM beside 2 build CTAs (per scheduler: 2 x 2 build warps x 80 registers +
+//                        one edit warp x 168 registers <= 16384): the two kernels share every SM;
+//   alongside_build = 2  CTAs of kEditSmWarps warps, each the whole register file of an SM: they only fit on SMs that
+//                        the build kernel has given back (LevelParams::reserve_sms) -- and, one per SM, everywhere
+//                        once the build kernel is through, which is what takes the tail.
 constexpr int kAlongsideWarps = 3;
 
 // load the kernel now (lazy module loading would otherwise do it at the first launch -- and that launch would wait for
@@ -1273,21 +1284,27 @@ void preload_edit()
 {
   cudaFuncAttributes a;
   if (cudaFuncGetAttributes(&a, (const void*)edit_kernel) != cudaSuccess) cudaGetLastError();
+  cudaFuncSetAttribute((const void*)edit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEditSmWarps * int(kWarpSmemBytes));
 }
 
-cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool alongside_build)
+cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, int alongside_build)
 {
   if (p.n_contigs == 0) return cudaSuccess;
-  // same shared-memory carve-out as the build kernel (132 KB), so that the two can share an SM (per device)
-  cudaFuncSetAttribute((const void*)edit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
+  if (alongside_build && std::getenv("GP_EXP_NO_EDIT")) return cudaSuccess; // (experiment: what the build costs in this mode by itself)
+  // (function attributes are per device: set on every launch, a cheap host-side call)
+  cudaFuncSetAttribute((const void*)edit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEditSmWarps * int(kWarpSmemBytes));
+  // same shared-memory carve-out as the build kernel (132 KB), so that the two can share an SM; a CTA that owns its
+  // SM asks for what it needs
+  cudaFuncSetAttribute((const void*)edit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, alongside_build == 2 ? 72 : 58);
   if (alongside_build) {
+    const uint32_t warps = alongside_build == 2 ? uint32_t(kEditSmWarps) : uint32_t(kAlongsideWarps);
     uint32_t grid = uint32_t(sm_count);
-    const uint32_t need = (p.n_contigs + kAlongsideWarps - 1) / kAlongsideWarps;
+    const uint32_t need = (p.n_contigs + warps - 1) / warps;
     if (grid > need) grid = need;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kAlongsideWarps * 32);
-    cfg.dynamicSmemBytes = 0;
+    cfg.blockDim = dim3(warps * 32);
+    cfg.dynamicSmemBytes = warps * kWarpSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1296,16 +1313,16 @@ cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool 
     cfg.numAttrs = 1;
     if (cudaLaunchKernelEx(&cfg, edit_kernel, p) == cudaSuccess) return cudaSuccess;
     cudaGetLastError(); // no programmatic launch on this driver: an ordinary launch runs after the build (correct, no overlap)
-    edit_kernel<<<grid, kAlongsideWarps * 32, 0, s>>>(p);
+    edit_kernel<<<grid, warps * 32, warps * kWarpSmemBytes, s>>>(p);
     return cudaGetLastError();
   }
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edit_kernel, kEditWarps * 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edit_kernel, kEditWarps * 32, kEditWarps * kWarpSmemBytes);
   if (per_sm < 1) per_sm = 1;
   uint32_t grid = uint32_t(sm_count) * uint32_t(per_sm);
   const uint32_t need = (p.n_contigs + kEditWarps - 1) / kEditWarps;
   if (grid > need) grid = need;
-  edit_kernel<<<grid, kEditWarps * 32, 0, s>>>(p);
+  edit_kernel<<<grid, kEditWarps * 32, kEditWarps * kWarpSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -51,6 +51,9 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   unsigned long long* bars;       // barrier arrival counter (zeroed before a launch)
   uint32_t* speed;                // per CTA: published round-0 rate (weighted shares)
   uint32_t weighted;              // 1: shares follow the measured speed of each CTA's SM
+  uint32_t reserve_sms;           // > 0 (gp_pipeline_run): SMs whose CTAs leave at once, for the edit kernel's whole-SM CTAs
+  uint32_t ctas_per_sm;           // CTAs that the launch put on every SM (needed with reserve_sms)
+  uint32_t* sm_table;             // with reserve_sms: [0] SMs seen, [1 + 2 smid] arrivals, [2 + 2 smid] rank + 1; zeroed before a launch
   uint32_t overlap;               // 1: a stream's late list rounds run beside round 0 / the level-1 round of the next stream
   uint32_t arrays;                // timestamp arrays in use: 3 (T_1 has its own: every late round can be joined), or 2 (only the last)
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
@@ -116,6 +119,7 @@ void launch_pack_reads(const char* ascii, const uint64_t* ascii_off, const uint6
                        uint32_t* nm, uint32_t n_reads, cudaStream_t s);
 void launch_build_filters(const BuildParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cudaStream_t s, int ctas_per_sm = 0);
+int levels_ctas_per_sm(int ctas_per_sm); // CTAs the launch puts on every SM
 void preload_levels();
 void launch_debug_nthash(const uint64_t* pk, const uint32_t* nm, uint64_t wbase, uint32_t len, uint32_t k, uint64_t* h,
                          uint8_t* valid, cudaStream_t s);
@@ -125,6 +129,6 @@ void launch_fill_anchor(const uint32_t* step_pre, const uint16_t* entry_rel, uin
                         uint32_t nk, uint64_t anchor_stride, cudaStream_t s);
 void launch_roof(uint8_t* cbf_pool, uint32_t* bf_pool, uint64_t region, uint32_t iters, uint32_t warps, cudaStream_t s);
 cudaError_t launch_prep(const PrepParams& p, int sm_count, cudaStream_t s);
-cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, bool alongside_build = false);
+cudaError_t launch_edit(const EditParams& p, int sm_count, cudaStream_t s, int alongside_build = 0); // 1: sharing SMs with the build kernel, 2: on SMs of its own
 
 } // namespace gp

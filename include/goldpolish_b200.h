@@ -110,6 +110,8 @@ typedef struct {
   uint32_t build_slots;     /* level-synchronous kernel: streams in flight */
   uint32_t polish_reruns;   /* times gp_polish_fetch had to run the polish again since the context was created
                                (a contig outgrew its buffers, or the overlapped edit kernel's watchdog fired) */
+  uint32_t edit_sms;        /* last gp_pipeline_run: SMs the edit kernel had to itself beside the build kernel
+                               (0: the two kernels shared every SM, or nothing was overlapped) */
 } gp_stats;
 
 void gp_default_config(gp_config* cfg);

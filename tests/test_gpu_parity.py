@@ -126,6 +126,38 @@ def test_pipeline_matches_separate_calls(gp, bsize):
             assert st["build_kernel"] == 2 and st["edits"] > 0
 
 
+@pytest.mark.parametrize("edit_sms", ["0", "1", "5", "40"])
+def test_pipeline_sm_sharing_schemes_agree(gp, edit_sms, monkeypatch):
+    """The overlapped pass with the edit kernel on SMs of its own (the build launch hands GP_EDIT_SMS SMs back and
+    renumbers its CTAs; whole-SM edit CTAs land there) and with the two kernels sharing every SM (GP_EDIT_SMS=0): the
+    same filters and records as the separate calls, through a bounded filter pool (several waves) as well."""
+    d = dataset(genome_len=150000)
+    pl = plan(d, bsize=2)
+    with gp.Context() as ctx:
+        ctx.upload_reads(d.read_seq, d.read_off)
+        bfs = ctx.build_filters(pl.batch_entry_off, pl.entries)
+        out, off, dropped = ctx.polish(d.contig_seq, d.contig_off, pl.contig_batch)
+        out = out[:int(off[-1])].copy()
+    monkeypatch.setenv("GP_EDIT_SMS", edit_sms)
+    for resident in (0, 3):
+        with gp.Context(max_resident_filters=resident) as ctx:
+            import torch
+            ctx.upload_reads(d.read_seq, d.read_off)
+            pinned = torch.zeros(bfs.shape, dtype=torch.uint8).pin_memory()
+            ctx.build_output(pinned)
+            ctx.build_stage(pl.batch_entry_off, pl.entries)
+            ctx.polish_stage(d.contig_seq, d.contig_off, pl.contig_batch)
+            ctx.pipeline_run()
+            ctx.build_fetch(out=pinned)
+            out2, off2, dropped2 = ctx.polish_fetch()
+            st = ctx.stats()
+            assert st["edit_sms"] == int(edit_sms) and st["polish_reruns"] == 0
+            assert np.array_equal(pinned.numpy(), bfs), (edit_sms, resident)
+            assert np.array_equal(off, off2) and np.array_equal(dropped, dropped2)
+            assert np.array_equal(out, out2[:int(off2[-1])])
+            ctx.build_output(None)
+
+
 @pytest.mark.parametrize("pipeline", [False, True])
 def test_filters_streamed_to_pinned_host_memory(gp, pipeline):
     """gp_build_output_host: the build kernel writes every final filter into page-locked host memory itself;
