@@ -79,6 +79,8 @@ struct gp_ctx {
   // level-synchronous build
   DevBuf d_step_pre, d_batch_max_thr, d_V, d_alive, d_anchor, d_entry_rel, d_cta_times, d_sm_table;
   uint32_t edit_sms = 0;   // SMs that the last overlapped pass gave to the edit kernel (0: the two kernels shared every SM)
+  uint32_t edit_ctas_per_sm = 0; // build CTAs per SM of that pass
+  int sm_split_state = 0;  // 0 unchecked, 1 the build launch vacates whole SMs on this device (checked), -1 it does not
   uint32_t level_grid = 0; // CTAs of the last level-synchronous launch
   uint64_t anchor_stride = 0;
   uint32_t alive_words = 0, n_entries = 0, surv_cap = 0, level_slots = 1, level_time_bits = 26, level_arrays = 2;
@@ -257,6 +259,26 @@ int gp_ctx_synchronize(gp_ctx* ctx)
   return GP_OK;
 }
 
+// After an overlapped pass that kept SMs back for the edit kernel: did the build CTAs that left really come in whole
+// SMs (the kernel counts them per %smid)?  Returns the number of SMs vacated; remembers a mismatch, after which
+// gp_pipeline_run lets the two kernels share every SM again.  The stream must be idle.
+static uint32_t sm_split_check(gp_ctx* ctx)
+{
+  if (!ctx->edit_sms || !ctx->d_sm_table.p) return 0;
+  std::vector<uint32_t> t(1 + 2 * 2048);
+  if (cudaMemcpy(t.data(), ctx->d_sm_table.p, t.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 0; }
+  uint32_t full = 0, other = 0, given_back = 0;
+  const uint32_t keep = uint32_t(ctx->sm_count) - ctx->edit_sms;
+  for (size_t i = 0; i < 2048; i++) {
+    const uint32_t arrived = t[1 + 2 * i], rank_p1 = t[2 + 2 * i];
+    if (arrived == ctx->edit_ctas_per_sm) { full++; if (rank_p1 > keep) given_back++; }
+    else if (arrived) other++;
+  }
+  const bool ok = !other && full == uint32_t(ctx->sm_count) && given_back == ctx->edit_sms;
+  if (ctx->sm_split_state == 0 || !ok) ctx->sm_split_state = ok ? 1 : -1;
+  return ok ? given_back : 0;
+}
+
 int gp_get_stats(const gp_ctx* cctx, gp_stats* out)
 {
   if (!cctx || !out) return GP_ERR_ARG;
@@ -276,6 +298,7 @@ int gp_get_stats(const gp_ctx* cctx, gp_stats* out)
     ctx->stats.edit_kernel_ms = float(double(pc[5] - pc[4]) * 1e-6);
     ctx->stats.polish_ms = ctx->stats.edit_kernel_ms;
     ctx->stats.triggers = pc[0]; ctx->stats.edits = pc[1]; ctx->stats.masked = pc[2]; ctx->stats.rollbacks = pc[3];
+    ctx->stats.edit_sms = sm_split_check(ctx); // SMs that were really vacated
     *out = ctx->stats;
     return GP_OK;
   }
@@ -704,15 +727,14 @@ static int build_launch_levels_wave(gp_ctx* ctx, cudaStream_t s, size_t wv, uint
       GP_CUDA(ctx, cudaMemsetAsync(ctx->d_cta_times.p, 0, size_t(ctx->sm_count) * 4 * 32 * 8, s));
       p.cta_times = ctx->d_cta_times.as<unsigned long long>();
     }
-    if (reserve_sms) { // the launch fills every SM; the kernel hands `reserve_sms` of them back (see there)
-      const size_t bytes = (1 + 2 * 4096) * 4; // (%nsmid is far below 4096)
+    if (reserve_sms) { // the launch fills every SM; the CTAs of the last `reserve_sms` SMs leave at once (see the kernel)
+      const size_t bytes = (1 + 2 * 2048) * 4; // (%nsmid is far below 2048)
       GP_CUDA(ctx, ctx->d_sm_table.ensure(bytes));
       GP_CUDA(ctx, cudaMemsetAsync(ctx->d_sm_table.p, 0, bytes, s));
-      p.reserve_sms = reserve_sms;
-      p.ctas_per_sm = uint32_t(gp::levels_ctas_per_sm(ctas_per_sm));
+      p.keep_sms = uint32_t(ctx->sm_count) - reserve_sms;
       p.sm_table = ctx->d_sm_table.as<uint32_t>();
     }
-    ctx->level_grid = uint32_t(gp::levels_max_grid(ctx->sm_count, ctas_per_sm));
+    ctx->level_grid = uint32_t((ctx->sm_count - int(reserve_sms)) * gp::levels_ctas_per_sm(ctas_per_sm));
     GP_CUDA(ctx, gp::launch_build_filters_levels(p, ctx->sm_count, s, ctas_per_sm));
     if (!batch_done) GP_CUDA(ctx, cudaEventRecord(ctx->wave_ev[2 * wv + 1], s));
   }
@@ -1193,6 +1215,7 @@ int gp_pipeline_run(gp_ctx* ctx)
     GP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->d_error.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->overlap_state == 0) ctx->overlap_state = err == 2 ? -1 : 1; // 2 = its watchdog fired: this device does not co-schedule the kernels
+    if (ctx->sm_split_state == 0) sm_split_check(ctx);
   }
   const int algo = ctx->build_algo_resolved;
   const bool overlap = algo == 2 && n && nb && !c.keep_counters && ctx->overlap_state >= 0 && !std::getenv("GP_NO_OVERLAP");
@@ -1267,8 +1290,10 @@ int gp_pipeline_run(gp_ctx* ctx)
     edit_sms = std::min(std::max(edit_sms, 2u), 24u);
     if (const char* e = std::getenv("GP_EDIT_SMS")) edit_sms = uint32_t(std::max(0, std::atoi(e)));
     if (std::getenv("GP_LEVEL_CTAS") || int(edit_sms) * 2 > ctx->sm_count) edit_sms = 0; // (experiments with other grids)
+    if (ctx->sm_split_state < 0) edit_sms = 0; // this device does not deal CTAs to SMs the way the split counts on
   }
   ctx->edit_sms = edit_sms;
+  ctx->edit_ctas_per_sm = uint32_t(gp::levels_ctas_per_sm(0));
   ctx->stats.edit_sms = edit_sms;
   int shared_ctas = 2; // build CTAs per SM when the edit kernel shares the SMs
   if (const char* e = std::getenv("GP_EXP_PIPE_CTAS")) shared_ctas = std::max(1, std::atoi(e)); // (experiments)

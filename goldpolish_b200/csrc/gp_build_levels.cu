@@ -462,22 +462,29 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   __shared__ unsigned long long cal_ns, cal_steps;      // round-0 work of this CTA's first warp since its last speed publication
   __shared__ unsigned long long red_sh[3][kLevelWarps];
   __shared__ unsigned long long diag[kLevelDiag];       // interval-time diagnostics of this CTA (thread 0)
-  __shared__ uint32_t bid_sh;
+  __shared__ uint32_t dense_sh; // this CTA's number among those that build
   if (p.batch_done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the edit kernel may join us now
-  // Which CTA am I, of how many?  Normally blockIdx.x of gridDim.x.  With p.reserve_sms (gp_pipeline_run) the launch
-  // fills EVERY SM with p.ctas_per_sm CTAs and then gives the last `reserve_sms` SMs to arrive back: their CTAs leave
-  // at once, and the edit kernel launched behind us -- CTAs that need a whole SM -- lands exactly there.  The two
-  // kernels then share L2 but no SM: an edit warp beside build warps slowed its SM's share of EVERY barrier interval,
-  // i.e. the whole grid.  SM ids are not contiguous (%smid), so the SMs are numbered in order of arrival: the first CTA
-  // on an SM draws the SM's rank, the others wait for it (all CTAs are resident: cooperative launch).
-  uint32_t bid = blockIdx.x, nb = gridDim.x;
-  if (p.reserve_sms) {
-    if (threadIdx.x == 0) {
+  // Which CTA am I, of how many?  Normally blockIdx.x of gridDim.x.  gp_pipeline_run keeps a few SMs back for the edit
+  // kernel (p.keep_sms < p.sms): the launch fills EVERY SM with gridDim.x / p.sms CTAs, the CTAs of the last SMs to
+  // arrive leave at once, and the edit kernel launched behind us -- CTAs that need a whole SM -- lands exactly there.
+  // The two kernels then share L2 but no SM; an edit warp beside build warps slowed its SM's share of EVERY barrier
+  // interval, i.e. the whole grid.  Which CTAs share an SM is the hardware's business (blockIdx.x % SMs it is not:
+  // tried), and %smid is not contiguous, so the SMs are numbered in order of arrival: the first CTA on an SM draws the
+  // SM's rank, the others wait for it (all CTAs are resident: cooperative launch).  The CTAs that stay are numbered
+  // densely, round * keep_sms + rank: the CTAs of one SM stay far apart, as in a plain launch -- neighbouring CTAs hold
+  // neighbouring pieces of every time slab (the same reads), and an SM whose three CTAs were neighbours carried three
+  // times the unevenness of survivors into every interval (measured: +7 %).  The dense number lives in shared memory
+  // and is read where it is needed (once per interval: the warp's list region), so that it costs no
+  // register across the hot loops.
+  if (threadIdx.x == 0) {
+    uint32_t dense = blockIdx.x;
+    if (p.keep_sms < p.sms) {
+      const uint32_t per_sm = gridDim.x / p.sms;
       uint32_t smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      uint32_t* arrivals = p.sm_table + 1u + 2u * smid;
+      uint32_t* arrivals = p.sm_table + 1u + 2u * (smid & 2047u);
       uint32_t* rank_p1 = arrivals + 1;
-      const uint32_t slot = atomicAdd(arrivals, 1u);
+      const uint32_t slot = atomicAdd(arrivals, 1u); // (the host checks afterwards that every SM counted per_sm)
       uint32_t rank;
       if (slot == 0u) {
         rank = atomicAdd(p.sm_table, 1u);
@@ -486,26 +493,25 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         while ((rank = *reinterpret_cast<volatile uint32_t*>(rank_p1)) == 0u) { }
         rank -= 1u;
       }
-      const uint32_t keep = gridDim.x / p.ctas_per_sm - p.reserve_sms; // SMs that build
-      // the CTAs of one SM are `keep` apart, as blockIdx.x puts them: neighbouring CTAs hold neighbouring pieces of
-      // every time slab (the same reads), and an SM whose three CTAs were neighbours carried three times the
-      // unevenness of survivors into every barrier interval (measured: +7 % on the whole build)
-      bid_sh = rank < keep && slot < p.ctas_per_sm ? slot * keep + rank : 0xFFFFFFFFu;
+      dense = rank < p.keep_sms && slot < per_sm ? slot * p.keep_sms + rank : 0xFFFFFFFFu;
     }
-    __syncthreads();
-    bid = bid_sh;
-    nb = (gridDim.x / p.ctas_per_sm - p.reserve_sms) * p.ctas_per_sm;
-    if (bid == 0xFFFFFFFFu) return; // (has taken part in nothing)
+    dense_sh = dense;
   }
+  __syncthreads();
+  if (dense_sh == 0xFFFFFFFFu) return; // an SM given back: this CTA has taken part in nothing
+#define nb (p.n_ctas)
+#define bid dense_sh
+#define gtid (dense_sh * blockDim.x + threadIdx.x)
+#define gthreads (nb * blockDim.x)
+  LevelCtx c;
+  c.lane = threadIdx.x & 31u;
+  c.gwarp = 0; // (not used by this kernel: the warp's number among those that build is gwarp_now)
   if (bid == 0 && threadIdx.x == 0) atomicMin(p.counters + 20, globaltimer_ns()); // (several waves: the first start)
   fill_hash_tables(tf, tr);
-  LevelCtx c;
   c.tf = tf; c.tr = tr;
-  c.lane = threadIdx.x & 31u;
-  c.gwarp = (bid * blockDim.x + threadIdx.x) >> 5;
+#define gwarp_now (dense_sh * uint32_t(kLevelWarps) + wib)
   const uint32_t nwarps = (nb * blockDim.x) >> 5;
   const uint32_t wib = threadIdx.x >> 5;
-  const uint32_t gtid = bid * blockDim.x + threadIdx.x, gthreads = nb * blockDim.x;
   const uint32_t tb = p.time_bits, vmask = (1u << tb) - 1u, maxtag = (1u << (32u - tb)) - 1u;
   const bool planner = threadIdx.x == 32u; // a thread that neither polls nor arrives: planning stays off the barrier's critical path
   unsigned long long ops = 0, list_seen = 0;
@@ -640,18 +646,17 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
     uint32_t pre_for = 0; // 1: tail list prefetched, 2: head list prefetched
     if (!P.finished && (tail_first || main_kind == MK_R1)) {
       const StreamSt* S = tail_first ? &P.tail : &P.cur;
-      const SurvList l = list_of(p, S->buf, S->n_steps, cum_sh[S->cum] + wib, c.gwarp);
+      const SurvList l = list_of(p, S->buf, S->n_steps, cum_sh[S->cum] + wib, gwarp_now);
       fetch_entries<2>(l, warp_cnt[S->buf][wib], 0, c.lane, nx_lo, nx_hi, nx_meta);
       pre_for = tail_first ? 1u : 2u;
     }
     unsigned long long t_a = 0, t_b = 0;
     if (threadIdx.x == 0) {
       t_a = globaltimer_ns();
-      uint32_t polls = 0;
       while (ld_relaxed_u64(p.bars) < target) {
         // an interval is microseconds; 10 s at a barrier means CTAs are missing (the launch did not fill the SMs the way
         // reserve_sms counts on, or somebody died): fail the launch rather than hang the device
-        if ((++polls & 0xFFFFu) == 0u && globaltimer_ns() - t_a > 10000000000ull) asm volatile("trap;");
+        if (globaltimer_ns() - t_a > 10000000000ull) asm volatile("trap;");
       }
       __threadfence();
       t_b = globaltimer_ns();
@@ -665,7 +670,9 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       // every CTA published the rate of its round-0 passes (steps per time) a few streams ago: the shares of the stream
       // that begins are proportional to them.  Integer sums, so that every CTA derives the very same boundaries.
       unsigned long long tot = 0;
-      for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) tot += __ldcg(p.speed + i);
+      // (up to gridDim.x >= nb: the entries beyond nb are zero.  Written with nb, ptxas (12.9) finds a worse register
+      // allocation for the whole kernel -- 30 more bytes of spills in the hot loops, -4 % k-mer ops/s)
+      for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot += __ldcg(p.speed + i);
       tot = block_sum(tot, red_sh[0]);
       const unsigned long long mean = max(1ull, tot / nb), lo = max(1ull, mean * 7ull / 10ull), hi = mean * 14ull / 10ull + 1ull;
       unsigned long long all = 0, before = 0, mine = 0;
@@ -696,7 +703,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
         const uint64_t* cum = cum_sh[P.cur.cum] + wib;
         const StreamConsts sc = stream_consts(p.k[ki]);
         uint32_t* __restrict__ bf = p.bf_pool + (uint64_t(P.cur.slot) * p.nk + ki) * kBfWords;
-        const SurvList lst = list_of(p, cb, n_steps, cum, c.gwarp);
+        const SurvList lst = list_of(p, cb, n_steps, cum, gwarp_now);
         uint32_t cnt = P.part ? warp_cnt[cb][wib] : 0u;
         const uint32_t tag = P.cur.tag;
         uint32_t* __restrict__ VC = t1_array(P.cur);
@@ -726,7 +733,7 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
       const StreamConsts sc = stream_consts(p.k[S->ki]);
       ListJob J;
       J.L = S->L; J.lread = S->lread; J.tag = S->tag; J.tag_next = S->tag_next; J.vmask = vmask;
-      J.lst = list_of(p, sbuf, S->n_steps, cum_sh[S->cum] + wib, c.gwarp);
+      J.lst = list_of(p, sbuf, S->n_steps, cum_sh[S->cum] + wib, gwarp_now);
       J.V = J.L == 1u ? t1_array(*S) : p.V + ((J.L + S->pb) & 1u) * kCbfCounters;
       J.Vn = p.V + ((J.L + 1u + S->pb) & 1u) * kCbfCounters;
       J.bf = p.bf_pool + (uint64_t(S->slot) * p.nk + S->ki) * kBfWords;
@@ -767,6 +774,11 @@ __global__ void __launch_bounds__(kLevelWarps * 32, 3) build_filters_levels_kern
   if (bid == p.report_cta && threadIdx.x == 0)
     for (uint32_t i = 0; i < kLevelDiag; i++) p.counters[kLevelDiagAt + i] += diag[i]; // several waves add up
   if (p.cta_times && threadIdx.x < kLevelDiag) p.cta_times[bid * 32u + threadIdx.x] = diag[threadIdx.x];
+#undef bid
+#undef nb
+#undef gtid
+#undef gthreads
+#undef gwarp_now
 }
 
 // ---- known-answer support: the hashes exactly as the build kernels compute them ----
@@ -833,9 +845,12 @@ cudaError_t launch_build_filters_levels(const LevelParams& p, int sm_count, cuda
   // share an SM.  Function attributes are per device: set on every launch (a cheap host-side call).
   cudaFuncSetAttribute((const void*)build_filters_levels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
   LevelParams lp = p;
+  lp.sms = uint32_t(sm_count);
+  if (lp.keep_sms == 0 || lp.keep_sms > lp.sms || !lp.sm_table) lp.keep_sms = lp.sms; // every SM builds
+  lp.n_ctas = lp.keep_sms * uint32_t(levels_ctas_per_sm(ctas_per_sm));
   void* args[] = { &lp };
   // cooperative launch: the barriers need every CTA resident
-  return cudaLaunchCooperativeKernel((const void*)build_filters_levels_kernel, dim3(levels_max_grid(sm_count, ctas_per_sm)),
+  return cudaLaunchCooperativeKernel((const void*)build_filters_levels_kernel, dim3(sm_count * levels_ctas_per_sm(ctas_per_sm)),
                                      dim3(kLevelWarps * 32), args, 0, s);
 }
 

@@ -51,9 +51,10 @@ struct LevelParams {              // level-synchronous filter build (gp_build_le
   unsigned long long* bars;       // barrier arrival counter (zeroed before a launch)
   uint32_t* speed;                // per CTA: published round-0 rate (weighted shares)
   uint32_t weighted;              // 1: shares follow the measured speed of each CTA's SM
-  uint32_t reserve_sms;           // > 0 (gp_pipeline_run): SMs whose CTAs leave at once, for the edit kernel's whole-SM CTAs
-  uint32_t ctas_per_sm;           // CTAs that the launch put on every SM (needed with reserve_sms)
-  uint32_t* sm_table;             // with reserve_sms: [0] SMs seen, [1 + 2 smid] arrivals, [2 + 2 smid] rank + 1; zeroed before a launch
+  uint32_t sms;                   // SMs of the device (set by the launch)
+  uint32_t n_ctas;                // CTAs that build: keep_sms x CTAs per SM (set by the launch)
+  uint32_t keep_sms;              // SMs that build: gridDim.x, or fewer (gp_pipeline_run: the others are the edit kernel's)
+  uint32_t* sm_table;             // with keep_sms < sms: [0] SMs seen, [1 + 2 smid] CTAs arrived, [2 + 2 smid] rank + 1; zeroed before a launch
   uint32_t overlap;               // 1: a stream's late list rounds run beside round 0 / the level-1 round of the next stream
   uint32_t arrays;                // timestamp arrays in use: 3 (T_1 has its own: every late round can be joined), or 2 (only the last)
   uint8_t* cbf_pool;              // optional counter bytes (parity / debugging), stream s at s * kCbfCounters
