@@ -357,6 +357,40 @@ public:
     }
   }
 
+  // The sequences of ids[first .. first + n) back to back in `out` (the slab the server hands to gp_reads_append), read
+  // by `threads` workers: the offsets follow from the index, every worker preads its share of the reads into place.
+  void read_many(const std::vector<const std::string*>& ids, size_t first, size_t n, std::string& out, unsigned threads = 0) const
+  {
+    std::vector<const SeqRecord*> recs(n);
+    std::vector<size_t> off(n + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+      recs[i] = &at(*ids[first + i]);
+      if (recs[i]->len >= 20ull * 1024ull * 1024ull) die("Seq size over buffer size."); // :88-90
+      off[i + 1] = off[i] + recs[i]->len;
+    }
+    out.resize(off[n]);
+    if (fd < 0) {
+      fd = open(seqs_path.c_str(), O_RDONLY);
+      if (fd < 0) die("cannot open " + seqs_path);
+    }
+    const size_t T = std::max<size_t>(1, std::min<size_t>(host_threads(threads), off[n] / (4u << 20) + 1));
+    auto work = [&](size_t t) { // reads whose first byte falls into the t-th part of the slab
+      const size_t lo = off[n] / T * t, hi = t + 1 == T ? off[n] + 1 : off[n] / T * (t + 1);
+      for (size_t i = size_t(std::lower_bound(off.begin(), off.begin() + n, lo) - off.begin()); i < n && off[i] < hi; i++) {
+        size_t got = 0;
+        while (got < recs[i]->len) {
+          const ssize_t r = pread(fd, &out[off[i] + got], recs[i]->len - got, off_t(recs[i]->start + got));
+          if (r <= 0) die("read did not read all bytes.");
+          got += size_t(r);
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+  }
+
   std::string seqs_path;
   std::vector<std::string> order; // insertion order (save() of the reference iterates a hash map)
 

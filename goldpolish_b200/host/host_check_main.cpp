@@ -9,10 +9,46 @@
 
 using namespace gph;
 
+// gp-host-check reads <seqs> <seqs.index> <ids file> <slab bytes> [threads]: the sequences named in the ids file, one per
+// line, fetched slab by slab the way the server feeds the device (SeqIndex::read_many)
+static int reads_mode(int argc, char** argv)
+{
+  if (argc < 6) return 2;
+  const SeqIndex ix = SeqIndex::load(argv[3], argv[2]);
+  std::vector<std::string> ids;
+  {
+    std::ifstream f(argv[4]);
+    std::string id;
+    while (bool(f >> id)) ids.push_back(id);
+  }
+  std::vector<const std::string*> order;
+  for (const auto& id : ids) order.push_back(&id);
+  const uint64_t slab_bytes = std::stoull(argv[5]);
+  const unsigned threads = argc > 6 ? unsigned(std::atoi(argv[6])) : 0;
+  std::string slab;
+  for (size_t first = 0; first < order.size();) {
+    size_t n = 0;
+    uint64_t bytes = 0;
+    while (first + n < order.size() && (n == 0 || bytes + ix.at(*order[first + n]).len <= slab_bytes)) bytes += ix.at(*order[first + n++]).len;
+    ix.read_many(order, first, n, slab, threads);
+    size_t pos = 0;
+    for (size_t i = 0; i < n; i++) {
+      const size_t len = ix.at(*order[first + i]).len;
+      std::fwrite(slab.data() + pos, 1, len, stdout);
+      std::fputc('\n', stdout);
+      pos += len;
+    }
+    first += n;
+  }
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
+  if (argc > 1 && std::string(argv[1]) == "reads") return reads_mode(argc, argv);
   if (argc < 6 || std::string(argv[1]) != "mappings") {
-    std::cerr << "usage: gp-host-check mappings <targets.fa> <targets.index> <mappings> <mx_max_per_10kbp> [threads]\n";
+    std::cerr << "usage: gp-host-check mappings <targets.fa> <targets.index> <mappings> <mx_max_per_10kbp> [threads]\n"
+                 "       gp-host-check reads <seqs> <seqs.index> <ids file> <slab bytes> [threads]\n";
     return 2;
   }
   const SeqIndex targets = SeqIndex::load(argv[3], argv[2]);

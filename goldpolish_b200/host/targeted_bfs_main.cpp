@@ -319,22 +319,17 @@ int main(int argc, char** argv)
     info("Uploading " + std::to_string(order.size()) + " mapped reads (" + std::to_string(total) + " bases) to " +
          std::to_string(devs.size()) + " device(s)");
     for (auto& d : devs) check_gp(d->ctx, gp_reads_begin(d->ctx, order.size(), lens.data()), "gp_reads_begin");
-    const size_t slab_bytes = 64u << 20;
-    std::string slab, one;
-    size_t in_slab = 0;
-    auto flush = [&] {
-      if (in_slab == 0) return;
-      for (auto& d : devs) check_gp(d->ctx, gp_reads_append(d->ctx, slab.data(), in_slab), "gp_reads_append");
-      slab.clear();
-      in_slab = 0;
-    };
-    for (const std::string* id : order) {
-      reads.read_seq(*id, one);
-      if (in_slab && slab.size() + one.size() > slab_bytes) flush();
-      slab += one;
-      in_slab++;
+    // slabs of ~64 MiB of consecutive reads, each read from the file by all host cores (SeqIndex::read_many)
+    const uint64_t slab_bytes = 64u << 20;
+    std::string slab;
+    for (size_t first = 0; first < order.size();) {
+      size_t n = 0;
+      uint64_t bytes = 0;
+      while (first + n < order.size() && (n == 0 || bytes + lens[first + n] <= slab_bytes)) bytes += lens[first + n++];
+      reads.read_many(order, first, n, slab);
+      for (auto& d : devs) check_gp(d->ctx, gp_reads_append(d->ctx, slab.data(), n), "gp_reads_append");
+      first += n;
     }
-    flush();
     for (auto& d : devs) check_gp(d->ctx, gp_reads_end(d->ctx), "gp_reads_end");
   }
 

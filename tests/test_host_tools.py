@@ -35,6 +35,27 @@ def test_index_tool_matches_reference_index():
             assert got == case["reads_index_sha256"], case["name"]
 
 
+def test_server_slab_reader_fetches_the_reads_the_index_names():
+    """SeqIndex::read_many (the server's slab reader: all host cores pread the reads of a slab into place) returns the
+    sequence line of every id, in the order asked, for FASTQ and FASTA, whatever the slab size and thread count --
+    what the reference's SeqIndex::get_seq<1> returns one read at a time (src/seqindex.hpp:59-102)."""
+    import sim
+    rng = np.random.default_rng(5)
+    for fastq in (1, 0):
+        with _tmp() as w:
+            d = sim.simulate(write_dir=w, genome_len=400000, coverage=12.0, seed=77, fastq=fastq)
+            reads = os.path.join(w, "reads.fq" if d.fastq else "reads.fa")
+            subprocess.check_call([os.path.join(BIN, "goldpolish-index"), reads, reads + ".idx"], env=ENV)
+            ids = rng.permutation(d.n_reads)[: d.n_reads // 2].tolist() + [3, 3, 0]      # scrambled, with repeats
+            with open(os.path.join(w, "ids"), "w") as f:
+                f.write("".join(d.read_name(i) + "\n" for i in ids))
+            want = b"".join(d.read(i) + b"\n" for i in ids)
+            for slab, threads in ((1, 1), (200000, 3), (5 << 20, 8), (64 << 20, 0)):
+                got = subprocess.check_output([os.path.join(BIN, "gp-host-check"), "reads", reads, reads + ".idx",
+                                               os.path.join(w, "ids"), str(slab), str(threads)], env=ENV)
+                assert got == want, (fastq, slab, threads)
+
+
 def _parse_bf(path):
     data = open(path, "rb").read()
     hdr_end = data.index(b"[HeaderEnd]\n")
