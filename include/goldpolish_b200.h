@@ -193,9 +193,11 @@ int gp_prep(gp_ctx* ctx, uint32_t n_records, const char* seqs, const uint64_t* o
  * persistent edit kernel -- launched behind the build kernel in the same stream with programmatic stream
  * serialization, so that it becomes resident beside it -- starts on each contig as soon as the nk filters of
  * its batch are final: the reference's per-batch order "BF server answers, then goldpolish-ntedit runs"
- * (scripts/goldpolish-polish-batch:62-105), kept per batch instead of per run.  Falls back to the two calls in
- * sequence when there is nothing to overlap (in-order build kernel, several waves, keep_counters) or when the
- * device turned out not to co-schedule the two kernels (the edit kernel's watchdog, checked after the first pass). */
+ * (scripts/goldpolish-polish-batch:62-105), kept per batch instead of per run.  The edit kernel runs on a few SMs of
+ * its own, which the build launch hands back (gp_stats.edit_sms; environment GP_EDIT_SMS=n fixes their number, 0 makes
+ * the two kernels share every SM).  Falls back to the two calls in sequence when there is nothing to overlap (in-order
+ * build kernel, keep_counters) or when the device turned out not to co-schedule the two kernels (the edit kernel's
+ * watchdog, checked after the first pass). */
 int gp_pipeline_run(gp_ctx* ctx);
 
 /* ---- flagged regions ---------------------------------------------------------------- */
