@@ -71,18 +71,29 @@ struct SlicedFile {
   size_t N = 0, T = 1;
   std::vector<size_t> cut; // slice t = [cut[t], cut[t + 1]); every slice starts at a line start
   int fd = -1;
+  bool mapped = false;
+  std::string owned;       // decoded bytes of a compressed input
 
-  SlicedFile(const std::string& path, unsigned threads)
+  // decode = true: a compressed or BAM file (by suffix) is decoded into memory first -- what btllib::DataSource does
+  // for the reference's mapping files (src/mappings.cpp:136-139): .gz through zlib, .bz2 / .xz / .zst / .zip through
+  // their tools, .bam through `samtools view -h`; a missing tool is an error, never a silently empty input
+  SlicedFile(const std::string& path, unsigned threads, bool decode = false)
   {
-    fd = open(path.c_str(), O_RDONLY);
-    if (fd < 0) die("cannot open " + path);
-    struct stat st;
-    if (fstat(fd, &st) != 0) die("cannot stat " + path);
-    N = size_t(st.st_size);
-    if (N) {
-      d = static_cast<const char*>(mmap(nullptr, N, PROT_READ, MAP_PRIVATE, fd, 0));
-      if (d == MAP_FAILED) die("cannot map " + path);
-      madvise(const_cast<char*>(d), N, MADV_SEQUENTIAL);
+    if (decode && decode_into(path, owned)) {
+      d = owned.data();
+      N = owned.size();
+    } else {
+      fd = open(path.c_str(), O_RDONLY);
+      if (fd < 0) die("cannot open " + path);
+      struct stat st;
+      if (fstat(fd, &st) != 0) die("cannot stat " + path);
+      N = size_t(st.st_size);
+      if (N) {
+        d = static_cast<const char*>(mmap(nullptr, N, PROT_READ, MAP_PRIVATE, fd, 0));
+        if (d == MAP_FAILED) die("cannot map " + path);
+        madvise(const_cast<char*>(d), N, MADV_SEQUENTIAL);
+        mapped = true;
+      }
     }
     T = std::max<size_t>(1, std::min<size_t>(host_threads(threads), N / (1u << 20) + 1));
     cut.assign(T + 1, N);
@@ -96,11 +107,46 @@ struct SlicedFile {
       cut[t] = std::min(pos, N);
     }
   }
+  // false: a plain file (map it).  true: `out` holds the decoded bytes.
+  static bool decode_into(const std::string& path, std::string& out)
+  {
+    if (endswith(path, ".gz")) {
+      gzFile g = gzopen(path.c_str(), "rb");
+      if (!g) die("cannot open " + path);
+      gzbuffer(g, 1u << 20);
+      std::vector<char> buf(4u << 20);
+      for (;;) {
+        const int n = gzread(g, buf.data(), unsigned(buf.size()));
+        if (n < 0) die("cannot decompress " + path);
+        if (n == 0) break;
+        out.append(buf.data(), size_t(n));
+      }
+      gzclose(g);
+      return true;
+    }
+    static const char* const tools[][2] = { { ".bam", "samtools view -h" }, { ".bz2", "bzip2 -dc" }, { ".xz", "xz -dc" },
+                                            { ".zst", "zstd -dc" }, { ".zip", "unzip -p" }, { ".lrz", "lrzip -dqo -" } };
+    for (const auto& t : tools) {
+      if (!endswith(path, t[0])) continue;
+      std::string quoted = "'";
+      for (const char c : path) quoted += c == '\'' ? std::string("'\\''") : std::string(1, c);
+      quoted += "'";
+      const std::string cmd = std::string(t[1]) + " " + quoted;
+      FILE* f = popen(cmd.c_str(), "r");
+      if (!f) die("cannot run: " + cmd);
+      std::vector<char> buf(4u << 20);
+      size_t n;
+      while ((n = std::fread(buf.data(), 1, buf.size(), f)) > 0) out.append(buf.data(), n);
+      if (pclose(f) != 0) die("failed: " + cmd + " (is the tool installed?)");
+      return true;
+    }
+    return false;
+  }
   SlicedFile(const SlicedFile&) = delete;
   SlicedFile& operator=(const SlicedFile&) = delete;
   ~SlicedFile()
   {
-    if (N) munmap(const_cast<char*>(d), N);
+    if (mapped) munmap(const_cast<char*>(d), N);
     if (fd >= 0) close(fd);
   }
   // fn(t) for every slice, one thread each
@@ -461,13 +507,9 @@ public:
   Mappings(const std::string& path, const SeqIndex& targets, unsigned mx_min, unsigned mx_max, double mx_max_per_10kbp,
            unsigned threads = 0)
   {
-    // The reference reads mappings through btllib::DataSource, which pipes .bam through samtools and compressed
-    // files through their decompressors (src/mappings.cpp:136-139); this reader takes plain text only, so those
-    // inputs are refused instead of being parsed as garbage.
-    for (const char* suf : { ".bam", ".gz", ".bz2", ".xz", ".zst", ".zip", ".lrz" })
-      if (endswith(path, suf)) die("mappings file " + path + ": binary/compressed mappings are not supported here; "
-                                   "convert first (e.g. `samtools view -h` / `zcat`) and pass the text file");
-    const int target_col = endswith(path, ".sam") ? 3 : endswith(path, ".paf") ? 6 : 0; // 0: ntLink triples
+    // (.bam reads as SAM through samtools, as btllib::DataSource pipes it; any other suffix -- "x.paf.gz" included,
+    // as in the reference -- is ntLink triples; compressed files are decoded first, see SlicedFile)
+    const int target_col = endswith(path, ".sam") || endswith(path, ".bam") ? 3 : endswith(path, ".paf") ? 6 : 0;
     if (target_col == 0) {
       if (mx_max_per_10kbp <= 0) die("max_mapped_seqs_per_target_10kbp is not positive.");
       if (mx_min >= mx_max) die("mx_threshold_min is not smaller than mx_threshold_max.");
@@ -531,7 +573,7 @@ private:
   void load(const std::string& path, const SeqIndex& targets, int target_col, unsigned mx_min, unsigned mx_max,
             double max_per_10kbp, unsigned threads)
   {
-    const SlicedFile f(path, threads);
+    const SlicedFile f(path, threads, true);
     const char* d = f.d;
     const size_t T = f.T;
     shards.assign(T, Map());

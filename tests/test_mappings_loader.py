@@ -124,3 +124,41 @@ def test_loader_matches_the_reference_mappings(tmp_path):
                 assert got == want, (name, threads)
             assert hashlib.sha256(got).hexdigest() == golden[name]["sha256"], (name, threads)
             assert got.count(b"\n") == golden[name]["targets"], name
+
+
+def test_compressed_and_bam_mappings_are_decoded(tmp_path):
+    """The reference reads its mapping file through btllib::DataSource, which decodes compressed files and pipes .bam
+    through `samtools view -h` (src/mappings.cpp:136-139); the format is still chosen by the FULL file name
+    (:21-33: "x.paf.gz" is ntLink triples).  Same here: .gz through zlib, .bz2 / .xz through their tools, .bam through
+    whatever `samtools` is on PATH (a stand-in script here); a missing tool is an error, not an empty mapping."""
+    import bz2
+    import gzip
+    import lzma
+    import stat
+    w = str(tmp_path)
+    cases = make_cases(w)
+    raw = open(os.path.join(w, "ragged.tsv"), "rb").read()
+    want = ours(w, "ragged.tsv", 60.0, 3)
+    for suffix, comp in ((".gz", gzip.compress), (".bz2", bz2.compress), (".xz", lzma.compress)):
+        with open(os.path.join(w, "ragged.tsv" + suffix), "wb") as f:
+            f.write(comp(raw))
+        assert ours(w, "ragged.tsv" + suffix, 60.0, 3) == want, suffix
+    # "m.paf.gz": ntLink triples by name, as in the reference -- not PAF
+    with open(os.path.join(w, "m.paf.gz"), "wb") as f:
+        f.write(gzip.compress(raw))
+    assert ours(w, "m.paf.gz", 60.0, 2) == want
+    # .bam: SAM text from `samtools view -h <file>`
+    sam_want = ours(w, "m.sam", 150.0, 2)
+    os.rename(os.path.join(w, "m.sam"), os.path.join(w, "m.bam"))       # (the stand-in just cats it)
+    bindir = os.path.join(w, "bin")
+    os.makedirs(bindir)
+    tool = os.path.join(bindir, "samtools")
+    with open(tool, "w") as f:
+        f.write('#!/bin/sh\n[ "$1" = view ] && [ "$2" = -h ] && exec cat "$3"\nexit 3\n')
+    os.chmod(tool, os.stat(tool).st_mode | stat.S_IEXEC)
+    env = dict(ENV, PATH=bindir + os.pathsep + os.environ.get("PATH", ""), GP_HOST_THREADS="2")
+    cmd = [os.path.join(BIN, "gp-host-check"), "mappings", os.path.join(w, "draft.fa"), os.path.join(w, "draft.fa.index"),
+           os.path.join(w, "m.bam"), "150", "2"]
+    assert subprocess.check_output(cmd, env=env) == sam_want
+    no_tool = subprocess.run(cmd, env=dict(ENV, PATH="/nonexistent"), capture_output=True)
+    assert no_tool.returncode != 0 and b"samtools" in no_tool.stderr
