@@ -93,10 +93,13 @@ def _streams(d, bsize, rnd):
     return reads, thrs
 
 
-@pytest.mark.parametrize("bsize,seed", [(1, 3), (1, 5), (4, 9)])
-def test_grouped_level_formulation_is_exact_and_touches_less(bsize, seed):
+@pytest.mark.parametrize("bsize,seed,mixed_thr", [(1, 3, False), (1, 5, False), (4, 9, False), (2, 11, True)])
+def test_grouped_level_formulation_is_exact_and_touches_less(bsize, seed, mixed_thr):
     d = dataset(genome_len=120000, seed=seed)
-    reads, thrs = _streams(d, bsize, np.random.default_rng(seed))
+    rnd = np.random.default_rng(seed)
+    reads, thrs = _streams(d, bsize, rnd)
+    if mixed_thr:  # members of one group with different thresholds (targets of a batch that differ in coverage)
+        thrs = [int(rnd.choice([4, 5, 6, 7])) for _ in reads]
     fs = ol.FilterSet(KS)
     for seq, T in zip(reads, thrs):
         fs.add_read(seq, T)
