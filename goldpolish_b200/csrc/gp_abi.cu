@@ -1267,11 +1267,11 @@ int gp_pipeline_run(gp_ctx* ctx)
   if (algo == 2)
     if (int rc = build_stream_tab(ctx, s, true)) return rc;
   if (int rc = polish_prepare(ctx)) return rc;
-  // Per wave: the build kernel (2 CTAs per SM when overlapped) signals `launch_dependents` as it starts; the edit
-  // kernel (persistent, one 3-warp CTA per SM) is launched behind it in the SAME stream with programmatic stream
-  // serialization, so it becomes resident next to the running build, takes the wave's contigs in build order and
-  // waits for each one's filters.  No event may sit between the two launches; their durations come from device
-  // timers.  The next wave's pool clear waits (stream order) for this wave's edit kernel.
+  // Per wave: the build kernel signals `launch_dependents` as it starts; the edit kernel (persistent) is launched behind
+  // it in the SAME stream with programmatic stream serialization, so it becomes resident while the build runs, takes
+  // the wave's contigs in build order and waits for each one's filters.  No event may sit between the two launches;
+  // their durations come from device timers.  The next wave's pool clear waits (stream order) for this wave's edit
+  // kernel.
   // How the two kernels share the GPU.  Default: the edit kernel gets SMs of its own -- the build launch fills every SM
   // (3 CTAs) and hands E of them back, the edit kernel's whole-SM CTAs land there (and on every SM once the build is
   // through).  E from the work staged: edit ~0.8 us of one warp per draft base and k chain when the warp has a
